@@ -1,0 +1,258 @@
+/*
+ * unav_b200.h — C ABI of the B200-native UnAV inference hot path.
+ *
+ * This header is the drop-in boundary: a plain-C interface (device pointers, sizes, a
+ * cudaStream_t passed as void*) with no torch types.  Python host code binds it with
+ * ctypes (unav_yolyolva_b200/_cabi.py); see INTEGRATION.md for the reference-side stubs.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *   unav_softnms_batched   libs/utils/csrc/nms_cpu.cpp:67-160 (softnms_1d_cpu), :172-182
+ *                          (pybind11 module nms_1d_cpu) and the per-class Python loop +
+ *                          final sort of libs/utils/nms.py:103-190 (batched_nms), plus the
+ *                          seconds conversion of libs/modeling/multimodal_meta_archs.py:852-856
+ *   unav_decode            libs/modeling/multimodal_meta_archs.py:745-817
+ *                          (PtTransformer.inference_single_video)
+ *   unav_gemm              every dense nn.Linear / nn.Conv1d(k=1) / im2col'd k=3 conv on the
+ *                          path (libs/modeling/blocks.py:36-61, :187-196, :296-302;
+ *                          multimodal_backbones.py:867-870, :929-932, :989-996, :1014-1034;
+ *                          multimodal_meta_archs.py:132-151, :214-242)
+ *   unav_layernorm_rows    libs/modeling/blocks.py:91-103 (channel LayerNorm) and the
+ *                          nn.LayerNorm(512) uses of multimodal_backbones.py:946-952,1011-1034
+ *   unav_dwconv_ln         depthwise MaskedConv1D + LayerNorm pairs: blocks.py:205-211
+ *                          (q/k/v convs of MaskedMHCA) and multimodal_backbones.py:44-48
+ *                          (Downsample_pyramid_levels)
+ *   unav_attention         blocks.py:218-240 (MaskedMHCA core) and
+ *                          multimodal_backbones.py:899-918 (MultiHeadAttention core with the
+ *                          fused mask of :1173-1183)
+ *   unav_maxsig_gate       multimodal_backbones.py:170-191 (MaxSigmoidAttnBlock weight)
+ *   unav_pool_match        multimodal_backbones.py:591-598 (avg-pool(4) x3 + match_projection)
+ *   unav_rowcopy           torch.cat / nn.Upsample(nearest) / im2col glue:
+ *                          multimodal_backbones.py:565-576, :609-610; meta_archs.py:469
+ *   unav_transpose_cast    the [B,C,T] <-> [B,T,C] transposes (multimodal_backbones.py:1145-1146,
+ *                          :1200-1201, :170)
+ *   unav_align_embed       multimodal_backbones.py:1157-1166 (CLS + pos + type embedding)
+ *   unav_build_masks       blocks.py:45-51 (mask[::s]) and multimodal_backbones.py:568-570
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - activations are token-major: a [nb, T, C] tensor is a row-major matrix of nb*T rows
+ *     ("rows" = time steps of consecutive videos) with leading dimension ld >= C in elements;
+ *   - "operand dtype" (op_dtype) is UNAV_F32 or UNAV_BF16 and names the element type of GEMM
+ *     operands (A, W, and out_op buffers); accumulation, residual stream, LayerNorm, softmax
+ *     and all detections are FP32;
+ *   - calls are asynchronous on `stream`, re-entrant per stream, own no memory (the caller
+ *     provides every buffer), and return 0 or a non-zero code: >0 = cudaError_t,
+ *     <0 = UNAV_ERR_*.  unav_last_error() returns a host string describing the last failure
+ *     of the calling thread.
+ */
+#ifndef UNAV_B200_H_
+#define UNAV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* UNAV_BF16X2: split BF16 pair, hi = bf16(x) at column c, lo = bf16(x - hi) at column ld/2 + c */
+enum { UNAV_F32 = 0, UNAV_BF16 = 1, UNAV_BF16X2 = 2 };
+enum { UNAV_ACT_NONE = 0, UNAV_ACT_RELU = 1, UNAV_ACT_GELU = 2, UNAV_ACT_SILU = 3 };
+enum { UNAV_GEMM_SIMT = 0, UNAV_GEMM_TCGEN05 = 1 };
+enum {
+  UNAV_ERR_BAD_ARG = -1,
+  UNAV_ERR_UNSUPPORTED = -2,
+  UNAV_ERR_NO_DEVICE = -3,
+  UNAV_ERR_DRIVER = -4
+};
+#define UNAV_MAX_GROUPS 8
+#define UNAV_MAX_COPY_JOBS 16
+
+/* ---- library / device ---------------------------------------------------------------- */
+const char* unav_version(void);
+const char* unav_last_error(void);
+/* 0 if device `dev` is an sm_100 part usable by this library. */
+int unav_check_device(int dev);
+/* number of kernel launches issued by this library in the calling process so far */
+long long unav_launch_count(void);
+
+/* ---- GEMM: C[M,N] = epilogue(A[M,K] . W[N,K]^T) ---------------------------------------- */
+/* Epilogue, per element (m, n), in this order:
+ *   v = acc + bias[n]; v *= rowmask[m]; v *= rowscale[m]; v *= gate[m*gate_groups + n/gate_width];
+ *   v = act(v); if res: v = res[m,n] * (res_masked ? rowmask[m] : 1) + colscale[n] * v
+ * (each factor skipped when its pointer is NULL; colscale NULL = 1).  v is stored to
+ * out_f32[m*ld_f32 + n] and/or, converted, to out_op[m*ld_op + n]. */
+typedef struct UnavGemmGroup {
+  const void* A;   long long lda;     /* [M,K] operand dtype */
+  const void* W;   long long ldw;     /* [N,K] operand dtype */
+  const float* bias;                  /* [N] */
+  const uint8_t* rowmask;             /* [M] */
+  const float* rowscale;              /* [M] */
+  const float* gate;                  /* [M, gate_groups] */
+  const float* res; long long ldres;  /* [M, >=N] */
+  const float* colscale;              /* [N] */
+  float* out_f32;  long long ld_f32;
+  void* out_op;    long long ld_op;
+  int gate_groups; int gate_width;
+} UnavGemmGroup;
+
+/* groups: host array of ngroups (<= UNAV_MAX_GROUPS) problems of identical M, N, K.
+ * backend UNAV_GEMM_TCGEN05 requires op_dtype == UNAV_BF16, 16-byte aligned A/W and
+ * lda, ldw multiples of 8 elements. */
+int unav_gemm(const UnavGemmGroup* groups, int ngroups, int M, int N, int K,
+              int op_dtype, int act, int res_masked, int backend, void* stream);
+
+/* ---- row LayerNorm (+pre-add, +activation, +position table, +im2col scatter) ----------- */
+/* For output row r (0 <= r < M):
+ *   src = x_seg_rows ? (r / x_seg_rows) * x_seg_stride + r % x_seg_rows + x_row_off : r
+ *   u = x[src, :] (+ add[r, :]);  y = (u - mean) / sqrt(var + eps) * w + b;  y = act(y)
+ *   if post: y += post[r % post_rows, :] * (rowmask ? rowmask[r] : 1)
+ * y goes to out_f32 (ld_f32), out_op (ld_op) and/or, as a k=3 im2col scatter, to out_im2col:
+ *   out_im2col[r, C + c] = y[c];  out_im2col[r+1, c] = y[c] unless edge[r]&2;
+ *   out_im2col[r-1, 2C + c] = y[c] unless edge[r]&1; rows with edge bit0 (first of a video
+ *   segment) zero their own tap-0 block, rows with bit1 (last) zero their tap-2 block. */
+typedef struct UnavLnGroup {
+  const float* x;   long long ldx;
+  const float* add; long long ldadd;
+  const float* w;   const float* b;          /* [C] */
+  const float* post;                         /* [post_rows, C] or NULL */
+  const uint8_t* rowmask;                    /* [M] or NULL */
+  const uint8_t* edge;                       /* [M], needed with out_im2col */
+  float* out_f32;     long long ld_f32;
+  void* out_op;       long long ld_op;
+  void* out_im2col;   long long ld_im2col;
+  int x_seg_rows, x_seg_stride, x_row_off, post_rows;
+} UnavLnGroup;
+
+int unav_layernorm_rows(const UnavLnGroup* groups, int ngroups, int M, int C, float eps,
+                        int act, int op_dtype, void* stream);
+
+/* ---- depthwise k=3 conv (stride 1|2, zero pad 1) * mask -> LayerNorm, up to 3 outputs --- */
+/* Input x: nseg segments of seg_len_in rows.  Optional pre-LayerNorms (n_pre <= 2) are applied
+ * to the input rows first (TransformerBlock ln11/ln12, blocks.py:314).  Output j (< n_out):
+ *   z[t, c] = sum_tap dw_j[c, tap] * pre_{src_j}(x)[stride*t + tap - 1, c]   (0 outside the segment)
+ *   z *= mask_out[seg*seg_len_out + t];  y = LN_j(z)  -> out_f32_j / out_op_j                      */
+typedef struct UnavDwLnOut {
+  const float* dw;                           /* [C,3] */
+  const float* ln_w; const float* ln_b;      /* [C] */
+  float* out_f32; long long ld_f32;
+  void* out_op;   long long ld_op;
+  int src;                                   /* -1 raw x, 0|1 pre-LN index */
+  int pad_;
+} UnavDwLnOut;
+
+typedef struct UnavDwLnGroup {
+  const float* x; long long ldx;
+  const uint8_t* mask_out;                   /* [nseg*seg_len_out] */
+  const float* pre_w[2]; const float* pre_b[2];
+  UnavDwLnOut out[3];
+} UnavDwLnGroup;
+
+int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg, int seg_len_in,
+                   int stride, int C, int n_pre, int n_out, float eps, int op_dtype,
+                   void* stream);
+
+/* ---- fused masked attention core --------------------------------------------------------- */
+/* For batch b < nb, head h < nh, query i < Tq:
+ *   s_j = scale * <q[b,i,h,:], k[b,j,h,:]>  over keys j < Tk with kmask[b*Tk+j] != 0,
+ *   plus, when xk != NULL and i >= x_first, one extra key/value row xk/xv[b*Tq + i] (always
+ *   allowed: the time-aligned token of the other modality, multimodal_backbones.py:1179-1183);
+ *   p = softmax(s);  out[b,i,h,:] = sum_j p_j * v[b,j,h,:].
+ * q/k/v rows are FP32 with head h at columns [h*hs, (h+1)*hs); out has operand dtype. */
+typedef struct UnavAttnGroup {
+  const float* q; long long ldq;
+  const float* k; long long ldk;
+  const float* v; long long ldv;
+  const uint8_t* kmask;
+  const float* xk; const float* xv; long long ldx;
+  void* out; long long ldo;
+  int x_first; int pad_;
+} UnavAttnGroup;
+
+int unav_attention(const UnavAttnGroup* groups, int ngroups, int nb, int Tq, int Tk,
+                   int nh, int hs, float scale, int op_dtype, void* stream);
+
+/* ---- MaxSigmoid gate ----------------------------------------------------------------------- */
+/* gate[r, h] = sigmoid( max_{n<nwords} <x[r, h*hc:(h+1)*hc], G[(r/T)*nwords + n, h*hc:...]> / sqrt(hc)
+ *                       + head_bias[h] ),   r < nb*T, h < H.  x, G FP32. */
+int unav_maxsig_gate(const float* x, long long ldx, const float* G, long long ldg,
+                     const float* head_bias, float* gate, int nb, int T, int nwords, int H,
+                     int hc, void* stream);
+
+/* ---- AdaptiveAvgPool1d(P) of 3 levels + Conv1d(3P -> Tq, k=1) along the pooled axis ------- */
+/* q[b*Tq + t, c] = bm[t] + sum_{l<3, p<P} Wm[t, l*P + p] * mean_{s in bin p of level l} u_l[b*T_l + s, c] */
+int unav_pool_match(const float* u0, const float* u1, const float* u2, int T0, int T1, int T2,
+                    long long ldu, const float* Wm, const float* bm, float* q, long long ldq,
+                    int nb, int C, int Tq, int P, void* stream);
+
+/* ---- row gather / nearest up-sample / k=3 im2col / concat into operand buffers ------------ */
+/* dst[(seg*dst_seg_stride + dst_row_off + t), tap*tap_stride + c] =
+ *     src[seg*seg_len_in + (t*num)/den + tap - ntaps/2, c]   (0 if outside [0, seg_len_in))
+ * for seg < nseg, t < seg_len_out, tap < ntaps, c < C.  dst has operand dtype (or FP32 when
+ * dst_f32 != 0). */
+typedef struct UnavCopyJob {
+  const float* src; long long ld_src;
+  void* dst;        long long ld_dst;
+  int nseg, seg_len_in, seg_len_out, dst_seg_stride, dst_row_off;
+  int num, den, ntaps, tap_stride, C;
+} UnavCopyJob;
+
+int unav_rowcopy(const UnavCopyJob* jobs, int njobs, int op_dtype, void* stream);
+
+/* in [nb, R, Cc] FP32 (row stride ld_in) -> out [nb, Cc, R] operand dtype (row stride ld_out) */
+int unav_transpose_cast(const float* in, long long ld_in, void* out, long long ld_out,
+                        int nb, int R, int Cc, int op_dtype, void* stream);
+
+/* tokens[m][b][0,:] = cls_m + pos_m[0] + type_m; tokens[m][b][1+t,:] = x0[m][b][t,:] + pos_m[1+t] + type_m
+ * for m in {0: video, 1: audio}; x0 is [2, nb, T, C], tokens [2, nb, T+1, C]. */
+int unav_align_embed(const float* x0, const float* cls_v, const float* cls_a,
+                     const float* pos_v, const float* pos_a, const float* type_v,
+                     const float* type_a, float* tokens, int nb, int T, int C, void* stream);
+
+/* Pyramid masks from the level-0 mask [nb, T]:  out_true[l][b][t] = mask[b][t << l]  (blocks.py:45-51),
+ * out_up[l][b][t] = out_true[l+1][b][t >> 1]  (multimodal_backbones.py:568-570), both concatenated
+ * over levels (level l starts at row offset nb * sum_{j<l} (T >> j)); out_up has L-1 levels. */
+int unav_build_masks(const uint8_t* mask, uint8_t* out_true, uint8_t* out_up, int nb, int T,
+                     int L, void* stream);
+
+/* ---- decode ---------------------------------------------------------------------------------- */
+/* logits [B, Ttot, ncls], offsets [B, Ttot, ncls, 2] (class_aware) or [B, Ttot, 2], masks [B, Ttot],
+ * points [Ttot, 4] = (t, reg_lo, reg_hi, stride); level l covers rows [level_off[l], level_off[l+1])
+ * (host array, L+1 entries).  Per (video, level): p = sigmoid(logit)*mask; keep p > pre_nms_thresh;
+ * keep the pre_nms_topk largest (ties: lower flat index); segment = (t - off0*stride, t + off1*stride);
+ * keep right-left > duration_thresh.  Candidates of video b land in slots
+ * [b*cap + cap_off[l], ...) in flat-index order; unused slots get label -1.
+ * cap must be >= sum_l min(pre_nms_topk, rows_l*ncls). */
+int unav_decode(const float* logits, const float* offsets, const uint8_t* masks,
+                const float* points, const int* level_off, int B, int L, int ncls,
+                int class_aware, float pre_nms_thresh, int pre_nms_topk, float duration_thresh,
+                float* cand_segs, float* cand_scores, int32_t* cand_labels, int cap,
+                void* stream);
+
+/* ---- per-class temporal soft-NMS + per-video merge ------------------------------------------ */
+/* Candidates: cand_segs [B, cap, 2], cand_scores [B, cap], cand_labels [B, cap] (int32, -1 = empty).
+ * method: 0 hard (weight 0 if IoU >= iou_threshold), 1 linear, 2 gaussian exp(-IoU^2/sigma)
+ * (nms_cpu.cpp:126-141); 3 = the NMSop path (nms.py:8-35 -> nms_cpu.cpp:19-58): pre-filter
+ * score > min_score, greedy suppression at IoU >= iou_threshold, scores unchanged.
+ * max_per_class: upper bound on candidates of one class in one video (0 = cap); the model path
+ * passes sum_l T_l because every (point, class) yields at most one candidate.  Per class: repeatedly take the highest-scoring live candidate (ties:
+ * lowest slot), emit it, decay the others, drop those below min_score; at most max_seg_num per
+ * class.  Then the per-class lists are merged by score (ties: lower class, earlier emission) and
+ * the best max_seg_num kept.  If vid_meta != NULL ([B,4] = feat_stride, feat_num_frames, fps,
+ * duration) segments are converted to seconds and clamped (multimodal_meta_archs.py:852-856).
+ * Outputs: out_segs [B, max_seg_num, 2], out_scores [B, max_seg_num], out_labels [B, max_seg_num]
+ * (int64), out_counts [B] (int32); rows beyond the count are zero.
+ * workspace: at least unav_softnms_workspace_bytes(B, ncls, max_seg_num) bytes. */
+size_t unav_softnms_workspace_bytes(int B, int ncls, int max_seg_num);
+int unav_softnms_batched(const float* cand_segs, const float* cand_scores,
+                         const int32_t* cand_labels, int B, int cap, int ncls,
+                         float iou_threshold, float sigma, float min_score, int method,
+                         int max_seg_num, int max_per_class, const float* vid_meta,
+                         float* out_segs,
+                         float* out_scores, int64_t* out_labels, int32_t* out_counts,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNAV_B200_H_ */

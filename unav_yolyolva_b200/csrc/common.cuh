@@ -1,0 +1,161 @@
+// common.cuh — shared device/host helpers for the UnAV B200 hot-path kernels.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/unav_b200.h"
+
+// Operand formats.  UNAV_F32 / UNAV_BF16 are public; BF16X2 is the split format used for the
+// FP32-accurate tensor-core mode: a row holds hi = bf16(x) in its first half and
+// lo = bf16(x - hi) at column offset ld/2, so A.W^T ~ Ahi.Whi + Alo.Whi + Ahi.Wlo (3 MMA passes).
+
+namespace unav {
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int finish_launch(const char* what);  // cudaGetLastError -> code, records message
+
+#define UNAV_REQUIRE(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::unav::set_error(__VA_ARGS__);      \
+      return UNAV_ERR_BAD_ARG;             \
+    }                                      \
+  } while (0)
+
+// ---- small device helpers ---------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float silu_(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case UNAV_ACT_RELU: return fmaxf(v, 0.0f);
+    case UNAV_ACT_GELU: return gelu_erf(v);
+    case UNAV_ACT_SILU: return silu_(v);
+    default: return v;
+  }
+}
+
+// Store one value into an operand buffer row (`p` points at the row start, `c` is the column).
+// split_off = ld/2 for BF16X2.
+__device__ __forceinline__ void store_op(void* row, int op_dtype, long long c, long long split_off,
+                                         float v) {
+  if (op_dtype == UNAV_F32) {
+    reinterpret_cast<float*>(row)[c] = v;
+  } else {
+    __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    reinterpret_cast<__nv_bfloat16*>(row)[c] = hi;
+    if (op_dtype == UNAV_BF16X2) {
+      float lo = v - __bfloat162float(hi);
+      reinterpret_cast<__nv_bfloat16*>(row)[split_off + c] = __float2bfloat16_rn(lo);
+    }
+  }
+}
+
+// 4 consecutive columns (c % 4 == 0, buffers 16-byte aligned, ld % 8 == 0).
+__device__ __forceinline__ void store_op4(void* row, int op_dtype, long long c, long long split_off,
+                                          float4 v) {
+  if (op_dtype == UNAV_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(row) + c) = v;
+  } else {
+    __nv_bfloat16* r = reinterpret_cast<__nv_bfloat16*>(row);
+    __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 h23 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h01);
+    pk.y = *reinterpret_cast<uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(r + c) = pk;
+    if (op_dtype == UNAV_BF16X2) {
+      float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+      __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+      __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+      pk.x = *reinterpret_cast<uint32_t*>(&l01);
+      pk.y = *reinterpret_cast<uint32_t*>(&l23);
+      *reinterpret_cast<uint2*>(r + split_off + c) = pk;
+    }
+  }
+}
+
+__host__ __device__ __forceinline__ size_t op_elem_size(int op_dtype) {
+  return op_dtype == UNAV_F32 ? 4 : 2;
+}
+
+// Load an operand element as float (SIMT GEMM path). For BF16X2 returns hi + lo.
+__device__ __forceinline__ float load_op(const void* row, int op_dtype, long long c,
+                                         long long split_off) {
+  if (op_dtype == UNAV_F32) return reinterpret_cast<const float*>(row)[c];
+  const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(row);
+  float v = __bfloat162float(r[c]);
+  if (op_dtype == UNAV_BF16X2) v += __bfloat162float(r[split_off + c]);
+  return v;
+}
+
+// ---- shared GEMM epilogue ---------------------------------------------------------------
+struct EpiParams {
+  const float* bias;
+  const uint8_t* rowmask;
+  const float* rowscale;
+  const float* gate;
+  const float* res;
+  const float* colscale;
+  float* out_f32;
+  void* out_op;
+  long long ldres, ld_f32, ld_op;
+  int gate_groups, gate_width;
+};
+
+__device__ __forceinline__ float epilogue_value(const EpiParams& e, int act, int res_masked,
+                                                long long m, int n, float acc) {
+  float v = acc;
+  if (e.bias) v += __ldg(e.bias + n);
+  float mk = 1.0f;
+  if (e.rowmask) {
+    mk = e.rowmask[m] ? 1.0f : 0.0f;
+    v *= mk;
+  }
+  if (e.rowscale) v *= __ldg(e.rowscale + m);
+  if (e.gate) v *= __ldg(e.gate + m * e.gate_groups + n / e.gate_width);
+  v = apply_act(v, act);
+  if (e.res) {
+    float r = e.res[m * e.ldres + n];
+    if (res_masked) r *= mk;
+    float cs = e.colscale ? __ldg(e.colscale + n) : 1.0f;
+    v = r + cs * v;
+  }
+  return v;
+}
+
+static inline EpiParams make_epi(const UnavGemmGroup& g) {
+  EpiParams e;
+  e.bias = g.bias; e.rowmask = g.rowmask; e.rowscale = g.rowscale; e.gate = g.gate;
+  e.res = g.res; e.colscale = g.colscale; e.out_f32 = g.out_f32; e.out_op = g.out_op;
+  e.ldres = g.ldres; e.ld_f32 = g.ld_f32; e.ld_op = g.ld_op;
+  e.gate_groups = g.gate_groups > 0 ? g.gate_groups : 1;
+  e.gate_width = g.gate_width > 0 ? g.gate_width : 1;
+  return e;
+}
+
+// tcgen05 backend entry (gemm_tcgen05.cu)
+int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, int op_dtype,
+                 int act, int res_masked, cudaStream_t stream);
+
+}  // namespace unav

@@ -1,0 +1,491 @@
+// decode_nms.cu — candidate decoding and per-class temporal soft-NMS, device resident.
+//
+// Replaces the reference's per-video / per-level Python decode loop
+// (libs/modeling/multimodal_meta_archs.py:745-817), the per-class Python loop + CPU extension of
+// libs/utils/nms.py:103-190 / libs/utils/csrc/nms_cpu.cpp:67-160 and the seconds conversion
+// (multimodal_meta_archs.py:852-856).  Integer / compare work is bit-exact w.r.t. the reference:
+//   * top-k selection is a radix select on the score bits (ties: lower flat index),
+//   * IoU / decay arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction),
+//   * the gaussian weight uses glibc's expf algorithm (exp2f_data table, double arithmetic), which
+//     reproduces libm bit-for-bit on [-1/sigma, 0].
+#include "common.cuh"
+
+namespace unav {
+
+// =============================================================================================
+// decode
+// =============================================================================================
+constexpr int DEC_THREADS = 512;
+
+struct DecodeParams {
+  const float* logits; const float* offsets; const uint8_t* masks; const float* points;
+  float* cand_segs; float* cand_scores; int32_t* cand_labels;
+  int level_off[9];     // rows
+  int cap_off[9];       // candidate slots
+  int B, L, ncls, class_aware, topk, cap, Ttot;
+  float thresh, dur_thresh;
+};
+
+__device__ __forceinline__ float decode_prob(const DecodeParams& p, int b, int row0, int i) {
+  const int row = row0 + i / p.ncls;
+  const long long r = static_cast<long long>(b) * p.Ttot + row;
+  const float m = p.masks[r] ? 1.f : 0.f;
+  return sigmoidf_(p.logits[r * p.ncls + (i % p.ncls)]) * m;
+}
+
+// block-wide exclusive scan of a 0/1 flag in index order; returns this thread's offset, total in *total
+__device__ __forceinline__ int block_scan_flag(bool flag, int* warp_tot, int* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int within = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) warp_tot[w] = __popc(bal);
+  __syncthreads();
+  int base = 0, tot = 0;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) {
+    const int c = warp_tot[i];
+    if (i < w) base += c;
+    tot += c;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + within;
+}
+
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_kernel(const __grid_constant__ DecodeParams p) {
+  __shared__ int hist[256];
+  __shared__ int warp_tot[DEC_THREADS / 32];
+  __shared__ unsigned s_prefix;
+  __shared__ int s_need, s_count;
+  const int l = blockIdx.x, b = blockIdx.y;
+  const int row0 = p.level_off[l];
+  const int n = (p.level_off[l + 1] - row0) * p.ncls;
+  const int slot0 = p.cap_off[l], nslots = p.cap_off[l + 1] - p.cap_off[l];
+  const int tid = threadIdx.x;
+
+  // ---- count candidates above the threshold
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  int cnt = 0;
+  for (int i = tid; i < n; i += DEC_THREADS) cnt += decode_prob(p, b, row0, i) > p.thresh;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((tid & 31) == 0 && cnt) atomicAdd(&s_count, cnt);
+  __syncthreads();
+  const int count = s_count;
+
+  // ---- radix select of the topk-th largest score (only when more than topk pass the threshold)
+  unsigned vstar = 0;       // key of the k-th largest; everything strictly above is taken
+  int need_eq = 0x7fffffff; // how many elements with key == vstar are taken (index order)
+  if (count > p.topk) {
+    if (tid == 0) { s_prefix = 0; s_need = p.topk; }
+    for (int pass = 0; pass < 4; ++pass) {
+      for (int i = tid; i < 256; i += DEC_THREADS) hist[i] = 0;
+      __syncthreads();
+      const unsigned prefix = s_prefix;
+      const int shift = 24 - 8 * pass;
+      for (int i = tid; i < n; i += DEC_THREADS) {
+        const float pr = decode_prob(p, b, row0, i);
+        if (pr > p.thresh) {
+          const unsigned key = __float_as_uint(pr);
+          if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int need = s_need, bin = 255;
+        for (; bin > 0; --bin) {
+          if (hist[bin] >= need) break;
+          need -= hist[bin];
+        }
+        s_need = need;
+        s_prefix = (prefix << 8) | static_cast<unsigned>(bin);
+      }
+      __syncthreads();
+    }
+    vstar = s_prefix;
+    need_eq = s_need;
+  }
+
+  // ---- emit in flat-index order
+  int eq_seen = 0, out_pos = 0;
+  for (int i0 = 0; i0 < n; i0 += DEC_THREADS) {
+    const int i = i0 + tid;
+    float pr = 0.f;
+    bool above = false, eq = false;
+    if (i < n) {
+      pr = decode_prob(p, b, row0, i);
+      if (pr > p.thresh) {
+        const unsigned key = __float_as_uint(pr);
+        above = (count <= p.topk) || key > vstar;
+        eq = (count > p.topk) && key == vstar;
+      }
+    }
+    int eq_tot;
+    const int eq_rank = block_scan_flag(eq, warp_tot, &eq_tot);
+    const bool sel = above || (eq && (eq_seen + eq_rank) < need_eq);
+    eq_seen += eq_tot;
+    float left = 0.f, right = 0.f;
+    bool keep = false;
+    int cls = 0;
+    if (sel) {
+      const int row = row0 + i / p.ncls;
+      cls = i % p.ncls;
+      const long long r = static_cast<long long>(b) * p.Ttot + row;
+      const float* off = p.class_aware ? p.offsets + (r * p.ncls + cls) * 2 : p.offsets + r * 2;
+      const float t = p.points[row * 4 + 0], st = p.points[row * 4 + 3];
+      left = __fsub_rn(t, __fmul_rn(off[0], st));
+      right = __fadd_rn(t, __fmul_rn(off[1], st));
+      keep = __fsub_rn(right, left) > p.dur_thresh;
+    }
+    int keep_tot;
+    const int pos = block_scan_flag(keep, warp_tot, &keep_tot);
+    if (keep) {
+      const long long s = static_cast<long long>(b) * p.cap + slot0 + out_pos + pos;
+      p.cand_segs[s * 2 + 0] = left;
+      p.cand_segs[s * 2 + 1] = right;
+      p.cand_scores[s] = pr;
+      p.cand_labels[s] = cls;
+    }
+    out_pos += keep_tot;
+  }
+  // ---- mark unused slots of this (video, level) region
+  for (int s = out_pos + tid; s < nslots; s += DEC_THREADS) {
+    const long long g = static_cast<long long>(b) * p.cap + slot0 + s;
+    p.cand_labels[g] = -1;
+    p.cand_scores[g] = 0.f;
+    p.cand_segs[g * 2] = 0.f;
+    p.cand_segs[g * 2 + 1] = 0.f;
+  }
+}
+
+// =============================================================================================
+// soft-NMS
+// =============================================================================================
+__constant__ unsigned long long kExp2fTab[32] = {
+    0x3ff0000000000000ULL, 0x3fefd9b0d3158574ULL, 0x3fefb5586cf9890fULL, 0x3fef9301d0125b51ULL,
+    0x3fef72b83c7d517bULL, 0x3fef54873168b9aaULL, 0x3fef387a6e756238ULL, 0x3fef1e9df51fdee1ULL,
+    0x3fef06fe0a31b715ULL, 0x3feef1a7373aa9cbULL, 0x3feedea64c123422ULL, 0x3feece086061892dULL,
+    0x3feebfdad5362a27ULL, 0x3feeb42b569d4f82ULL, 0x3feeab07dd485429ULL, 0x3feea47eb03a5585ULL,
+    0x3feea09e667f3bcdULL, 0x3fee9f75e8ec5f74ULL, 0x3feea11473eb0187ULL, 0x3feea589994cce13ULL,
+    0x3feeace5422aa0dbULL, 0x3feeb737b0cdc5e5ULL, 0x3feec49182a3f090ULL, 0x3feed503b23e255dULL,
+    0x3feee89f995ad3adULL, 0x3feeff76f2fb5e47ULL, 0x3fef199bdd85529cULL, 0x3fef3720dcef9069ULL,
+    0x3fef5818dcfba487ULL, 0x3fef7c97337b9b5fULL, 0x3fefa4afa2a490daULL, 0x3fefd0765b6e4540ULL};
+
+// glibc expf (sysdeps/ieee754/flt-32/e_expf.c, EXP2F_TABLE_BITS = 5) for |x| small enough that no
+// overflow/underflow path is taken (here x in [-1/sigma, 0]).  Double arithmetic, explicit rounding.
+__device__ __forceinline__ float expf_glibc(float x) {
+  const double InvLn2N = 0x1.71547652b82fep+0 * 32.0;
+  const double Shift = 0x1.8p+52;
+  const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0;
+  const double C1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0;
+  const double C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
+  const double xd = static_cast<double>(x);
+  const double z = __dmul_rn(InvLn2N, xd);
+  double kd = __dadd_rn(z, Shift);
+  const unsigned long long ki = static_cast<unsigned long long>(__double_as_longlong(kd));
+  kd = __dsub_rn(kd, Shift);
+  const double r = __dsub_rn(z, kd);
+  unsigned long long t = kExp2fTab[ki & 31ULL];
+  t += ki << (52 - 5);
+  const double s = __longlong_as_double(static_cast<long long>(t));
+  const double zz = __dadd_rn(__dmul_rn(C0, r), C1);
+  const double r2 = __dmul_rn(r, r);
+  double y = __dadd_rn(__dmul_rn(C2, r), 1.0);
+  y = __dadd_rn(__dmul_rn(zz, r2), y);
+  y = __dmul_rn(y, s);
+  return static_cast<float>(y);
+}
+
+struct NmsParams {
+  const float* cand_segs; const float* cand_scores; const int32_t* cand_labels;
+  float* ws_dets;      // [B, ncls, max_seg, 3]
+  int32_t* ws_counts;  // [B, ncls]
+  int B, cap, ncls, method, max_seg, maxn;
+  float iou_thr, sigma, min_score;
+};
+
+// One block per (class, video).  Candidates of the class are gathered in slot order into shared memory;
+// each round takes the best live one (ties: lowest slot), emits it and decays the rest.
+__global__ void softnms_kernel(const __grid_constant__ NmsParams p) {
+  extern __shared__ __align__(16) uint8_t nms_smem[];
+  float* x1 = reinterpret_cast<float*>(nms_smem);
+  float* x2 = x1 + p.maxn;
+  float* ar = x2 + p.maxn;
+  float* sc = ar + p.maxn;
+  __shared__ int s_n;
+  __shared__ float red_s[8];
+  __shared__ int red_i[8];
+  __shared__ int s_win;
+  const int c = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+  // ---- gather (warp 0, ordered)
+  if (warp == 0) {
+    int n = 0;
+    const long long base = static_cast<long long>(b) * p.cap;
+    for (int s0 = 0; s0 < p.cap; s0 += 32) {
+      const int s = s0 + lane;
+      bool hit = s < p.cap && p.cand_labels[base + s] == c;
+      float sv = 0.f;
+      if (hit) {
+        sv = p.cand_scores[base + s];
+        if (p.method == 3 && !(sv > p.min_score)) hit = false;   // NMSop pre-filter (nms.py:15-19)
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      const int pos = n + __popc(bal & ((1u << lane) - 1u));
+      if (hit && pos < p.maxn) {
+        const float a = p.cand_segs[(base + s) * 2], e = p.cand_segs[(base + s) * 2 + 1];
+        x1[pos] = a; x2[pos] = e;
+        ar[pos] = __fadd_rn(__fsub_rn(e, a), 1e-6f);
+        sc[pos] = sv;
+      }
+      n += __popc(bal);
+    }
+    if (lane == 0) s_n = n < p.maxn ? n : p.maxn;
+  }
+  __syncthreads();
+  const int n = s_n;
+  float* dets = p.ws_dets + (static_cast<long long>(b) * p.ncls + c) * p.max_seg * 3;
+  int emitted = 0;
+  const int rounds = n < p.max_seg ? n : p.max_seg;
+  for (int r = 0; r < rounds; ++r) {
+    // ---- argmax over live candidates
+    float bs = -CUDART_INF_F;     // dead candidates carry -inf
+    int bi = 0x7fffffff;
+    for (int j = tid; j < n; j += blockDim.x) {
+      const float s = sc[j];
+      if (s > bs) { bs = s; bi = j; }       // strict > keeps the lowest index within a thread's stride order
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+    }
+    if (nwarps > 1) {
+      if (lane == 0) { red_s[warp] = bs; red_i[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < nwarps; ++w)
+          if (red_s[w] > bs || (red_s[w] == bs && red_i[w] < bi)) { bs = red_s[w]; bi = red_i[w]; }
+        s_win = bi;
+      }
+      __syncthreads();
+      bi = s_win;
+    }
+    if (bi == 0x7fffffff) break;
+    const float ix1 = x1[bi], ix2 = x2[bi], ia = ar[bi], is = sc[bi];
+    if (nwarps > 1) __syncthreads();   // everyone has read the winner before it is retired
+    else __syncwarp();
+    if (tid == 0) {
+      dets[r * 3 + 0] = ix1; dets[r * 3 + 1] = ix2; dets[r * 3 + 2] = is;
+      sc[bi] = -CUDART_INF_F;
+    }
+    emitted = r + 1;
+    // ---- decay the others
+    for (int j = tid; j < n; j += blockDim.x) {
+      if (j == bi) continue;
+      float s = sc[j];
+      if (s == -CUDART_INF_F) continue;
+      const float xx1 = fmaxf(ix1, x1[j]);
+      const float xx2 = fminf(ix2, x2[j]);
+      const float inter = fmaxf(0.f, __fsub_rn(xx2, xx1));
+      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ia, ar[j]), inter));
+      float w = 1.f;
+      if (p.method == 0 || p.method == 3) { if (ovr >= p.iou_thr) w = 0.f; }
+      else if (p.method == 1) { if (ovr >= p.iou_thr) w = __fsub_rn(1.f, ovr); }
+      else w = expf_glibc(__fdiv_rn(-__fmul_rn(ovr, ovr), p.sigma));
+      s = __fmul_rn(s, w);
+      if (p.method == 3) { if (w == 0.f) s = -CUDART_INF_F; }   // hard NMS: suppressed, scores otherwise untouched
+      else if (s < p.min_score) s = -CUDART_INF_F;
+      sc[j] = s;
+    }
+    if (nwarps > 1) __syncthreads();
+    else __syncwarp();
+  }
+  if (tid == 0) p.ws_counts[b * p.ncls + c] = emitted;
+}
+
+// =============================================================================================
+// per-video merge of the (sorted) per-class lists + seconds conversion
+// =============================================================================================
+struct MergeParams {
+  const float* ws_dets; const int32_t* ws_counts; const float* vid_meta;
+  float* out_segs; float* out_scores; int64_t* out_labels; int32_t* out_counts;
+  int ncls, max_seg;
+};
+
+__global__ void __launch_bounds__(256)
+merge_kernel(const __grid_constant__ MergeParams p) {
+  __shared__ float red_s[8];
+  __shared__ int red_c[8];
+  __shared__ int s_win;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  // thread t owns classes t, t + blockDim, ...  (ncls <= 4 * blockDim supported through the loop below)
+  constexpr int OWN = 4;
+  int head[OWN], cnt[OWN];
+#pragma unroll
+  for (int o = 0; o < OWN; ++o) {
+    const int c = tid + o * blockDim.x;
+    head[o] = 0;
+    cnt[o] = c < p.ncls ? p.ws_counts[b * p.ncls + c] : 0;
+  }
+  float stride = 1.f, half = 0.f, fps = 1.f, dur = 0.f;
+  if (p.vid_meta) {
+    stride = p.vid_meta[b * 4 + 0];
+    half = 0.5f * p.vid_meta[b * 4 + 1];
+    fps = p.vid_meta[b * 4 + 2];
+    dur = p.vid_meta[b * 4 + 3];
+  }
+  int produced = 0;
+  for (int r = 0; r < p.max_seg; ++r) {
+    float bs = -1.f;
+    int bc = 0x7fffffff;
+#pragma unroll
+    for (int o = 0; o < OWN; ++o) {
+      const int c = tid + o * blockDim.x;
+      if (head[o] < cnt[o]) {
+        const float s = p.ws_dets[((static_cast<long long>(b) * p.ncls + c) * p.max_seg + head[o]) * 3 + 2];
+        if (s > bs || (s == bs && c < bc)) { bs = s; bc = c; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (os > bs || (os == bs && oc < bc)) { bs = os; bc = oc; }
+    }
+    if (lane == 0) { red_s[warp] = bs; red_c[warp] = bc; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < nwarps; ++w)
+        if (red_s[w] > bs || (red_s[w] == bs && red_c[w] < bc)) { bs = red_s[w]; bc = red_c[w]; }
+      s_win = bc;
+    }
+    __syncthreads();
+    const int win = s_win;
+    if (win == 0x7fffffff) break;
+    const int o = win / blockDim.x;
+    if (static_cast<int>(win % blockDim.x) == tid) {
+      int hd = 0;
+#pragma unroll
+      for (int k = 0; k < OWN; ++k) if (k == o) { hd = head[k]; head[k]++; }
+      const float* d = p.ws_dets + ((static_cast<long long>(b) * p.ncls + win) * p.max_seg + hd) * 3;
+      float s0 = d[0], s1 = d[1];
+      if (p.vid_meta) {
+        // (segs * stride + 0.5 * nframes) / fps, then clamp to [0, duration] the way the reference does
+        s0 = __fdiv_rn(__fadd_rn(__fmul_rn(s0, stride), half), fps);
+        s1 = __fdiv_rn(__fadd_rn(__fmul_rn(s1, stride), half), fps);
+        if (s0 <= 0.f) s0 = __fmul_rn(s0, 0.f);
+        if (s1 <= 0.f) s1 = __fmul_rn(s1, 0.f);
+        if (s0 >= dur) s0 = __fadd_rn(__fmul_rn(s0, 0.f), dur);
+        if (s1 >= dur) s1 = __fadd_rn(__fmul_rn(s1, 0.f), dur);
+      }
+      const long long orow = static_cast<long long>(b) * p.max_seg + r;
+      p.out_segs[orow * 2] = s0;
+      p.out_segs[orow * 2 + 1] = s1;
+      p.out_scores[orow] = d[2];
+      p.out_labels[orow] = win;
+    }
+    produced = r + 1;
+    __syncthreads();
+  }
+  for (int r = produced + tid; r < p.max_seg; r += blockDim.x) {
+    const long long orow = static_cast<long long>(b) * p.max_seg + r;
+    p.out_segs[orow * 2] = 0.f; p.out_segs[orow * 2 + 1] = 0.f;
+    p.out_scores[orow] = 0.f; p.out_labels[orow] = 0;
+  }
+  if (tid == 0) p.out_counts[b] = produced;
+}
+
+}  // namespace unav
+
+using namespace unav;
+
+extern "C" int unav_decode(const float* logits, const float* offsets, const uint8_t* masks, const float* points,
+                           const int* level_off, int B, int L, int ncls, int class_aware, float pre_nms_thresh,
+                           int pre_nms_topk, float duration_thresh, float* cand_segs, float* cand_scores,
+                           int32_t* cand_labels, int cap, void* stream) {
+  UNAV_REQUIRE(logits && offsets && masks && points && level_off && cand_segs && cand_scores && cand_labels,
+               "decode: null pointer");
+  UNAV_REQUIRE(L >= 1 && L <= 8 && B >= 1 && ncls >= 1 && pre_nms_topk >= 1 && pre_nms_thresh >= 0.f,
+               "decode: bad arguments");
+  DecodeParams p;
+  p.logits = logits; p.offsets = offsets; p.masks = masks; p.points = points;
+  p.cand_segs = cand_segs; p.cand_scores = cand_scores; p.cand_labels = cand_labels;
+  int slots = 0;
+  for (int l = 0; l <= L; ++l) p.level_off[l] = level_off[l];
+  for (int l = 0; l < L; ++l) {
+    p.cap_off[l] = slots;
+    const long long n = static_cast<long long>(level_off[l + 1] - level_off[l]) * ncls;
+    slots += static_cast<int>(n < pre_nms_topk ? n : pre_nms_topk);
+  }
+  p.cap_off[L] = slots;
+  UNAV_REQUIRE(cap >= slots, "decode: cap %d < required %d candidate slots", cap, slots);
+  p.B = B; p.L = L; p.ncls = ncls; p.class_aware = class_aware; p.topk = pre_nms_topk; p.cap = cap;
+  p.Ttot = level_off[L]; p.thresh = pre_nms_thresh; p.dur_thresh = duration_thresh;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (cap > slots) {   // slots past the last level region are never written by the kernel
+    for (int b = 0; b < B; ++b) {
+      cudaError_t e = cudaMemsetAsync(cand_labels + static_cast<long long>(b) * cap + slots, 0xff,
+                                      sizeof(int32_t) * (cap - slots), s);
+      if (e != cudaSuccess) { set_error("decode: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+  }
+  dim3 grid(L, B);
+  decode_kernel<<<grid, DEC_THREADS, 0, s>>>(p);
+  count_launch();
+  return finish_launch("decode");
+}
+
+extern "C" size_t unav_softnms_workspace_bytes(int B, int ncls, int max_seg_num) {
+  const size_t dets = static_cast<size_t>(B) * ncls * max_seg_num * 3 * sizeof(float);
+  const size_t cnts = static_cast<size_t>(B) * ncls * sizeof(int32_t);
+  return ((dets + 255) / 256) * 256 + ((cnts + 255) / 256) * 256;
+}
+
+extern "C" int unav_softnms_batched(const float* cand_segs, const float* cand_scores, const int32_t* cand_labels,
+                                    int B, int cap, int ncls, float iou_threshold, float sigma, float min_score,
+                                    int method, int max_seg_num, int max_per_class, const float* vid_meta, float* out_segs,
+                                    float* out_scores, int64_t* out_labels, int32_t* out_counts, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  UNAV_REQUIRE(cand_segs && cand_scores && cand_labels && out_segs && out_scores && out_labels && out_counts,
+               "softnms: null pointer");
+  UNAV_REQUIRE(B >= 1 && cap >= 1 && ncls >= 1 && ncls <= 1024 && max_seg_num >= 1, "softnms: bad arguments");
+  UNAV_REQUIRE(method >= 0 && method <= 3, "softnms: method %d not in 0..3", method);
+  UNAV_REQUIRE(workspace && workspace_bytes >= unav_softnms_workspace_bytes(B, ncls, max_seg_num),
+               "softnms: workspace too small");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  NmsParams p;
+  p.cand_segs = cand_segs; p.cand_scores = cand_scores; p.cand_labels = cand_labels;
+  p.ws_dets = reinterpret_cast<float*>(workspace);
+  const size_t dets = static_cast<size_t>(B) * ncls * max_seg_num * 3 * sizeof(float);
+  p.ws_counts = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + ((dets + 255) / 256) * 256);
+  p.B = B; p.cap = cap; p.ncls = ncls; p.method = method; p.max_seg = max_seg_num;
+  p.iou_thr = iou_threshold; p.sigma = sigma; p.min_score = min_score;
+  // a class holds at most max_per_class candidates (caller's structural bound; 0 = cap); small classes run
+  // as a single warp, big ones as a full block
+  p.maxn = (max_per_class > 0 && max_per_class < cap) ? max_per_class : cap;
+  const size_t smem = static_cast<size_t>(p.maxn) * 4 * sizeof(float);
+  UNAV_REQUIRE(smem <= 200 * 1024, "softnms: %d candidates per class exceed the shared-memory budget", p.maxn);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(softnms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("softnms: smem %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
+    smem_set = smem;
+  }
+  const int threads = p.maxn <= 1024 ? 32 : 256;
+  dim3 grid(ncls, B);
+  softnms_kernel<<<grid, threads, smem, s>>>(p);
+  count_launch();
+  int rc = finish_launch("softnms");
+  if (rc) return rc;
+  MergeParams m;
+  m.ws_dets = p.ws_dets; m.ws_counts = p.ws_counts; m.vid_meta = vid_meta;
+  m.out_segs = out_segs; m.out_scores = out_scores; m.out_labels = out_labels; m.out_counts = out_counts;
+  m.ncls = ncls; m.max_seg = max_seg_num;
+  merge_kernel<<<B, 256, 0, s>>>(m);
+  count_launch();
+  return finish_launch("softnms_merge");
+}

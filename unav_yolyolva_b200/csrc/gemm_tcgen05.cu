@@ -1,0 +1,372 @@
+// gemm_tcgen05.cu — sm_100a tensor-core GEMM: TMA -> swizzled smem -> tcgen05.mma (BF16 in,
+// FP32 accumulate in TMEM) -> tcgen05.ld -> fused epilogue.
+//
+//   C[M,N] = epilogue( A[M,K] . W[N,K]^T ),  A and W K-major (row-major, K contiguous) BF16.
+//
+// One 128 x BN output tile per CTA (the hot path's GEMMs are sub-wave at batch 16, so a persistent
+// scheduler would buy nothing).  Warp roles (192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d loads of a 128x64 A box and a BNx64 W box per
+//               k-block into a 4-stage ring, completion on mbarriers (complete_tx::bytes)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16),
+//               tcgen05.commit releases ring slots / signals the accumulator
+//   warps 2..5  epilogue: tcgen05.ld 32x32b (one accumulator row per thread), bias / mask / gate /
+//               activation / scaled residual, FP32 and/or BF16(-split) stores
+//
+// Split mode (UNAV_BF16X2 operands): rows hold hi = bf16(x) and lo = bf16(x - hi) at column ld/2; the
+// k-loop runs three segments (Ahi,Whi), (Alo,Whi), (Ahi,Wlo) into the same TMEM accumulator, which
+// gives ~FP32 products on the BF16 tensor pipe (measured 5e-6 of range on the logits vs 3e-3 for
+// plain BF16 operands; SURVEY.md §7 "hard parts").
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace unav {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B span
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr long long TC_SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks, then trap instead of hanging
+
+struct TcGroup {
+  CUtensorMap tmA[2];   // [0] = hi (or plain), [1] = lo
+  CUtensorMap tmW[2];
+  EpiParams epi;
+};
+struct TcParams {
+  TcGroup g[UNAV_MAX_GROUPS];
+  int M, N, K, op_dtype, act, res_masked, nseg;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > TC_SPIN_LIMIT) __trap();   // a lost arrival becomes an error, not a hung GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) |
+//   [32,46) SBO >> 4 = 1024 B (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
+// a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+template <int BN>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TILE_BYTES = STAGE_BYTES * TC_STAGES;
+  static constexpr int TOTAL = TILE_BYTES + 256 + 1024;   // barriers + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const TcGroup& g = p.g[blockIdx.z];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
+  const uint32_t bar_base = base + TcSmem<BN>::TILE_BYTES;
+  // barriers: full[s] at +8s, empty[s] at +8(S+s), accum at +8(2S); tmem slot at +8(2S+1)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * TC_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 1);
+
+  const int m0 = blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * BN;
+  const int nkb = (p.K + TC_BK - 1) / TC_BK;
+  const int total = nkb * p.nseg;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&g.tmA[0]);
+    tma_prefetch_desc(&g.tmW[0]);
+    if (p.nseg > 1) { tma_prefetch_desc(&g.tmA[1]); tma_prefetch_desc(&g.tmW[1]); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int it = 0; it < total; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        const int seg = it / nkb, kb = it - seg * nkb;
+        // segments: 0 = (Ahi,Whi), 1 = (Alo,Whi), 2 = (Ahi,Wlo)
+        const CUtensorMap* ma = &g.tmA[seg == 1 ? 1 : 0];
+        const CUtensorMap* mw = &g.tmW[seg == 2 ? 1 : 0];
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), TcSmem<BN>::STAGE_BYTES);
+        const uint32_t sa = base + s * TcSmem<BN>::STAGE_BYTES;
+        tma_load_2d(sa, ma, full_bar(s), kb * TC_BK, m0);
+        tma_load_2d(sa + TcSmem<BN>::A_BYTES, mw, full_bar(s), kb * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * TcSmem<BN>::STAGE_BYTES;
+        const uint64_t adesc = make_smem_desc(sa);
+        const uint64_t bdesc = make_smem_desc(sa + TcSmem<BN>::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (addr >> 4) field
+          tc_mma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(empty_bar(s));        // frees the ring slot once these MMAs have read it
+      }
+      tc_commit(accum_bar);             // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const long long m = static_cast<long long>(m0) + q * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const EpiParams& e = g.epi;
+    const bool row_ok = m < p.M;
+    float mk = 1.f, rs = 1.f;
+    if (row_ok) {
+      if (e.rowmask) mk = e.rowmask[m] ? 1.f : 0.f;
+      if (e.rowscale) rs = e.rowscale[m];
+    }
+    const size_t es = 2;
+    const long long op_split = e.ld_op / 2;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tc_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      tc_wait_ld();
+      const int nb = n0 + c * 32;
+      if (!row_ok || nb >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = nb + j;
+        float x = __uint_as_float(r[j]);
+        if (n < p.N) {
+          if (e.bias) x += __ldg(e.bias + n);
+          x *= mk;
+          x *= rs;
+          if (e.gate) x *= __ldg(e.gate + m * e.gate_groups + n / e.gate_width);
+          x = apply_act(x, p.act);
+          if (e.res) {
+            float rr = e.res[m * e.ldres + n];
+            if (p.res_masked) rr *= mk;
+            const float cs = e.colscale ? __ldg(e.colscale + n) : 1.f;
+            x = rr + cs * x;
+          }
+        }
+        v[j] = x;
+      }
+      const bool full = nb + 32 <= p.N;
+      if (e.out_f32) {
+        float* o = e.out_f32 + m * e.ld_f32 + nb;
+        if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) o[j] = v[j];
+        }
+      }
+      if (e.out_op) {
+        char* row = reinterpret_cast<char*>(e.out_op) + static_cast<size_t>(m) * e.ld_op * es;
+        if (full && (((reinterpret_cast<uintptr_t>(row) + static_cast<size_t>(nb) * es) & 7) == 0) &&
+            ((op_split & 3) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            store_op4(row, p.op_dtype, nb + j, op_split, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) store_op(row, p.op_dtype, nb + j, op_split, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+  if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || sym == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(err));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// 2-D K-major BF16 tensor map: dims {K, rows}, row stride ld elements, box {64, box_rows}, SWIZZLE_128B,
+// out-of-bounds elements read as zero (ragged M / N / K tails need no special casing in the kernel).
+static int encode_map(CUtensorMap* map, const void* ptr, long long rows, long long K, long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return UNAV_ERR_DRIVER;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(TC_BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld K=%lld ld=%lld", (int)r, ptr, rows, K, ld);
+    return UNAV_ERR_DRIVER;
+  }
+  return 0;
+}
+
+template <int BN>
+static int launch_tc(const TcParams& p, int ngroups, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcSmem<BN>::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm_tcgen05<%d>): %s", BN, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + BN - 1) / BN, ngroups);
+  gemm_tcgen05_kernel<BN><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, stream>>>(p);
+  count_launch();
+  return finish_launch("gemm_tcgen05");
+}
+
+int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, int op_dtype, int act,
+                 int res_masked, cudaStream_t stream) {
+  UNAV_REQUIRE(op_dtype == UNAV_BF16 || op_dtype == UNAV_BF16X2, "gemm_tcgen05: operands must be BF16 (got %d)", op_dtype);
+  TcParams p;
+  p.M = M; p.N = N; p.K = K; p.op_dtype = op_dtype; p.act = act; p.res_masked = res_masked;
+  p.nseg = (op_dtype == UNAV_BF16X2) ? 3 : 1;
+  // tile width: prefer more CTAs when the problem cannot fill the 148 SMs
+  const long long tiles128 = static_cast<long long>((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128) * ngroups;
+  const int bn = (N <= 64 || tiles128 < 120) ? 64 : 128;
+  for (int i = 0; i < ngroups; ++i) {
+    const UnavGemmGroup& g = groups[i];
+    UNAV_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.W) & 15) == 0,
+                 "gemm_tcgen05: A/W must be 16-byte aligned");
+    UNAV_REQUIRE(g.lda % 8 == 0 && g.ldw % 8 == 0, "gemm_tcgen05: lda/ldw must be multiples of 8 (got %lld, %lld)", g.lda, g.ldw);
+    if (op_dtype == UNAV_BF16X2)
+      UNAV_REQUIRE(g.lda % 16 == 0 && g.ldw % 16 == 0 && g.lda / 2 >= K && g.ldw / 2 >= K,
+                   "gemm_tcgen05: split operands need ld %% 16 == 0 and ld/2 >= K");
+    int rc;
+    if ((rc = encode_map(&p.g[i].tmA[0], g.A, M, K, g.lda, TC_BM))) return rc;
+    if ((rc = encode_map(&p.g[i].tmW[0], g.W, N, K, g.ldw, bn))) return rc;
+    if (op_dtype == UNAV_BF16X2) {
+      const __nv_bfloat16* alo = reinterpret_cast<const __nv_bfloat16*>(g.A) + g.lda / 2;
+      const __nv_bfloat16* wlo = reinterpret_cast<const __nv_bfloat16*>(g.W) + g.ldw / 2;
+      if ((rc = encode_map(&p.g[i].tmA[1], alo, M, K, g.lda, TC_BM))) return rc;
+      if ((rc = encode_map(&p.g[i].tmW[1], wlo, N, K, g.ldw, bn))) return rc;
+    } else {
+      p.g[i].tmA[1] = p.g[i].tmA[0];
+      p.g[i].tmW[1] = p.g[i].tmW[0];
+    }
+    p.g[i].epi = make_epi(g);
+  }
+  return bn == 64 ? launch_tc<64>(p, ngroups, stream) : launch_tc<128>(p, ngroups, stream);
+}
+
+}  // namespace unav

@@ -1,0 +1,52 @@
+// lib.cu — library-level entry points: version, per-thread error string, device check, launch counter.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace unav {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int finish_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+}  // namespace unav
+
+extern "C" const char* unav_version(void) { return "unav_b200 0.1 (sm_100a)"; }
+extern "C" const char* unav_last_error(void) { return unav::g_err; }
+extern "C" long long unav_launch_count(void) { return unav::g_launches.load(); }
+
+extern "C" int unav_check_device(int dev) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0 || dev >= n) {
+    unav::set_error("no usable CUDA device (%s)", cudaGetErrorString(e));
+    return UNAV_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { unav::set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return (int)e; }
+  if (prop.major != 10) {
+    unav::set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    return UNAV_ERR_UNSUPPORTED;
+  }
+  return 0;
+}

@@ -1,0 +1,538 @@
+// rowops.cu — the bandwidth-bound row kernels of the hot path (token-major [rows, C] FP32 activations):
+// LayerNorm (+pre-add, activation, position table, im2col scatter), depthwise-conv + mask + LayerNorm,
+// row gather / up-sample / im2col copies, transposes, Alignment token embedding, pyramid masks,
+// avg-pool + match projection, and the MaxSigmoid gate.  All 128-bit vectorised, one warp per row.
+#include "common.cuh"
+
+namespace unav {
+
+constexpr int MAXV = 8;   // float4 chunks per lane: C <= 32 * 4 * MAXV = 1024
+
+// =============================================================================================
+// LayerNorm rows
+// =============================================================================================
+struct LnParams {
+  UnavLnGroup g[UNAV_MAX_GROUPS];
+  int M, C, act, op_dtype;
+  float eps;
+};
+
+__global__ void __launch_bounds__(128)
+ln_rows_kernel(const __grid_constant__ LnParams p) {
+  const UnavLnGroup& g = p.g[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (r >= p.M) return;
+  const int C = p.C;
+  long long src = r;
+  if (g.x_seg_rows > 0) src = (r / g.x_seg_rows) * g.x_seg_stride + (r % g.x_seg_rows) + g.x_row_off;
+  const float* xr = g.x + src * g.ldx;
+  const float* ar = g.add ? g.add + r * g.ldadd : nullptr;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    if (c < C) {
+      float4 t = *reinterpret_cast<const float4*>(xr + c);
+      if (ar) {
+        const float4 a = *reinterpret_cast<const float4*>(ar + c);
+        t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+      }
+      v[j] = t;
+      s += (t.x + t.y) + (t.z + t.w);
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    if (c < C) {
+      v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+      q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
+  const float mk = g.rowmask ? (g.rowmask[r] ? 1.f : 0.f) : 1.f;
+  const float* pr = g.post ? g.post + static_cast<long long>(r % g.post_rows) * C : nullptr;
+  const uint8_t edge = g.edge ? g.edge[r] : 0;
+  const size_t es = op_elem_size(p.op_dtype);
+  char* op_row = g.out_op ? reinterpret_cast<char*>(g.out_op) + static_cast<size_t>(r) * g.ld_op * es : nullptr;
+  char* ic_row = g.out_im2col ? reinterpret_cast<char*>(g.out_im2col) + static_cast<size_t>(r) * g.ld_im2col * es : nullptr;
+  const long long ic_rowbytes = g.ld_im2col * static_cast<long long>(es);
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    if (c < C) {
+      const float4 w = *reinterpret_cast<const float4*>(g.w + c);
+      const float4 b = *reinterpret_cast<const float4*>(g.b + c);
+      float4 y;
+      y.x = apply_act(v[j].x * rstd * w.x + b.x, p.act);
+      y.y = apply_act(v[j].y * rstd * w.y + b.y, p.act);
+      y.z = apply_act(v[j].z * rstd * w.z + b.z, p.act);
+      y.w = apply_act(v[j].w * rstd * w.w + b.w, p.act);
+      if (pr) {
+        const float4 t = *reinterpret_cast<const float4*>(pr + c);
+        y.x += t.x * mk; y.y += t.y * mk; y.z += t.z * mk; y.w += t.w * mk;
+      }
+      if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + r * g.ld_f32 + c) = y;
+      if (op_row) store_op4(op_row, p.op_dtype, c, g.ld_op / 2, y);
+      if (ic_row) {
+        const long long sp = g.ld_im2col / 2;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        store_op4(ic_row, p.op_dtype, C + c, sp, y);
+        if (edge & 1) store_op4(ic_row, p.op_dtype, c, sp, z);
+        else store_op4(ic_row - ic_rowbytes, p.op_dtype, 2 * C + c, sp, y);
+        if (edge & 2) store_op4(ic_row, p.op_dtype, 2 * C + c, sp, z);
+        else store_op4(ic_row + ic_rowbytes, p.op_dtype, c, sp, y);
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// depthwise conv (k=3) * mask -> LayerNorm, with optional pre-LayerNorms of the input rows
+// =============================================================================================
+struct DwLnParams {
+  UnavDwLnGroup g[UNAV_MAX_GROUPS];
+  int nseg, seg_len_in, seg_len_out, stride, C, n_pre, n_out, op_dtype;
+  float eps;
+};
+
+constexpr int DWV = 4;   // C <= 512
+
+__global__ void __launch_bounds__(128)
+dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
+  const UnavDwLnGroup& g = p.g[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);   // output row
+  const long long M = static_cast<long long>(p.nseg) * p.seg_len_out;
+  if (r >= M) return;
+  const int C = p.C;
+  const int seg = static_cast<int>(r / p.seg_len_out), t = static_cast<int>(r % p.seg_len_out);
+  // three input rows (tap 0,1,2) = stride*t - 1 .. stride*t + 1, zero outside the segment
+  float4 x[3][DWV];
+  bool ok[3];
+  float mean[3], rstd[3];
+#pragma unroll
+  for (int tap = 0; tap < 3; ++tap) {
+    const int ti = p.stride * t + tap - 1;
+    ok[tap] = ti >= 0 && ti < p.seg_len_in;
+    const float* xr = g.x + (static_cast<long long>(seg) * p.seg_len_in + (ok[tap] ? ti : 0)) * g.ldx;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < DWV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      if (c < C) {
+        x[tap][j] = ok[tap] ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (x[tap][j].x + x[tap][j].y) + (x[tap][j].z + x[tap][j].w);
+      }
+    }
+    if (p.n_pre > 0) {
+      mean[tap] = warp_sum(s) / C;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < DWV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        if (c < C) {
+          const float a = x[tap][j].x - mean[tap], b = x[tap][j].y - mean[tap];
+          const float cc = x[tap][j].z - mean[tap], d = x[tap][j].w - mean[tap];
+          q += (a * a + b * b) + (cc * cc + d * d);
+        }
+      }
+      rstd[tap] = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
+    }
+  }
+  const float mk = g.mask_out ? (g.mask_out[r] ? 1.f : 0.f) : 1.f;
+  const size_t es = op_elem_size(p.op_dtype);
+  for (int o = 0; o < p.n_out; ++o) {
+    const UnavDwLnOut& od = g.out[o];
+    const float* pw = (od.src >= 0) ? g.pre_w[od.src] : nullptr;
+    const float* pb = (od.src >= 0) ? g.pre_b[od.src] : nullptr;
+    float4 z[DWV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < DWV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      if (c < C) {
+        // taps of 4 consecutive channels: 12 contiguous floats of dw[C][3]
+        const float4 d0 = *reinterpret_cast<const float4*>(od.dw + c * 3);
+        const float4 d1 = *reinterpret_cast<const float4*>(od.dw + c * 3 + 4);
+        const float4 d2 = *reinterpret_cast<const float4*>(od.dw + c * 3 + 8);
+        const float wt[4][3] = {{d0.x, d0.y, d0.z}, {d0.w, d1.x, d1.y}, {d1.z, d1.w, d2.x}, {d2.y, d2.z, d2.w}};
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 lw = make_float4(1.f, 1.f, 1.f, 1.f), lb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pw) { lw = *reinterpret_cast<const float4*>(pw + c); lb = *reinterpret_cast<const float4*>(pb + c); }
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap) {
+          if (!ok[tap]) continue;
+          float4 u = x[tap][j];
+          if (pw) {
+            u.x = (u.x - mean[tap]) * rstd[tap] * lw.x + lb.x;
+            u.y = (u.y - mean[tap]) * rstd[tap] * lw.y + lb.y;
+            u.z = (u.z - mean[tap]) * rstd[tap] * lw.z + lb.z;
+            u.w = (u.w - mean[tap]) * rstd[tap] * lw.w + lb.w;
+          }
+          acc[0] = fmaf(wt[0][tap], u.x, acc[0]);
+          acc[1] = fmaf(wt[1][tap], u.y, acc[1]);
+          acc[2] = fmaf(wt[2][tap], u.z, acc[2]);
+          acc[3] = fmaf(wt[3][tap], u.w, acc[3]);
+        }
+        z[j] = make_float4(acc[0] * mk, acc[1] * mk, acc[2] * mk, acc[3] * mk);
+        s += (z[j].x + z[j].y) + (z[j].z + z[j].w);
+      }
+    }
+    const float mu = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < DWV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      if (c < C) {
+        z[j].x -= mu; z[j].y -= mu; z[j].z -= mu; z[j].w -= mu;
+        q += (z[j].x * z[j].x + z[j].y * z[j].y) + (z[j].z * z[j].z + z[j].w * z[j].w);
+      }
+    }
+    const float rs = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
+    char* op_row = od.out_op ? reinterpret_cast<char*>(od.out_op) + static_cast<size_t>(r) * od.ld_op * es : nullptr;
+#pragma unroll
+    for (int j = 0; j < DWV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      if (c < C) {
+        const float4 w = *reinterpret_cast<const float4*>(od.ln_w + c);
+        const float4 b = *reinterpret_cast<const float4*>(od.ln_b + c);
+        float4 y;
+        y.x = z[j].x * rs * w.x + b.x; y.y = z[j].y * rs * w.y + b.y;
+        y.z = z[j].z * rs * w.z + b.z; y.w = z[j].w * rs * w.w + b.w;
+        if (od.out_f32) *reinterpret_cast<float4*>(od.out_f32 + r * od.ld_f32 + c) = y;
+        if (op_row) store_op4(op_row, p.op_dtype, c, od.ld_op / 2, y);
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// row copy jobs (gather / nearest up-sample / im2col / concat)
+// =============================================================================================
+struct CopyParams {
+  UnavCopyJob j[UNAV_MAX_COPY_JOBS];
+  int op_dtype;
+};
+
+__global__ void __launch_bounds__(256)
+rowcopy_kernel(const __grid_constant__ CopyParams p) {
+  const UnavCopyJob& jb = p.j[blockIdx.y];
+  const int cv = jb.C / 4;
+  const long long per_row = static_cast<long long>(jb.ntaps) * cv;
+  const long long total = static_cast<long long>(jb.nseg) * jb.seg_len_out * per_row;
+  const size_t es = op_elem_size(p.op_dtype);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / per_row;
+    const int rem = static_cast<int>(i % per_row);
+    const int tap = rem / cv, c = (rem % cv) * 4;
+    const int seg = static_cast<int>(row / jb.seg_len_out), t = static_cast<int>(row % jb.seg_len_out);
+    const int ti = (t * jb.num) / jb.den + tap - jb.ntaps / 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ti >= 0 && ti < jb.seg_len_in)
+      v = *reinterpret_cast<const float4*>(jb.src + (static_cast<long long>(seg) * jb.seg_len_in + ti) * jb.ld_src + c);
+    const long long drow = static_cast<long long>(seg) * jb.dst_seg_stride + jb.dst_row_off + t;
+    char* dr = reinterpret_cast<char*>(jb.dst) + static_cast<size_t>(drow) * jb.ld_dst * es;
+    store_op4(dr, p.op_dtype, static_cast<long long>(tap) * jb.tap_stride + c, jb.ld_dst / 2, v);
+  }
+}
+
+// =============================================================================================
+// batched transpose + cast: in [nb, R, Cc] -> out [nb, Cc, R]
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+transpose_cast_kernel(const float* __restrict__ in, long long ld_in, void* out, long long ld_out, int R, int Cc,
+                      int op_dtype) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const float* ib = in + static_cast<long long>(b) * R * ld_in;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i, c = c0 + tx;
+    tile[ty + i][tx] = (r < R && c < Cc) ? ib[static_cast<long long>(r) * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  const size_t es = op_elem_size(op_dtype);
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, r = r0 + tx;
+    if (c < Cc && r < R) {
+      char* orow = reinterpret_cast<char*>(out) + (static_cast<size_t>(b) * Cc + c) * ld_out * es;
+      store_op(orow, op_dtype, r, ld_out / 2, tile[tx][ty + i]);
+    }
+  }
+}
+
+// =============================================================================================
+// Alignment token embedding
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+align_embed_kernel(const float* __restrict__ x0, const float* cls_v, const float* cls_a, const float* pos_v,
+                   const float* pos_a, const float* type_v, const float* type_a, float* tokens, int nb, int T,
+                   int C) {
+  // grid: (T+1, nb, 2)
+  const int n = blockIdx.x, b = blockIdx.y, m = blockIdx.z;
+  const float* cls = m ? cls_a : cls_v;
+  const float* pos = (m ? pos_a : pos_v) + static_cast<long long>(n) * C;
+  const float* typ = m ? type_a : type_v;
+  const float* src = n == 0 ? cls : x0 + ((static_cast<long long>(m) * nb + b) * T + (n - 1)) * C;
+  float* dst = tokens + ((static_cast<long long>(m) * nb + b) * (T + 1) + n) * C;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    const float4 a = *reinterpret_cast<const float4*>(src + c);
+    const float4 p = *reinterpret_cast<const float4*>(pos + c);
+    const float4 t = *reinterpret_cast<const float4*>(typ + c);
+    float4 y;
+    y.x = (a.x + p.x) + t.x; y.y = (a.y + p.y) + t.y; y.z = (a.z + p.z) + t.z; y.w = (a.w + p.w) + t.w;
+    *reinterpret_cast<float4*>(dst + c) = y;
+  }
+}
+
+// =============================================================================================
+// pyramid masks
+// =============================================================================================
+__global__ void build_masks_kernel(const uint8_t* __restrict__ mask, uint8_t* out_true, uint8_t* out_up, int nb,
+                                   int T, int L) {
+  long long off = 0, off_up = 0;
+  const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (int l = 0; l < L; ++l) {
+    const int Tl = T >> l;
+    const long long n = static_cast<long long>(nb) * Tl;
+    for (long long i = i0; i < n; i += stride) {
+      const int b = static_cast<int>(i / Tl), t = static_cast<int>(i % Tl);
+      out_true[off + i] = mask[static_cast<long long>(b) * T + (static_cast<long long>(t) << l)];
+      if (l + 1 < L)   // mask of level l+1 repeated twice, laid out at level l's resolution
+        out_up[off_up + i] = mask[static_cast<long long>(b) * T + (static_cast<long long>(t >> 1) << (l + 1))];
+    }
+    off += n;
+    if (l + 1 < L) off_up += n;
+  }
+}
+
+// =============================================================================================
+// adaptive avg-pool (P bins) of three levels + match projection
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+pool_match_kernel(const float* __restrict__ u0, const float* __restrict__ u1, const float* __restrict__ u2, int T0,
+                  int T1, int T2, long long ldu, const float* __restrict__ Wm, const float* __restrict__ bm,
+                  float* q, long long ldq, int C, int Tq, int P) {
+  extern __shared__ float sm[];          // pooled[3P][128] then Wm[Tq][3P], bm[Tq]
+  float* pooled = sm;
+  float* ws = sm + 3 * P * 128;
+  float* bs = ws + Tq * 3 * P;
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  for (int i = threadIdx.x; i < Tq * 3 * P; i += 128) ws[i] = Wm[i];
+  for (int i = threadIdx.x; i < Tq; i += 128) bs[i] = bm[i];
+  const float* us[3] = {u0, u1, u2};
+  const int Ts[3] = {T0, T1, T2};
+  if (c < C) {
+    for (int l = 0; l < 3; ++l) {
+      const int T = Ts[l];
+      for (int pb = 0; pb < P; ++pb) {
+        const int s = (pb * T) / P;                 // floor(pb*T/P)
+        const int e = ((pb + 1) * T + P - 1) / P;   // ceil((pb+1)*T/P)
+        float acc = 0.f;
+        for (int t = s; t < e; ++t) acc += us[l][(static_cast<long long>(b) * T + t) * ldu + c];
+        pooled[(l * P + pb) * 128 + threadIdx.x] = acc / static_cast<float>(e - s);
+      }
+    }
+  }
+  __syncthreads();
+  if (c >= C) return;
+  const int J = 3 * P;
+  for (int t = 0; t < Tq; ++t) {
+    float acc = 0.f;
+    for (int j = 0; j < J; ++j) acc = fmaf(ws[t * J + j], pooled[j * 128 + threadIdx.x], acc);
+    q[(static_cast<long long>(b) * Tq + t) * ldq + c] = acc + bs[t];
+  }
+}
+
+// =============================================================================================
+// MaxSigmoid gate: per (batch, head) [T x hc] . [hc x nwords] -> row max -> sigmoid
+// =============================================================================================
+constexpr int MS_TR = 32, MS_TN = 64;
+
+__global__ void __launch_bounds__(128)
+maxsig_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ G, long long ldg,
+              const float* __restrict__ head_bias, float* gate, int T, int nwords, int H, int hc) {
+  __shared__ float Xs[64][MS_TR + 4];   // [k][row]
+  __shared__ float Gs[64][MS_TN + 4];   // [k][n]
+  const int b = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * MS_TR;
+  const int tid = threadIdx.x;
+  const int tr = tid / 16, tc = tid % 16;       // rows 4*tr.., words 4*tc..
+  for (int i = tid; i < MS_TR * hc; i += 128) {
+    const int row = i / hc, k = i % hc;
+    const int t = t0 + row;
+    Xs[k][row] = t < T ? x[(static_cast<long long>(b) * T + t) * ldx + h * hc + k] : 0.f;
+  }
+  float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  for (int n0 = 0; n0 < nwords; n0 += MS_TN) {
+    __syncthreads();
+    for (int i = tid; i < MS_TN * hc; i += 128) {
+      const int n = i / hc, k = i % hc;
+      Gs[k][n] = (n0 + n < nwords) ? G[(static_cast<long long>(b) * nwords + n0 + n) * ldg + h * hc + k] : 0.f;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k = 0; k < hc; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&Xs[k][tr * 4]);
+      const float4 g4 = *reinterpret_cast<const float4*>(&Gs[k][tc * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], gv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n0 + tc * 4 + j < nwords) mx[i] = fmaxf(mx[i], acc[i][j]);
+  }
+  // reduce over the 16 threads (tc) sharing a row group: they are 16 consecutive lanes
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], o));
+  }
+  if (tc == 0) {
+    const float inv = 1.0f / sqrtf(static_cast<float>(hc));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + tr * 4 + i;
+      if (t < T) gate[(static_cast<long long>(b) * T + t) * H + h] = sigmoidf_(mx[i] * inv + head_bias[h]);
+    }
+  }
+}
+
+}  // namespace unav
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace unav;
+
+extern "C" int unav_layernorm_rows(const UnavLnGroup* groups, int ngroups, int M, int C, float eps, int act,
+                                   int op_dtype, void* stream) {
+  UNAV_REQUIRE(groups && ngroups >= 1 && ngroups <= UNAV_MAX_GROUPS, "layernorm_rows: bad group count");
+  UNAV_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && C <= 128 * MAXV, "layernorm_rows: unsupported C=%d", C);
+  LnParams p;
+  for (int i = 0; i < ngroups; ++i) {
+    p.g[i] = groups[i];
+    UNAV_REQUIRE(groups[i].x && groups[i].w && groups[i].b, "layernorm_rows: null input");
+    UNAV_REQUIRE(!groups[i].out_im2col || groups[i].edge, "layernorm_rows: im2col output needs edge flags");
+    UNAV_REQUIRE(!groups[i].post || groups[i].post_rows > 0, "layernorm_rows: post table needs post_rows");
+  }
+  p.M = M; p.C = C; p.act = act; p.op_dtype = op_dtype; p.eps = eps;
+  dim3 grid((M + 3) / 4, ngroups);
+  ln_rows_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  count_launch();
+  return finish_launch("layernorm_rows");
+}
+
+extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg, int seg_len_in, int stride,
+                              int C, int n_pre, int n_out, float eps, int op_dtype, void* stream) {
+  UNAV_REQUIRE(groups && ngroups >= 1 && ngroups <= UNAV_MAX_GROUPS, "dwconv_ln: bad group count");
+  UNAV_REQUIRE(C % 4 == 0 && C <= 128 * DWV, "dwconv_ln: unsupported C=%d", C);
+  UNAV_REQUIRE((stride == 1 || stride == 2) && seg_len_in % stride == 0, "dwconv_ln: bad stride/length");
+  UNAV_REQUIRE(n_pre >= 0 && n_pre <= 2 && n_out >= 1 && n_out <= 3, "dwconv_ln: bad n_pre/n_out");
+  DwLnParams p;
+  for (int i = 0; i < ngroups; ++i) p.g[i] = groups[i];
+  p.nseg = nseg; p.seg_len_in = seg_len_in; p.seg_len_out = seg_len_in / stride; p.stride = stride; p.C = C;
+  p.n_pre = n_pre; p.n_out = n_out; p.op_dtype = op_dtype; p.eps = eps;
+  const long long M = static_cast<long long>(nseg) * p.seg_len_out;
+  dim3 grid(static_cast<unsigned>((M + 3) / 4), ngroups);
+  dwconv_ln_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  count_launch();
+  return finish_launch("dwconv_ln");
+}
+
+extern "C" int unav_rowcopy(const UnavCopyJob* jobs, int njobs, int op_dtype, void* stream) {
+  UNAV_REQUIRE(jobs && njobs >= 1 && njobs <= UNAV_MAX_COPY_JOBS, "rowcopy: bad job count %d", njobs);
+  CopyParams p;
+  long long maxtotal = 0;
+  for (int i = 0; i < njobs; ++i) {
+    p.j[i] = jobs[i];
+    UNAV_REQUIRE(jobs[i].C % 4 == 0 && jobs[i].den > 0 && jobs[i].ntaps >= 1, "rowcopy: bad job %d", i);
+    const long long tot = static_cast<long long>(jobs[i].nseg) * jobs[i].seg_len_out * jobs[i].ntaps * (jobs[i].C / 4);
+    maxtotal = tot > maxtotal ? tot : maxtotal;
+  }
+  p.op_dtype = op_dtype;
+  long long blocks = (maxtotal + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  dim3 grid(static_cast<unsigned>(blocks), njobs);
+  rowcopy_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  count_launch();
+  return finish_launch("rowcopy");
+}
+
+extern "C" int unav_transpose_cast(const float* in, long long ld_in, void* out, long long ld_out, int nb, int R,
+                                   int Cc, int op_dtype, void* stream) {
+  UNAV_REQUIRE(in && out && nb > 0 && R > 0 && Cc > 0, "transpose_cast: bad arguments");
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, nb);
+  transpose_cast_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, ld_in, out, ld_out, R, Cc, op_dtype);
+  count_launch();
+  return finish_launch("transpose_cast");
+}
+
+extern "C" int unav_align_embed(const float* x0, const float* cls_v, const float* cls_a, const float* pos_v,
+                                const float* pos_a, const float* type_v, const float* type_a, float* tokens,
+                                int nb, int T, int C, void* stream) {
+  UNAV_REQUIRE(x0 && tokens && C % 4 == 0, "align_embed: bad arguments");
+  dim3 grid(T + 1, nb, 2);
+  align_embed_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x0, cls_v, cls_a, pos_v, pos_a, type_v,
+                                                                             type_a, tokens, nb, T, C);
+  count_launch();
+  return finish_launch("align_embed");
+}
+
+extern "C" int unav_build_masks(const uint8_t* mask, uint8_t* out_true, uint8_t* out_up, int nb, int T, int L,
+                                void* stream) {
+  UNAV_REQUIRE(mask && out_true && out_up && L >= 1 && (T % (1 << (L - 1))) == 0, "build_masks: bad arguments");
+  int blocks = (nb * T + 255) / 256;
+  build_masks_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(mask, out_true, out_up, nb, T, L);
+  count_launch();
+  return finish_launch("build_masks");
+}
+
+extern "C" int unav_pool_match(const float* u0, const float* u1, const float* u2, int T0, int T1, int T2,
+                               long long ldu, const float* Wm, const float* bm, float* q, long long ldq, int nb,
+                               int C, int Tq, int P, void* stream) {
+  UNAV_REQUIRE(u0 && u1 && u2 && Wm && bm && q, "pool_match: null pointer");
+  const size_t smem = (static_cast<size_t>(3 * P) * 128 + static_cast<size_t>(Tq) * 3 * P + Tq) * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(pool_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("pool_match: smem %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
+    smem_set = smem;
+  }
+  dim3 grid((C + 127) / 128, nb);
+  pool_match_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(u0, u1, u2, T0, T1, T2, ldu, Wm, bm, q,
+                                                                              ldq, C, Tq, P);
+  count_launch();
+  return finish_launch("pool_match");
+}
+
+extern "C" int unav_maxsig_gate(const float* x, long long ldx, const float* G, long long ldg, const float* head_bias,
+                                float* gate, int nb, int T, int nwords, int H, int hc, void* stream) {
+  UNAV_REQUIRE(x && G && head_bias && gate, "maxsig_gate: null pointer");
+  UNAV_REQUIRE(hc >= 1 && hc <= 64, "maxsig_gate: head channels %d > 64", hc);
+  dim3 grid((T + MS_TR - 1) / MS_TR, H, nb);
+  maxsig_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ldx, G, ldg, head_bias, gate, T, nwords, H, hc);
+  count_launch();
+  return finish_launch("maxsig_gate");
+}
