@@ -131,7 +131,7 @@ int unav_layernorm_rows(const UnavLnGroup* groups, int ngroups, int M, int C, fl
 /* Input x: nseg segments of seg_len_in rows.  Optional pre-LayerNorms (n_pre <= 2) are applied
  * to the input rows first (TransformerBlock ln11/ln12, blocks.py:314).  Output j (< n_out):
  *   z[t, c] = sum_tap dw_j[c, tap] * pre_{src_j}(x)[stride*t + tap - 1, c]   (0 outside the segment)
- *   z *= mask_out[seg*seg_len_out + t];  y = LN_j(z)  -> out_f32_j / out_op_j                      */
+ *   z *= mask_out[seg*seg_len_out + t];  y = LN_j(z) (y = z when ln_w is NULL) -> out_f32_j / out_op_j */
 typedef struct UnavDwLnOut {
   const float* dw;                           /* [C,3] */
   const float* ln_w; const float* ln_b;      /* [C] */
@@ -209,11 +209,15 @@ int unav_align_embed(const float* x0, const float* cls_v, const float* cls_a,
                      const float* pos_v, const float* pos_a, const float* type_v,
                      const float* type_a, float* tokens, int nb, int T, int C, void* stream);
 
-/* Pyramid masks from the level-0 mask [nb, T]:  out_true[l][b][t] = mask[b][t << l]  (blocks.py:45-51),
+/* Pyramid masks from the level-0 mask [nb_src, T] replicated to nb = k*nb_src batch items (item b uses
+ * mask[b % nb_src]):  out_true[l][b][t] = mask[b][t << l]  (blocks.py:45-51),
  * out_up[l][b][t] = out_true[l+1][b][t >> 1]  (multimodal_backbones.py:568-570), both concatenated
- * over levels (level l starts at row offset nb * sum_{j<l} (T >> j)); out_up has L-1 levels. */
-int unav_build_masks(const uint8_t* mask, uint8_t* out_true, uint8_t* out_up, int nb, int T,
-                     int L, void* stream);
+ * over levels (level l starts at row offset nb * sum_{j<l} (T >> j)); out_up has L-1 levels.
+ * out_cls (optional) [nb_src, T+1] = [1, mask] (the CLS-extended mask, multimodal_backbones.py:1159).
+ * out_heads (optional) [nb_src, sum_l (T >> l)]: the true masks of all levels, video-major (the row
+ * order of the heads / decode, multimodal_meta_archs.py:478-493). */
+int unav_build_masks(const uint8_t* mask, uint8_t* out_true, uint8_t* out_up, uint8_t* out_cls,
+                     uint8_t* out_heads, int nb, int nb_src, int T, int L, void* stream);
 
 /* ---- decode ---------------------------------------------------------------------------------- */
 /* logits [B, Ttot, ncls], offsets [B, Ttot, ncls, 2] (class_aware) or [B, Ttot, 2], masks [B, Ttot],

@@ -1,0 +1,67 @@
+"""Fused attention kernel vs torch FP32 reference (masked softmax attention, optional per-query extra key)."""
+import math
+
+import pytest
+import torch
+
+from unav_yolyolva_b200 import kernels as K
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v, kmask, nh, hs, scale, xk=None, xv=None, x_first=0):
+    nb, Tq, _ = q.shape
+    Tk = k.shape[1]
+    out = torch.zeros(nb, Tq, nh * hs, dtype=torch.float64)
+    for b in range(nb):
+        for h in range(nh):
+            sl = slice(h * hs, (h + 1) * hs)
+            s = (q[b, :, sl].double() @ k[b, :, sl].double().t()) * scale
+            s = s.masked_fill(~kmask[b].bool()[None, :], float("-inf"))
+            vv = v[b, :, sl].double()
+            if xk is not None:
+                sx = (q[b, :, sl].double() * xk[b, :, sl].double()).sum(-1) * scale
+                sx[:x_first] = float("-inf")
+                s = torch.cat([s, sx[:, None]], 1)
+                p = s.softmax(-1)
+                out[b, :, sl] = p[:, :Tk] @ vv + p[:, Tk:] * xv[b, :, sl].double()
+            else:
+                out[b, :, sl] = s.softmax(-1) @ vv
+    return out.float()
+
+
+@pytest.mark.parametrize("nb,T,nh,hs", [(3, 224, 4, 128), (2, 112, 4, 64), (5, 7, 4, 64), (2, 56, 4, 64), (1, 300, 2, 64)])
+def test_mhca_attention(cuda, nb, T, nh, hs):
+    g = torch.Generator().manual_seed(T)
+    C = nh * hs
+    q, k, v = (torch.randn(nb, T, C, generator=g) for _ in range(3))
+    lens = torch.randint(1, T + 1, (nb,), generator=g)
+    kmask = (torch.arange(T)[None] < lens[:, None]).to(torch.uint8)
+    out = torch.zeros(nb * T, C, device=cuda)
+    K.attention([{"q": q.reshape(-1, C).to(cuda), "k": k.reshape(-1, C).to(cuda), "v": v.reshape(-1, C).to(cuda),
+                  "kmask": kmask.to(cuda), "out": out}], nb, T, T, nh, hs, 1 / math.sqrt(hs), K.F32)
+    ref = _ref(q, k, v, kmask, nh, hs, 1 / math.sqrt(hs))
+    assert (out.cpu().view(nb, T, C) - ref).abs().max() < 2e-5
+
+
+def test_alignment_attention_with_cross_key(cuda):
+    g = torch.Generator().manual_seed(3)
+    nb, N, nh, hs = 2, 225, 8, 64
+    C = nh * hs
+    qkv = [torch.randn(2, nb, N, 3 * C, generator=g) for _ in range(1)][0]     # [modality, b, token, qkv]
+    lens = torch.tensor([180, 61])
+    kmask = torch.cat([torch.ones(nb, 1), (torch.arange(N - 1)[None] < lens[:, None]).float()], 1).to(torch.uint8)
+    dq = qkv.reshape(2 * nb * N, 3 * C).to(cuda)
+    out = torch.zeros(2 * nb * N, C, device=cuda)
+    hm = nb * N
+    groups = []
+    for m in range(2):
+        own, oth = dq[m * hm:(m + 1) * hm], dq[(1 - m) * hm:(2 - m) * hm]
+        groups.append({"q": K.View(own, 0, C), "k": K.View(own, C, C), "v": K.View(own, 2 * C, C), "kmask": kmask.to(cuda),
+                       "xk": K.View(oth, C, C), "xv": K.View(oth, 2 * C, C), "x_first": 1, "out": out[m * hm:(m + 1) * hm]})
+    K.attention(groups, nb, N, N, nh, hs, 0.125, K.F32)
+    for m in range(2):
+        q, k, v = qkv[m, ..., :C], qkv[m, ..., C:2 * C], qkv[m, ..., 2 * C:]
+        xk, xv = qkv[1 - m, ..., C:2 * C], qkv[1 - m, ..., 2 * C:]
+        ref = _ref(q, k, v, kmask, nh, hs, 0.125, xk, xv, 1)
+        assert (out[m * hm:(m + 1) * hm].cpu().view(nb, N, C) - ref).abs().max() < 2e-5

@@ -1,0 +1,128 @@
+"""GEMM kernels vs a plain FP32 torch reference (same op): CUDA-core FFMA path and the tcgen05/TMA path,
+ragged shapes, grouped launches and every epilogue term."""
+import pytest
+import torch
+
+from unav_yolyolva_b200 import kernels as K
+
+pytestmark = pytest.mark.gpu
+
+ACTS = {K.ACT_NONE: lambda x: x, K.ACT_RELU: torch.relu, K.ACT_GELU: torch.nn.functional.gelu,
+        K.ACT_SILU: torch.nn.functional.silu}
+
+
+def _ref(A, W, bias, rowmask, rowscale, gate, gw, res, colscale, act, res_masked):
+    v = A.double() @ W.double().t()
+    if bias is not None:
+        v = v + bias.double()
+    mk = rowmask.double()[:, None] if rowmask is not None else 1.0
+    v = v * mk
+    if rowscale is not None:
+        v = v * rowscale.double()[:, None]
+    if gate is not None:
+        v = v * gate.double().repeat_interleave(gw, dim=1)[:, :v.shape[1]]
+    v = ACTS[act](v)
+    if res is not None:
+        r = res.double() * (mk if res_masked else 1.0)
+        v = r + (colscale.double() if colscale is not None else 1.0) * v
+    return v.float()
+
+
+def _run(cuda, M, N, Kd, op, backend, act=K.ACT_NONE, full_epi=False, groups=1, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    outs, refs, grp = [], [], []
+    for _ in range(groups):
+        A = torch.randn(M, Kd, generator=g)
+        W = torch.randn(N, Kd, generator=g) / Kd ** 0.5
+        bias = torch.randn(N, generator=g)
+        rowmask = rowscale = gate = res = colscale = None
+        gw = 1
+        if full_epi:
+            rowmask = (torch.rand(M, generator=g) > 0.3).to(torch.uint8)
+            rowscale = torch.rand(M, generator=g) + 0.5
+            gw = 32 if N % 32 == 0 else N
+            gate = torch.rand(M, (N + gw - 1) // gw, generator=g)
+            res = torch.randn(M, N, generator=g)
+            colscale = torch.rand(N, generator=g) + 0.5
+        Aop = K.pack_operand(A.to(cuda), op)
+        Wop = K.pack_operand(W.to(cuda), op)
+        if op != K.F32:   # the reference sees what the kernel sees: BF16(-split) rounded operands
+            def rt(x):
+                hi = x.to(torch.bfloat16).float()
+                return hi + ((x - hi).to(torch.bfloat16).float() if op == K.BF16X2 else 0)
+            A, W = rt(A), rt(W)
+        out = torch.full((M, N), float("nan"), device=cuda)
+        out_op = K.new_operand(M, N, op, cuda)
+        d = {"A": Aop, "W": Wop, "bias": bias.to(cuda), "out_f32": out, "out_op": out_op}
+        if full_epi:
+            d.update({"rowmask": rowmask.to(cuda), "rowscale": rowscale.to(cuda), "gate": gate.to(cuda),
+                      "gate_groups": gate.shape[1], "gate_width": gw, "res": res.to(cuda), "colscale": colscale.to(cuda)})
+        grp.append(d)
+        outs.append((out, out_op))
+        refs.append(_ref(A, W, bias, rowmask, rowscale, gate, gw, res, colscale, act, True))
+    K.gemm(grp, M, N, Kd, op, act, True, backend)
+    torch.cuda.synchronize()
+    for (out, out_op), ref in zip(outs, refs):
+        scale = ref.abs().max().item() + 1e-6
+        tol = 2e-5 if op != K.BF16 or backend == K.GEMM_SIMT else 2e-5
+        err = (out.cpu() - ref).abs().max().item() / scale
+        assert err < tol, f"out_f32 err {err}"
+        if op == K.F32:
+            got = out_op[:, :N].cpu()
+        else:
+            half = out_op.shape[1] // 2
+            got = out_op[:, :N].float().cpu()
+            if op == K.BF16X2:
+                got = got + out_op[:, half:half + N].float().cpu()
+        tol_op = 1e-5 if op != K.BF16 else 5e-3
+        assert (got - ref).abs().max().item() / scale < tol_op
+
+
+SHAPES = [(128, 128, 64), (256, 512, 512), (200, 100, 1536), (7, 512, 512), (3584, 512, 1536), (441, 200, 224),
+          (130, 64, 128), (64, 1280, 224), (1000, 256, 768), (77, 40, 72)]
+
+
+@pytest.mark.parametrize("M,N,Kd", SHAPES)
+def test_simt_fp32(cuda, M, N, Kd):
+    _run(cuda, M, N, Kd, K.F32, K.GEMM_SIMT, full_epi=True, act=K.ACT_GELU)
+
+
+@pytest.mark.parametrize("M,N,Kd", SHAPES)
+@pytest.mark.parametrize("op", [K.BF16, K.BF16X2])
+def test_tcgen05_matches_reference(cuda, M, N, Kd, op):
+    _run(cuda, M, N, Kd, op, K.GEMM_TCGEN05)
+
+
+@pytest.mark.parametrize("act", [K.ACT_NONE, K.ACT_RELU, K.ACT_GELU, K.ACT_SILU])
+def test_tcgen05_full_epilogue(cuda, act):
+    _run(cuda, 300, 256, 512, K.BF16X2, K.GEMM_TCGEN05, act=act, full_epi=True)
+    _run(cuda, 300, 200, 512, K.BF16, K.GEMM_TCGEN05, act=act, full_epi=True)
+
+
+def test_tcgen05_grouped(cuda):
+    _run(cuda, 500, 512, 512, K.BF16X2, K.GEMM_TCGEN05, groups=6, full_epi=True)
+    _run(cuda, 224, 256, 256, K.BF16, K.GEMM_TCGEN05, groups=3)
+
+
+def test_simt_bf16_operands(cuda):
+    _run(cuda, 300, 200, 520, K.BF16X2, K.GEMM_SIMT, full_epi=True)
+    _run(cuda, 300, 200, 520, K.BF16, K.GEMM_SIMT)
+
+
+def test_tcgen05_linearity_large(cuda):
+    """Size-independent property at a full-size problem: C(A1 + A2) == C(A1) + C(A2) for exactly
+    representable operands (small integers), so the tensor-core result must be exact."""
+    g = torch.Generator().manual_seed(1)
+    M, N, Kd = 7056, 512, 3072
+    A1 = torch.randint(-3, 4, (M, Kd), generator=g).float()
+    A2 = torch.randint(-3, 4, (M, Kd), generator=g).float()
+    W = torch.randint(-2, 3, (N, Kd), generator=g).float()
+    outs = []
+    for A in (A1, A2, A1 + A2):
+        out = torch.empty(M, N, device=cuda)
+        K.gemm([{"A": K.pack_operand(A.to(cuda), K.BF16), "W": K.pack_operand(W.to(cuda), K.BF16), "out_f32": out}],
+               M, N, Kd, K.BF16, K.ACT_NONE, False, K.GEMM_TCGEN05)
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0] + outs[1], outs[2])
+    assert torch.equal(outs[0].cpu(), A1 @ W.t())

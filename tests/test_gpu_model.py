@@ -1,0 +1,129 @@
+"""End-to-end parity of the fused CUDA path (through the C ABI) against the CPU oracle and the committed
+reference outputs: logits / offsets within the stated tolerance per precision mode, detections bit-exact
+at the decode+NMS stage."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref as R
+from oracle import nms_ref
+from unav_yolyolva_b200 import synth
+from unav_yolyolva_b200.config import TEST_CFG, default_model_cfg
+from unav_yolyolva_b200.modeling import make_multimodal_meta_arch
+
+pytestmark = pytest.mark.gpu
+
+# max |err| / max |ref| per tensor (SURVEY.md §8d parity gates): FP32 mode 1e-5; tensor-core modes as measured
+TOL = {"fp32": 1e-5, "bf16x3": 5e-5, "bf16": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def model(cuda):
+    m = make_multimodal_meta_arch("LocPointTransformer", **default_model_cfg())
+    m.load_state_dict(synth.trained_like_state_dict(), strict=True)
+    return m.to(cuda).eval()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    sd = synth.trained_like_state_dict()
+    b = synth.make_batch(2, 224)
+    with torch.no_grad():
+        logits, offsets, masks = R.forward_logits(sd, b["visual"], b["audio"], b["mask"])
+    return {"batch": b, "logits": torch.cat(logits, 1), "offsets": torch.cat(offsets, 1), "masks": torch.cat(masks, 1),
+            "lv_logits": logits, "lv_offsets": offsets, "lv_masks": masks}
+
+
+def _rel(a, r):
+    return float((a - r).abs().max() / r.abs().max())
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+def test_logits_offsets_vs_oracle(model, oracle, mode):
+    model.precision = mode
+    model.use_cuda_graph = False
+    plan = model.run_hot_path(oracle["batch"])
+    torch.cuda.synchronize()
+    B = 2
+    lg = plan["logits"].cpu().view(B, 441, 100)
+    of = plan["offsets"].cpu().view(B, 441, 100, 2)
+    e1, e2 = _rel(lg, oracle["logits"]), _rel(of, oracle["offsets"])
+    print(f"[{mode}] logits rel err {e1:.3e}, offsets rel err {e2:.3e}")
+    assert e1 <= TOL[mode] and e2 <= TOL[mode] * 4
+    assert torch.equal(plan["m_heads"].cpu().view(B, 441).bool(), oracle["masks"])
+
+
+def test_detections_bit_exact_given_same_logits(model, oracle):
+    """Stage-level gate: decode + soft-NMS + seconds on the device vs the oracle fed the SAME (device-produced)
+    logits/offsets: identical labels, identical score and segment bits."""
+    model.precision = "fp32"
+    model.use_cuda_graph = False
+    b = oracle["batch"]
+    plan = model.run_hot_path(b)
+    torch.cuda.synchronize()
+    B = 2
+    lg = plan["logits"].cpu().view(B, 441, 100)
+    of = plan["offsets"].cpu().view(B, 441, 100, 2)
+    mk = plan["m_heads"].cpu().view(B, 441).bool()
+    off = [0, 224, 336, 392, 420, 434, 441]
+    pts = R.make_points(224)
+    n_exact_scores = 0
+    for i in range(B):
+        segs, scores, labels, _ = R.decode_single_video(pts, [mk[i, off[l]:off[l + 1]] for l in range(6)],
+                                                        [lg[i, off[l]:off[l + 1]] for l in range(6)],
+                                                        [of[i, off[l]:off[l + 1]] for l in range(6)])
+        # device scores (CUDA expf sigmoid) replace torch's CPU sigmoid so the NMS inputs are identical
+        cs = plan["cand_segs"][i].cpu().numpy(); csc = plan["cand_scores"][i].cpu().numpy(); cl = plan["cand_labels"][i].cpu().numpy()
+        keep = cl >= 0
+        assert keep.sum() == len(labels)
+        r = nms_ref.batched_nms(cs[keep], csc[keep], cl[keep].astype(np.int64), TEST_CFG["iou_threshold"], TEST_CFG["min_score"],
+                                TEST_CFG["max_seg_num"], True, TEST_CFG["nms_sigma"])
+        sec = nms_ref.to_seconds(r[0], b["feat_stride"][i], b["feat_num_frames"][i], b["fps"][i], b["duration"][i])
+        n = int(plan["out_counts"][i].item())
+        assert n == len(r[1]) == 100
+        assert np.array_equal(plan["out_labels"][i].cpu().numpy(), r[2])
+        assert np.array_equal(plan["out_scores"][i].cpu().numpy().view(np.uint32), r[1].view(np.uint32))
+        assert np.array_equal(np.abs(plan["out_segs"][i].cpu().numpy()).view(np.uint32), np.abs(sec).view(np.uint32))
+
+
+def test_detections_vs_reference_golden(model, oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "model_b2.npz"))
+    model.precision = "fp32"
+    model.use_cuda_graph = True
+    results, losses = model(oracle["batch"])
+    assert results["segments"].shape == (2, 100, 2) and results["scores"].shape == (2, 100)
+    assert results["labels"].dtype == torch.int64 and results["segments"].is_cuda
+    assert set(losses) == {"cls_loss", "reg_loss", "final_loss", "inter_contr_loss", "intra_contr_loss",
+                           "score_loss_video", "score_loss_audio"}
+    lab, sc, seg = results["labels"].cpu().numpy(), results["scores"].cpu().numpy(), results["segments"].cpu().numpy()
+    # FP32-mode logits differ from the reference's by ~1e-6, so near-tied ranks may swap: compare the bulk
+    same = (lab == g["labels"])
+    assert same.mean() > 0.97
+    assert np.allclose(sc[same], g["scores"][same], rtol=1e-4, atol=1e-6)
+    assert np.allclose(seg[same], g["segments"][same], atol=5e-3)
+
+
+def test_graph_replay_is_deterministic_and_batch_sizes(model):
+    model.precision = "bf16x3"
+    model.use_cuda_graph = True
+    for B in (1, 3):
+        b = synth.make_batch(B, 224, first_index=10)
+        r1, _ = model(b)
+        r2, _ = model(b)
+        assert torch.equal(r1["labels"], r2["labels"]) and torch.equal(r1["scores"], r2["scores"])
+        # a different batch through the same captured graph must give different, valid results
+        b2 = synth.make_batch(B, 224, first_index=50)
+        r3, _ = model(b2)
+        assert not torch.equal(r1["scores"], r3["scores"])
+        assert (r3["scores"][:, :-1] >= r3["scores"][:, 1:]).all()
+        dur = torch.tensor(b2["duration"], device=r3["segments"].device)[:, None, None]
+        assert (r3["segments"] >= 0).all() and (r3["segments"] <= dur).all()
+    # per-video results do not depend on batch composition (videos are independent)
+    ba = synth.make_batch(3, 224, first_index=10)
+    bb = synth.make_batch(1, 224, first_index=11)
+    ra, _ = model(ba)
+    rb, _ = model(bb)
+    assert torch.equal(ra["labels"][1], rb["labels"][0]) and torch.equal(ra["scores"][1], rb["scores"][0])

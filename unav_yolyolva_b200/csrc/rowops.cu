@@ -194,16 +194,21 @@ dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
       }
     }
     const float rs = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
+    const bool has_ln = od.ln_w != nullptr;   // NULL: plain masked depthwise conv (MaskedConv1D with groups = C)
     char* op_row = od.out_op ? reinterpret_cast<char*>(od.out_op) + static_cast<size_t>(r) * od.ld_op * es : nullptr;
 #pragma unroll
     for (int j = 0; j < DWV; ++j) {
       const int c = (j * 32 + lane) * 4;
       if (c < C) {
-        const float4 w = *reinterpret_cast<const float4*>(od.ln_w + c);
-        const float4 b = *reinterpret_cast<const float4*>(od.ln_b + c);
         float4 y;
-        y.x = z[j].x * rs * w.x + b.x; y.y = z[j].y * rs * w.y + b.y;
-        y.z = z[j].z * rs * w.z + b.z; y.w = z[j].w * rs * w.w + b.w;
+        if (has_ln) {
+          const float4 w = *reinterpret_cast<const float4*>(od.ln_w + c);
+          const float4 b = *reinterpret_cast<const float4*>(od.ln_b + c);
+          y.x = z[j].x * rs * w.x + b.x; y.y = z[j].y * rs * w.y + b.y;
+          y.z = z[j].z * rs * w.z + b.z; y.w = z[j].w * rs * w.w + b.w;
+        } else {
+          y = make_float4(z[j].x + mu, z[j].y + mu, z[j].z + mu, z[j].w + mu);
+        }
         if (od.out_f32) *reinterpret_cast<float4*>(od.out_f32 + r * od.ld_f32 + c) = y;
         if (op_row) store_op4(op_row, p.op_dtype, c, od.ld_op / 2, y);
       }
@@ -297,22 +302,35 @@ align_embed_kernel(const float* __restrict__ x0, const float* cls_v, const float
 // =============================================================================================
 // pyramid masks
 // =============================================================================================
-__global__ void build_masks_kernel(const uint8_t* __restrict__ mask, uint8_t* out_true, uint8_t* out_up, int nb,
-                                   int T, int L) {
+__global__ void build_masks_kernel(const uint8_t* __restrict__ mask, uint8_t* out_true, uint8_t* out_up,
+                                   uint8_t* out_cls, uint8_t* out_heads, int nb, int nb_src, int T, int L) {
   long long off = 0, off_up = 0;
+  int lvl_off = 0;
+  const int Ttot = 2 * T - (T >> (L - 1));
   const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (int l = 0; l < L; ++l) {
     const int Tl = T >> l;
     const long long n = static_cast<long long>(nb) * Tl;
     for (long long i = i0; i < n; i += stride) {
-      const int b = static_cast<int>(i / Tl), t = static_cast<int>(i % Tl);
-      out_true[off + i] = mask[static_cast<long long>(b) * T + (static_cast<long long>(t) << l)];
+      const int b = static_cast<int>(i / Tl) % nb_src, t = static_cast<int>(i % Tl);
+      const uint8_t mv = mask[static_cast<long long>(b) * T + (static_cast<long long>(t) << l)] != 0;
+      out_true[off + i] = mv;
+      if (out_heads && i < static_cast<long long>(nb_src) * Tl)   // video-major copy for the heads / decode
+        out_heads[static_cast<long long>(b) * Ttot + lvl_off + t] = mv;
       if (l + 1 < L)   // mask of level l+1 repeated twice, laid out at level l's resolution
-        out_up[off_up + i] = mask[static_cast<long long>(b) * T + (static_cast<long long>(t >> 1) << (l + 1))];
+        out_up[off_up + i] = mask[static_cast<long long>(b) * T + (static_cast<long long>(t >> 1) << (l + 1))] != 0;
     }
     off += n;
+    lvl_off += Tl;
     if (l + 1 < L) off_up += n;
+  }
+  if (out_cls) {   // [nb_src, T+1]: a always-valid CLS slot in front of the frame mask (multimodal_backbones.py:1159)
+    const long long n = static_cast<long long>(nb_src) * (T + 1);
+    for (long long i = i0; i < n; i += stride) {
+      const int b = static_cast<int>(i / (T + 1)), t = static_cast<int>(i % (T + 1));
+      out_cls[i] = t == 0 ? 1 : (mask[static_cast<long long>(b) * T + t - 1] != 0);
+    }
   }
 }
 
@@ -500,11 +518,13 @@ extern "C" int unav_align_embed(const float* x0, const float* cls_v, const float
   return finish_launch("align_embed");
 }
 
-extern "C" int unav_build_masks(const uint8_t* mask, uint8_t* out_true, uint8_t* out_up, int nb, int T, int L,
-                                void* stream) {
-  UNAV_REQUIRE(mask && out_true && out_up && L >= 1 && (T % (1 << (L - 1))) == 0, "build_masks: bad arguments");
+extern "C" int unav_build_masks(const uint8_t* mask, uint8_t* out_true, uint8_t* out_up, uint8_t* out_cls,
+                                uint8_t* out_heads, int nb, int nb_src, int T, int L, void* stream) {
+  UNAV_REQUIRE(mask && out_true && (out_up || L == 1) && L >= 1 && (T % (1 << (L - 1))) == 0 && nb_src >= 1 &&
+                   nb % nb_src == 0, "build_masks: bad arguments");
   int blocks = (nb * T + 255) / 256;
-  build_masks_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(mask, out_true, out_up, nb, T, L);
+  build_masks_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(mask, out_true, out_up, out_cls,
+                                                                               out_heads, nb, nb_src, T, L);
   count_launch();
   return finish_launch("build_masks");
 }

@@ -1,0 +1,561 @@
+"""Fused, token-major execution of the PtTransformer inference hot path on sm_100a.
+
+``HotPathEngine`` turns a ``PtTransformer`` (parameter holder with the reference's state_dict layout) into
+a static launch plan over hand-written CUDA kernels (C ABI, ``kernels.py``): Alignment multiway transformer
+-> conv/transformer stem -> depthwise pyramid -> two fusion passes (batched as 2B) -> cls/reg heads -> decode
+-> per-class soft-NMS.  About 330 kernel launches per batch replace the reference's ~51 k ATen calls
+(SURVEY.md §2.2); the whole sequence is captured once per batch size into a CUDA graph and replayed.
+
+Data layout: activations are token-major FP32 ``[rows, C]`` matrices (rows = time steps of
+consecutive batch items); the two modalities are stacked along the batch ("NB = 2B": visual items first), the
+6 pyramid levels are separate matrices until the heads, where they are concatenated per video (441 rows).
+GEMM operands are separate buffers in the operand dtype of the chosen precision mode:
+
+    mode      operands              GEMM backend                    max |err| / range on logits vs FP32 oracle
+    fp32      FP32                  CUDA-core FFMA (gemm_simt)      ~1e-6
+    bf16x3    BF16 hi/lo split      tcgen05, 3 MMA passes           ~5e-6
+    bf16      BF16                  tcgen05, 1 MMA pass             ~3e-3
+
+k=3 convolutions are GEMMs over im2col operands that the producing kernel scatters directly (no separate
+im2col pass for LayerNorm outputs).  Reference semantics restated per step with file:line in the comments
+(paths relative to /root/reference/libs/modeling).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import kernels as K
+from .kernels import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, BF16, BF16X2, F32, GEMM_SIMT, GEMM_TCGEN05, View
+
+MODES = {"fp32": (F32, GEMM_SIMT), "bf16": (BF16, GEMM_TCGEN05), "bf16x3": (BF16X2, GEMM_TCGEN05),
+         "bf16_simt": (BF16, GEMM_SIMT), "bf16x3_simt": (BF16X2, GEMM_SIMT)}
+
+
+def _flat(p: torch.Tensor) -> torch.Tensor:
+    return p.detach().float().reshape(-1).contiguous()
+
+
+class HotPathEngine:
+    def __init__(self, model, mode: str = "bf16x3", use_graph: bool = True):
+        if mode not in MODES:
+            raise ValueError(f"unknown precision mode {mode!r}; choose from {sorted(MODES)}")
+        self.mode = mode
+        self.op, self.backend = MODES[mode]
+        self.use_graph = use_graph
+        self.model = model
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("HotPathEngine needs the model on a CUDA device (no CPU fallback)")
+        self.dev = dev
+        from . import _cabi
+        _cabi.check(_cabi.load().unav_check_device(dev.index if dev.index is not None else torch.cuda.current_device()),
+                    "unav_check_device")
+        self.T = model.max_seq_len
+        self.C = model.backbone.n_embd
+        self.L = len(model.fpn_strides)
+        self.ncls = model.num_classes
+        self.n_head = model.backbone.n_head
+        self.Tl = [self.T // s for s in model.fpn_strides]
+        self.Ttot = sum(self.Tl)
+        self.level_off = [0]
+        for t in self.Tl:
+            self.level_off.append(self.level_off[-1] + t)
+        self.w: Dict[str, torch.Tensor] = {}
+        self._pack_weights()
+        self._plans: Dict[int, dict] = {}
+
+    # ------------------------------------------------------------------------------ weights
+    def _pack_weights(self):
+        sd = {k: v for k, v in self.model.state_dict().items()}
+        w = self.w
+        op = self.op
+
+        def lin(name, key):            # nn.Linear / Conv1d k=1: [N, K(,1)]
+            t = sd[key].float()
+            w[name] = K.pack_operand(t.reshape(t.shape[0], -1), op)
+
+        def conv3(name, key):          # Conv1d k=3 [N, Cin, 3] -> im2col layout [N, 3*Cin] (tap-major)
+            t = sd[key].float()
+            w[name] = K.pack_operand(t.permute(0, 2, 1).reshape(t.shape[0], -1).contiguous(), op)
+
+        def vec(name, key):
+            w[name] = _flat(sd[key])
+
+        def cat_lin(name, keys):
+            w[name] = K.pack_operand(torch.cat([sd[k].float().reshape(sd[k].shape[0], -1) for k in keys], 0), op)
+
+        def cat_vec(name, keys):
+            w[name] = torch.cat([_flat(sd[k]) for k in keys])
+
+        # ---- Alignment (multimodal_backbones.py:989-1034)
+        a = "alignment."
+        lin("al.pv", a + "proj_fc_video.0.weight"); vec("al.pv.b", a + "proj_fc_video.0.bias")
+        lin("al.pa", a + "proj_fc_text.0.weight"); vec("al.pa.b", a + "proj_fc_text.0.bias")
+        N = self.T + 1
+        w["al.pos_v"] = sd[a + "pos_embed_video"][0, :N].float().contiguous()
+        w["al.pos_a"] = sd[a + "pos_embed_text"][0, :N].float().contiguous()
+        for nm in ("type_video", "type_text", "cls_token_video", "cls_token_text"):
+            vec("al." + nm, a + nm)
+        m = a + "multiway_list.0."
+        vec("al.n1.w", m + "norm1_fused.weight"); vec("al.n1.b", m + "norm1_fused.bias")
+        cat_lin("al.qkv", [m + f"attn_fusion.{x}.weight" for x in "qkv"])
+        cat_vec("al.qkv.b", [m + f"attn_fusion.{x}.bias" for x in "qkv"])
+        lin("al.m", m + "attn_fusion.m.weight"); vec("al.m.b", m + "attn_fusion.m.bias")
+        for mod in ("video", "text"):
+            vec(f"al.n2.{mod}.w", m + f"norm2_{mod}.weight"); vec(f"al.n2.{mod}.b", m + f"norm2_{mod}.bias")
+            lin(f"al.fc1.{mod}", m + f"ffn_{mod}.fc1.weight"); vec(f"al.fc1.{mod}.b", m + f"ffn_{mod}.fc1.bias")
+            lin(f"al.fc2.{mod}", m + f"ffn_{mod}.fc2.weight"); vec(f"al.fc2.{mod}.b", m + f"ffn_{mod}.fc2.bias")
+            vec(f"al.nf.{mod}.w", a + f"norm_{mod}.weight"); vec(f"al.nf.{mod}.b", a + f"norm_{mod}.bias")
+            lin(f"al.fc.{mod}", a + f"fc_{mod}.0.weight"); vec(f"al.fc.{mod}.b", a + f"fc_{mod}.0.bias")
+            vec(f"al.fcn.{mod}.w", a + f"fc_{mod}.3.weight"); vec(f"al.fcn.{mod}.b", a + f"fc_{mod}.3.bias")
+
+        # ---- backbone stem (multimodal_backbones.py:660-713)
+        b = "backbone."
+        for X in "VA":
+            for i in range(2):
+                conv3(f"bb.embd{X}{i}", b + f"embd_{X}.{i}.conv.weight")
+                vec(f"bb.embdn{X}{i}.w", b + f"embd_norm_{X}.{i}.weight"); vec(f"bb.embdn{X}{i}.b", b + f"embd_norm_{X}.{i}.bias")
+            for i in range(len(self.model.backbone.self_att_V)):
+                self._pack_tblock(sd, f"bb.sa{X}{i}", b + f"self_att_{X}.{i}.")
+        w["bb.pe"] = self.model.backbone.pos_embd[0].detach().float().t().contiguous()      # [T, C]
+        for i in range(self.L - 1):
+            vec(f"bb.down{i}.dw", b + f"downsample_list.{i}.down_conv.conv.weight")
+            vec(f"bb.down{i}.w", b + f"downsample_list.{i}.down_norm.weight"); vec(f"bb.down{i}.b", b + f"downsample_list.{i}.down_norm.bias")
+        # ---- fusion module (multimodal_backbones.py:367-549)
+        f = b + "fusion_module."
+        self._pack_mhca(sd, "fu.te", f + "text_enhancer.")
+        conv3("fu.ds", f + "downsample_layers.0.down_conv.conv.weight"); vec("fu.ds.b", f + "downsample_layers.0.down_conv.conv.bias")
+        vec("fu.dsn.w", f + "downsample_layers.0.down_norm.weight"); vec("fu.dsn.b", f + "downsample_layers.0.down_norm.bias")
+        w["fu.match.w"] = sd[f + "match_projection.weight"].float().reshape(sd[f + "match_projection.weight"].shape[0], -1).contiguous()
+        vec("fu.match.b", f + "match_projection.bias")
+        self.td_heads, self.bu_heads = [], []
+        for kind, heads in (("top_down_layers", self.td_heads), ("bottom_up_layers", self.bu_heads)):
+            tag = "td" if kind.startswith("top") else "bu"
+            for i in range(self.L - 1):
+                p = f + f"{kind}.{i}."
+                lin(f"fu.{tag}{i}.main", p + "main_conv.conv.weight"); vec(f"fu.{tag}{i}.main.b", p + "main_conv.conv.bias")
+                for j in range(3):
+                    self._pack_mhca(sd, f"fu.{tag}{i}.blk{j}", p + f"blocks.{j}.")
+                vec(f"fu.{tag}{i}.hb", p + "attn_block.bias")
+                heads.append(sd[p + "attn_block.bias"].numel())
+                conv3(f"fu.{tag}{i}.proj", p + "attn_block.project_conv.conv.weight"); vec(f"fu.{tag}{i}.proj.b", p + "attn_block.project_conv.conv.bias")
+                lin(f"fu.{tag}{i}.final", p + "final_conv.conv.weight"); vec(f"fu.{tag}{i}.final.b", p + "final_conv.conv.bias")
+            cat_lin(f"fu.{tag}.gfc", [f + f"{kind}.{i}.attn_block.guide_fc.weight" for i in range(self.L - 1)])
+            cat_vec(f"fu.{tag}.gfc.b", [f + f"{kind}.{i}.attn_block.guide_fc.bias" for i in range(self.L - 1)])
+        # ---- heads (multimodal_meta_archs.py:101-259): first convs of cls and reg fused along N
+        t0 = [sd[f"{h}.head.0.conv.weight"].float().permute(0, 2, 1).reshape(self.C, -1) for h in ("cls_head", "reg_head")]
+        w["hd.c0"] = K.pack_operand(torch.cat(t0, 0).contiguous(), op)
+        for h, tag in (("cls_head", "cls"), ("reg_head", "reg")):
+            conv3(f"hd.{tag}.c1", f"{h}.head.1.conv.weight")
+            for i in range(2):
+                vec(f"hd.{tag}.n{i}.w", f"{h}.norm.{i}.weight"); vec(f"hd.{tag}.n{i}.b", f"{h}.norm.{i}.bias")
+        conv3("hd.cls.out", "cls_head.cls_head.conv.weight"); vec("hd.cls.out.b", "cls_head.cls_head.conv.bias")
+        conv3("hd.reg.out", "reg_head.offset_head.conv.weight"); vec("hd.reg.out.b", "reg_head.offset_head.conv.bias")
+        w["hd.scales"] = torch.stack([sd[f"reg_head.scale.{l}.scale"].float() for l in range(self.L)]).contiguous()
+
+    def _pack_mhca(self, sd, name, p):
+        w = self.w
+        for x in ("query", "key", "value"):
+            w[f"{name}.{x}.dw"] = _flat(sd[p + f"{x}_conv.conv.weight"])
+            w[f"{name}.{x}.nw"] = _flat(sd[p + f"{x}_norm.weight"]); w[f"{name}.{x}.nb"] = _flat(sd[p + f"{x}_norm.bias"])
+            t = sd[p + f"{x}.weight"].float()
+            w[f"{name}.{x}"] = K.pack_operand(t.reshape(t.shape[0], -1), self.op)
+            w[f"{name}.{x}.b"] = _flat(sd[p + f"{x}.bias"])
+        t = sd[p + "proj.weight"].float()
+        w[f"{name}.proj"] = K.pack_operand(t.reshape(t.shape[0], -1), self.op)
+        w[f"{name}.proj.b"] = _flat(sd[p + "proj.bias"])
+
+    def _pack_tblock(self, sd, name, p):
+        w = self.w
+        self._pack_mhca(sd, name + ".attn", p + "attn.")
+        for ln in ("ln11", "ln12", "ln2"):
+            w[f"{name}.{ln}.w"] = _flat(sd[p + ln + ".weight"]); w[f"{name}.{ln}.b"] = _flat(sd[p + ln + ".bias"])
+        for i, tag in ((0, "mlp0"), (3, "mlp3")):
+            t = sd[p + f"mlp.{i}.weight"].float()
+            w[f"{name}.{tag}"] = K.pack_operand(t.reshape(t.shape[0], -1), self.op)
+            w[f"{name}.{tag}.b"] = _flat(sd[p + f"mlp.{i}.bias"])
+        w[f"{name}.sa"] = _flat(sd[p + "drop_path_attn.scale"])
+        w[f"{name}.sm"] = _flat(sd[p + "drop_path_mlp.scale"])
+
+    # ------------------------------------------------------------------------------ buffers
+    def _plan(self, B: int) -> dict:
+        if B in self._plans:
+            return self._plans[B]
+        dev, op, T, C, L = self.dev, self.op, self.T, self.C, self.L
+        NB = 2 * B
+        f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        u8 = lambda *s: torch.zeros(*s, dtype=torch.uint8, device=dev)
+        opb = lambda rows, Kc: K.new_operand(rows, Kc, op, dev)
+        P: dict = {"B": B}
+        Tl, Ttot = self.Tl, self.Ttot
+        # inputs (static addresses for graph replay)
+        P["visual"] = f32(B, 2048, T); P["audio"] = f32(B, 128, T); P["mask_in"] = u8(B, T)
+        P["vid_meta"] = f32(B, 4)
+        # masks
+        P["m_true"] = u8(NB * Ttot); P["m_up"] = u8(NB * (Ttot - Tl[-1])); P["m_cls"] = u8(B, T + 1)
+        offs, o = [], 0
+        for l in range(L):
+            offs.append(o); o += NB * Tl[l]
+        P["m_off"] = offs
+        # edge flags
+        def edges(nseg, seglens):
+            e = []
+            for _ in range(nseg):
+                for sl in seglens:
+                    row = [0] * sl
+                    row[0] |= 1; row[-1] |= 2
+                    e.extend(row)
+            return torch.tensor(e, dtype=torch.uint8, device=dev)
+        P["edge_T"] = edges(NB, [T])
+        P["edge_heads"] = edges(B, Tl)
+        # alignment
+        M_al = NB * (T + 1)
+        P["Xv"] = opb(B * T, 2048); P["Xa"] = opb(B * T, 128)
+        P["x0"] = f32(NB * T, C)
+        P["F"] = f32(M_al, C); P["F1"] = f32(M_al, C)
+        P["Fn"] = opb(M_al, C)
+        P["QKV"] = f32(M_al, 3 * C)
+        P["AOa"] = opb(M_al, C)
+        P["Ha"] = opb(M_al, 4 * C)
+        P["Z"] = opb(NB * T, C); P["Y"] = f32(NB * T, C)
+        # stem
+        M0 = NB * T
+        P["E"] = opb(M0, 3 * C)
+        P["e"] = f32(M0, C)
+        P["X"] = f32(M0, C); P["X1"] = f32(M0, C)
+        P["Qin"] = opb(M0, C); P["Kin"] = opb(M0, C); P["Vin"] = opb(M0, C)
+        P["Qp"] = f32(M0, C); P["Kp"] = f32(M0, C); P["Vp"] = f32(M0, C)
+        P["AO"] = opb(M0, C)
+        P["Hn"] = opb(M0, C); P["Hm"] = opb(M0, 4 * C)
+        # pyramid / fusion
+        P["P"] = [None] + [f32(NB * Tl[l], C) for l in range(1, L)]
+        P["TDin"] = [opb(NB * Tl[l], 2 * C) for l in range(L - 1)]
+        P["BUin"] = [None] + [opb(NB * Tl[l], 2 * C) for l in range(1, L)]
+        P["u"] = [f32(NB * Tl[l], C) for l in range(L - 1)] + [None]
+        P["o"] = [None] + [f32(NB * Tl[l], C) for l in range(1, L)]
+        P["h"] = f32(M0, C)
+        P["CAT"] = opb(M0, 3 * C)
+        Ch = C // 2
+        P["c"] = [f32(M0, Ch) for _ in range(3)]
+        P["q2"] = opb(M0, Ch); P["k2"] = opb(M0, Ch); P["v2"] = opb(M0, Ch)
+        P["qp2"] = f32(M0, Ch); P["kp2"] = f32(M0, Ch); P["vp2"] = f32(M0, Ch)
+        P["ao2"] = opb(M0, Ch)
+        P["c3i"] = opb(M0, 3 * Ch)
+        P["gate"] = f32(M0, 8)
+        P["gT"] = opb(NB * C, T)
+        nG = (L - 1) * Ch
+        P["G_td"] = f32(NB * C, nG); P["G_bu"] = f32(NB * C, nG)
+        P["qm"] = f32(M0, C); P["g2"] = f32(M0, C)
+        P["DS"] = opb(NB * Tl[1], 3 * C); P["dconv"] = f32(NB * Tl[1], C)
+        # heads
+        Mh = B * Ttot
+        P["HIN"] = opb(Mh, 3 * 2 * C)
+        P["hc1"] = f32(Mh, 2 * C)
+        P["HC"] = opb(Mh, 3 * C); P["HR"] = opb(Mh, 3 * C)
+        P["hc2"] = f32(Mh, C); P["hr2"] = f32(Mh, C)
+        P["HC2"] = opb(Mh, 3 * C); P["HR2"] = opb(Mh, 3 * C)
+        P["logits"] = f32(Mh, self.ncls); P["offsets"] = f32(Mh, 2 * self.ncls)
+        P["m_heads"] = u8(Mh)
+        P["rowscale"] = f32(Mh)
+        rs = P["rowscale"].view(B, Ttot)
+        for l in range(L):       # Scale_l per row (meta_archs.py:257), constant per plan
+            rs[:, self.level_off[l]:self.level_off[l + 1]] = self.w["hd.scales"][l]
+        pts = []
+        for l in range(L):
+            s = float(self.model.fpn_strides[l])
+            rr = self.model.reg_range[l]
+            for t in range(Tl[l]):
+                pts.append([t * s, float(rr[0]), float(rr[1]), s])
+        P["points"] = torch.tensor(pts, dtype=torch.float32, device=dev)
+        # decode / nms
+        topk = self.model.test_pre_nms_topk
+        P["cap"] = sum(min(topk, Tl[l] * self.ncls) for l in range(L))
+        P["cand_segs"] = f32(B, P["cap"], 2); P["cand_scores"] = f32(B, P["cap"])
+        P["cand_labels"] = torch.zeros(B, P["cap"], dtype=torch.int32, device=dev)
+        Kd = self.model.test_max_seg_num
+        P["out_segs"] = f32(B, Kd, 2); P["out_scores"] = f32(B, Kd)
+        P["out_labels"] = torch.zeros(B, Kd, dtype=torch.int64, device=dev)
+        P["out_counts"] = torch.zeros(B, dtype=torch.int32, device=dev)
+        P["nms_ws"] = torch.zeros(K.softnms_workspace_bytes(B, self.ncls, Kd), dtype=torch.uint8, device=dev)
+        P["graph"] = None
+        self._plans[B] = P
+        return P
+
+    # ------------------------------------------------------------------------------ helpers
+    def _gemm(self, groups, M, N, Kd, act=ACT_NONE, res_masked=False):
+        K.gemm(groups, M, N, Kd, self.op, act, res_masked, self.backend)
+
+    def _mask(self, P, l, kind="true"):
+        """u8 view of the level-l mask over the NB-stacked rows."""
+        NB = 2 * P["B"]
+        o = P["m_off"][l]
+        buf = P["m_true"] if kind == "true" else P["m_up"]
+        return buf[o:o + NB * self.Tl[l]]
+
+    # ------------------------------------------------------------------------------ forward
+    def _launch_all(self, P):
+        w, op, B, T, C, L = self.w, self.op, P["B"], self.T, self.C, self.L
+        NB, Tl, Ttot = 2 * B, self.Tl, self.Ttot
+        N1 = T + 1
+        M0 = NB * T
+        half = B * T                       # rows of one modality in NB-stacked level-0 matrices
+        m0 = self._mask(P, 0)
+
+        # ---- masks: true pyramid masks, up-sampled coarse masks, CLS-extended mask
+        K.build_masks(P["mask_in"], P["m_true"], P["m_up"], P["m_cls"], P["m_heads"], NB, B, T, L)
+
+        # ================================================================== Alignment (:1144-1207)
+        K.transpose_cast(P["visual"], T, P["Xv"], B, 2048, T, op)        # [B,2048,T] -> [B*T,2048]
+        K.transpose_cast(P["audio"], T, P["Xa"], B, 128, T, op)
+        self._gemm([{"A": P["Xv"], "W": w["al.pv"], "bias": w["al.pv.b"], "out_f32": P["x0"][:half]}], half, C, 2048)
+        self._gemm([{"A": P["Xa"], "W": w["al.pa"], "bias": w["al.pa.b"], "out_f32": P["x0"][half:]}], half, C, 128)
+        K.align_embed(P["x0"], w["al.cls_token_video"], w["al.cls_token_text"], w["al.pos_v"], w["al.pos_a"],
+                      w["al.type_video"], w["al.type_text"], P["F"], B, T, C)
+        Ma = NB * N1
+        hm = B * N1                        # rows of one modality in the token matrix
+        F, F1 = P["F"], P["F1"]
+        for _layer in range(self.model.alignment.num_layers):          # same weights twice (:1009)
+            K.layernorm_rows([{"x": F, "w": w["al.n1.w"], "b": w["al.n1.b"], "out_op": P["Fn"]}], Ma, C, op)
+            self._gemm([{"A": P["Fn"], "W": w["al.qkv"], "bias": w["al.qkv.b"], "out_f32": P["QKV"]}], Ma, 3 * C, C)
+            qkv = P["QKV"]
+            groups = []
+            for g in range(2):
+                own, oth = qkv[g * hm:(g + 1) * hm], qkv[(1 - g) * hm:(2 - g) * hm]
+                groups.append({"q": View(own, 0, C), "k": View(own, C, C), "v": View(own, 2 * C, C),
+                               "kmask": P["m_cls"], "xk": View(oth, C, C), "xv": View(oth, 2 * C, C), "x_first": 1,
+                               "out": P["AOa"][g * hm:(g + 1) * hm]})
+            K.attention(groups, B, N1, N1, 8, C // 8, 1.0 / math.sqrt(C // 8), op)
+            self._gemm([{"A": P["AOa"], "W": w["al.m"], "bias": w["al.m.b"], "res": F, "out_f32": F1}], Ma, C, C)
+            K.layernorm_rows([{"x": F1[g * hm:(g + 1) * hm], "w": w[f"al.n2.{mod}.w"], "b": w[f"al.n2.{mod}.b"],
+                               "out_op": P["Fn"][g * hm:(g + 1) * hm]} for g, mod in enumerate(("video", "text"))], hm, C, op)
+            self._gemm([{"A": P["Fn"][g * hm:(g + 1) * hm], "W": w[f"al.fc1.{mod}"], "bias": w[f"al.fc1.{mod}.b"],
+                         "out_op": P["Ha"][g * hm:(g + 1) * hm]} for g, mod in enumerate(("video", "text"))],
+                       hm, 4 * C, C, act=ACT_GELU)
+            self._gemm([{"A": P["Ha"][g * hm:(g + 1) * hm], "W": w[f"al.fc2.{mod}"], "bias": w[f"al.fc2.{mod}.b"],
+                         "res": F1[g * hm:(g + 1) * hm], "out_f32": F[g * hm:(g + 1) * hm]}
+                        for g, mod in enumerate(("video", "text"))], hm, C, 4 * C)
+        # drop CLS, LN(residual + x), Linear -> ReLU -> LN (:1192-1198)
+        K.layernorm_rows([{"x": F[g * hm:(g + 1) * hm], "x_seg_rows": T, "x_seg_stride": N1, "x_row_off": 1,
+                           "add": P["x0"][g * half:(g + 1) * half], "w": w[f"al.nf.{mod}.w"], "b": w[f"al.nf.{mod}.b"],
+                           "out_op": P["Z"][g * half:(g + 1) * half]} for g, mod in enumerate(("video", "text"))], half, C, op)
+        self._gemm([{"A": P["Z"][g * half:(g + 1) * half], "W": w[f"al.fc.{mod}"], "bias": w[f"al.fc.{mod}.b"],
+                     "out_f32": P["Y"][g * half:(g + 1) * half]} for g, mod in enumerate(("video", "text"))],
+                   half, C, C, act=ACT_RELU)
+        K.layernorm_rows([{"x": P["Y"][g * half:(g + 1) * half], "w": w[f"al.fcn.{mod}.w"], "b": w[f"al.fcn.{mod}.b"],
+                           "edge": P["edge_T"][g * half:(g + 1) * half],
+                           "out_im2col": P["E"][g * half:(g + 1) * half]} for g, mod in enumerate(("video", "text"))], half, C, op)
+
+        # ================================================================== backbone stem (:771-807)
+        X, X1 = P["X"], P["X1"]
+        for i in range(2):
+            self._gemm([{"A": P["E"][g * half:(g + 1) * half], "W": w[f"bb.embd{Xm}{i}"], "rowmask": m0[g * half:(g + 1) * half],
+                         "out_f32": P["e"][g * half:(g + 1) * half]} for g, Xm in enumerate("VA")], half, C, 3 * C)
+            grp = []
+            for g, Xm in enumerate("VA"):
+                d = {"x": P["e"][g * half:(g + 1) * half], "w": w[f"bb.embdn{Xm}{i}.w"], "b": w[f"bb.embdn{Xm}{i}.b"]}
+                if i == 0:
+                    d.update({"edge": P["edge_T"][g * half:(g + 1) * half], "out_im2col": P["E"][g * half:(g + 1) * half]})
+                else:   # + pos_embd * mask (:794-802)
+                    d.update({"post": w["bb.pe"], "post_rows": T, "rowmask": m0[g * half:(g + 1) * half],
+                              "out_f32": X[g * half:(g + 1) * half]})
+                grp.append(d)
+            K.layernorm_rows(grp, half, C, op, act=ACT_GELU)
+        n_stem = len(self.model.backbone.self_att_V)
+        for i in range(n_stem):
+            names = [f"bb.sa{Xm}{i}" for Xm in "VA"]
+            # LN11/LN12 -> depthwise conv -> mask -> LN for q (from ln12), k, v (from ln11)   (blocks.py:314, :205-211)
+            K.dwconv_ln([{"x": X[g * half:(g + 1) * half], "mask_out": m0[g * half:(g + 1) * half],
+                          "pre": [(w[nm + ".ln11.w"], w[nm + ".ln11.b"]), (w[nm + ".ln12.w"], w[nm + ".ln12.b"])],
+                          "outs": [{"dw": w[nm + ".attn.query.dw"], "ln_w": w[nm + ".attn.query.nw"], "ln_b": w[nm + ".attn.query.nb"],
+                                    "src": 1, "out_op": P["Qin"][g * half:(g + 1) * half]},
+                                   {"dw": w[nm + ".attn.key.dw"], "ln_w": w[nm + ".attn.key.nw"], "ln_b": w[nm + ".attn.key.nb"],
+                                    "src": 0, "out_op": P["Kin"][g * half:(g + 1) * half]},
+                                   {"dw": w[nm + ".attn.value.dw"], "ln_w": w[nm + ".attn.value.nw"], "ln_b": w[nm + ".attn.value.nb"],
+                                    "src": 0, "out_op": P["Vin"][g * half:(g + 1) * half]}]}
+                         for g, nm in enumerate(names)], B, T, 1, C, op)
+            grp = []
+            for g, nm in enumerate(names):
+                for xin, xout, key in ((P["Qin"], P["Qp"], "query"), (P["Kin"], P["Kp"], "key"), (P["Vin"], P["Vp"], "value")):
+                    grp.append({"A": xin[g * half:(g + 1) * half], "W": w[f"{nm}.attn.{key}"], "bias": w[f"{nm}.attn.{key}.b"],
+                                "out_f32": xout[g * half:(g + 1) * half]})
+            self._gemm(grp, half, C, C)
+            hs = C // self.n_head
+            K.attention([{"q": P["Qp"], "k": P["Kp"], "v": P["Vp"], "kmask": m0, "out": P["AO"]}], NB, T, T, self.n_head, hs,
+                        1.0 / math.sqrt(hs), op)
+            # out = x*mask + scale_attn * (proj(att)*mask)   (blocks.py:243, :316)
+            self._gemm([{"A": P["AO"][g * half:(g + 1) * half], "W": w[nm + ".attn.proj"], "bias": w[nm + ".attn.proj.b"],
+                         "rowmask": m0[g * half:(g + 1) * half], "res": X[g * half:(g + 1) * half], "colscale": w[nm + ".sa"],
+                         "out_f32": X1[g * half:(g + 1) * half]} for g, nm in enumerate(names)], half, C, C, res_masked=True)
+            K.layernorm_rows([{"x": X1[g * half:(g + 1) * half], "w": w[nm + ".ln2.w"], "b": w[nm + ".ln2.b"],
+                               "out_op": P["Hn"][g * half:(g + 1) * half]} for g, nm in enumerate(names)], half, C, op)
+            self._gemm([{"A": P["Hn"][g * half:(g + 1) * half], "W": w[nm + ".mlp0"], "bias": w[nm + ".mlp0.b"],
+                         "out_op": P["Hm"][g * half:(g + 1) * half]} for g, nm in enumerate(names)], half, 4 * C, C, act=ACT_GELU)
+            # out = out + scale_mlp * (mlp(ln2(out)) * mask)   (blocks.py:318)
+            grp = []
+            for g, nm in enumerate(names):
+                d = {"A": P["Hm"][g * half:(g + 1) * half], "W": w[nm + ".mlp3"], "bias": w[nm + ".mlp3.b"],
+                     "rowmask": m0[g * half:(g + 1) * half], "res": X1[g * half:(g + 1) * half], "colscale": w[nm + ".sm"],
+                     "out_f32": X[g * half:(g + 1) * half]}
+                if i == n_stem - 1:        # level-0 pyramid feature straight into the top-down concat operand
+                    d["out_op"] = View(P["TDin"][0], C, C).rows(g * half, (g + 1) * half)
+                grp.append(d)
+            self._gemm(grp, half, C, 4 * C)
+
+        # ================================================================== pyramid (:813-829, shared weights)
+        feats = [X] + P["P"][1:]
+        for l in range(L - 1):
+            o = {"dw": w[f"bb.down{l}.dw"], "ln_w": w[f"bb.down{l}.w"], "ln_b": w[f"bb.down{l}.b"], "out_f32": feats[l + 1]}
+            o["out_op"] = View(P["TDin"][l + 1], C, C) if l + 1 < L - 1 else View(P["BUin"][L - 1], C, C)
+            K.dwconv_ln([{"x": feats[l], "mask_out": self._mask(P, l + 1), "outs": [o]}], NB, Tl[l], 2, C, op)
+
+        # ================================================================== fusion, both passes as one 2B batch (:552-619)
+        # guide of item i = stem output of the other modality: rows rolled by B*T
+        K.transpose_cast(X[half:], C, P["gT"][:B * C], B, T, C, op)      # [B,T,C] -> [B*C, T]
+        K.transpose_cast(X[:half], C, P["gT"][B * C:], B, T, C, op)
+        nG = (L - 1) * (C // 2)
+        self._gemm([{"A": P["gT"], "W": w["fu.td.gfc"], "bias": w["fu.td.gfc.b"], "out_f32": P["G_td"]}], NB * C, nG, T)
+        u = P["u"][:L - 1] + [feats[L - 1]]                                  # u_5 = p_5
+        for idx in range(L - 1, 0, -1):
+            l = idx - 1                                                      # output level
+            K.rowcopy([{"src": u[idx], "dst": View(P["TDin"][l], 0, C), "nseg": NB, "seg_len_in": Tl[idx],
+                        "seg_len_out": Tl[l], "num": 1, "den": 2, "C": C}], op)   # nearest x2 up-sample (:565-566)
+            out_op = View(P["BUin"][l], C, C) if l >= 1 else None
+            self._csp(P, f"fu.td{L - 1 - idx}", P["TDin"][l], P["G_td"], (L - 1 - idx) * (C // 2), self.td_heads[L - 1 - idx],
+                      self._mask(P, l, "up"), l, u[l], out_op)
+        # guide enhancement (:591-600): pooled top-down outputs -> match projection -> query of text_enhancer
+        K.pool_match(u[0], u[1], u[2], Tl[0], Tl[1], Tl[2], w["fu.match.w"], w["fu.match.b"], P["qm"], NB, C, T, 4)
+        te = "fu.te"
+        kv_out = lambda key, buf: {"dw": w[f"{te}.{key}.dw"], "ln_w": w[f"{te}.{key}.nw"], "ln_b": w[f"{te}.{key}.nb"], "out_op": buf}
+        K.dwconv_ln([{"x": X[half:], "mask_out": m0[:half], "outs": [kv_out("key", P["Kin"][:half]), kv_out("value", P["Vin"][:half])]},
+                     {"x": X[:half], "mask_out": m0[half:], "outs": [kv_out("key", P["Kin"][half:]), kv_out("value", P["Vin"][half:])]}],
+                    B, T, 1, C, op)
+        K.dwconv_ln([{"x": P["qm"], "mask_out": m0, "outs": [kv_out("query", P["Qin"])]}], NB, T, 1, C, op)
+        self._gemm([{"A": xin, "W": w[f"{te}.{key}"], "bias": w[f"{te}.{key}.b"], "out_f32": xout}
+                    for xin, xout, key in ((P["Qin"], P["Qp"], "query"), (P["Kin"], P["Kp"], "key"), (P["Vin"], P["Vp"], "value"))],
+                   M0, C, C)
+        hs = C // 4
+        K.attention([{"q": P["Qp"], "k": P["Kp"], "v": P["Vp"], "kmask": m0, "out": P["AO"]}], NB, T, T, 4, hs, 1.0 / math.sqrt(hs), op)
+        self._gemm([{"A": P["AO"], "W": w[f"{te}.proj"], "bias": w[f"{te}.proj.b"], "rowmask": m0, "out_f32": P["g2"]}], M0, C, C)
+        K.transpose_cast(P["g2"], C, P["gT"], NB, T, C, op)
+        self._gemm([{"A": P["gT"], "W": w["fu.bu.gfc"], "bias": w["fu.bu.gfc.b"], "out_f32": P["G_bu"]}], NB * C, nG, T)
+        # bottom-up (:602-612)
+        o = [u[0]] + P["o"][1:]
+        for l in range(L - 1):
+            Mn = NB * Tl[l + 1]
+            mt = self._mask(P, l + 1)
+            K.rowcopy([{"src": o[l], "dst": P["DS"], "nseg": NB, "seg_len_in": Tl[l], "seg_len_out": Tl[l + 1],
+                        "num": 2, "den": 1, "ntaps": 3, "tap_stride": C, "C": C}], op)        # stride-2 im2col
+            self._gemm([{"A": P["DS"], "W": w["fu.ds"], "bias": w["fu.ds.b"], "rowmask": mt, "out_f32": P["dconv"]}], Mn, C, 3 * C)
+            K.layernorm_rows([{"x": P["dconv"], "w": w["fu.dsn.w"], "b": w["fu.dsn.b"], "out_op": View(P["BUin"][l + 1], 0, C)}],
+                             Mn, C, op, act=ACT_SILU)
+            self._csp(P, f"fu.bu{l}", P["BUin"][l + 1], P["G_bu"], l * (C // 2), self.bu_heads[l], mt, l + 1, o[l + 1], None)
+
+        # ================================================================== heads (meta_archs.py:166-178, :245-259)
+        Mh = B * Ttot
+        jobs = []
+        for l in range(L):
+            for m in range(2):         # feats_AV = cat(V, A) along channels (:469)
+                jobs.append({"src": o[l][m * B * Tl[l]:(m + 1) * B * Tl[l]], "dst": View(P["HIN"], m * C, C), "nseg": B,
+                             "seg_len_in": Tl[l], "seg_len_out": Tl[l], "dst_seg_stride": Ttot, "dst_row_off": self.level_off[l],
+                             "ntaps": 3, "tap_stride": 2 * C, "C": C})
+        K.rowcopy(jobs, op)
+        mh = P["m_heads"]
+        self._gemm([{"A": P["HIN"], "W": w["hd.c0"], "rowmask": mh, "out_f32": P["hc1"]}], Mh, 2 * C, 6 * C)
+        K.layernorm_rows([{"x": View(P["hc1"], 0, C), "w": w["hd.cls.n0.w"], "b": w["hd.cls.n0.b"], "edge": P["edge_heads"], "out_im2col": P["HC"]},
+                          {"x": View(P["hc1"], C, C), "w": w["hd.reg.n0.w"], "b": w["hd.reg.n0.b"], "edge": P["edge_heads"], "out_im2col": P["HR"]}],
+                         Mh, C, op, act=ACT_RELU)
+        self._gemm([{"A": P["HC"], "W": w["hd.cls.c1"], "rowmask": mh, "out_f32": P["hc2"]},
+                    {"A": P["HR"], "W": w["hd.reg.c1"], "rowmask": mh, "out_f32": P["hr2"]}], Mh, C, 3 * C)
+        K.layernorm_rows([{"x": P["hc2"], "w": w["hd.cls.n1.w"], "b": w["hd.cls.n1.b"], "edge": P["edge_heads"], "out_im2col": P["HC2"]},
+                          {"x": P["hr2"], "w": w["hd.reg.n1.w"], "b": w["hd.reg.n1.b"], "edge": P["edge_heads"], "out_im2col": P["HR2"]}],
+                         Mh, C, op, act=ACT_RELU)
+        self._gemm([{"A": P["HC2"], "W": w["hd.cls.out"], "bias": w["hd.cls.out.b"], "rowmask": mh, "out_f32": P["logits"]}],
+                   Mh, self.ncls, 3 * C)
+        # offsets = relu(scale_l * (conv * mask))   (:256-257)
+        self._gemm([{"A": P["HR2"], "W": w["hd.reg.out"], "bias": w["hd.reg.out.b"], "rowmask": mh, "rowscale": P["rowscale"],
+                     "out_f32": P["offsets"]}], Mh, 2 * self.ncls, 3 * C, act=ACT_RELU)
+
+        # ================================================================== decode + soft-NMS (meta_archs.py:745-875)
+        md = self.model
+        K.decode(P["logits"], P["offsets"], mh, P["points"], self.level_off, B, self.ncls, md.class_aware,
+                 md.test_pre_nms_thresh, md.test_pre_nms_topk, md.test_duration_thresh, P["cand_segs"], P["cand_scores"],
+                 P["cand_labels"], P["cap"])
+        if md.test_nms_method == "none":
+            raise NotImplementedError("nms_method='none' is not on the hot path")
+        method = 2 if md.test_nms_method == "soft" else 3
+        K.softnms_batched(P["cand_segs"], P["cand_scores"], P["cand_labels"], B, P["cap"], self.ncls, md.test_iou_threshold,
+                          md.test_nms_sigma, md.test_min_score, method, md.test_max_seg_num, Ttot, P["vid_meta"],
+                          P["out_segs"], P["out_scores"], P["out_labels"], P["out_counts"], P["nms_ws"])
+
+    def _csp(self, P, name, xin, G, g_off, heads, mask, l, out_f32, out_op):
+        """MaxSigmoidCSPLayerWithTwoConv.forward (multimodal_backbones.py:243-256) at pyramid level l."""
+        w, op, C = self.w, self.op, self.C
+        NB = 2 * P["B"]
+        Tl = self.Tl[l]
+        M = NB * Tl
+        Ch = C // 2
+        CAT = P["CAT"][:M]
+        h = P["h"][:M]
+        # main 1x1 conv (+bias) * mask; split halves h_a | h_b live in `h`, operand copy in CAT[:, 0:C]
+        self._gemm([{"A": xin, "W": w[name + ".main"], "bias": w[name + ".main.b"], "rowmask": mask, "out_f32": h,
+                     "out_op": View(CAT, 0, C)}], M, C, 2 * C)
+        x = View(h, Ch, Ch)
+        q2, k2, v2 = P["q2"][:M], P["k2"][:M], P["v2"][:M]
+        qp, kp, vp = P["qp2"][:M], P["kp2"][:M], P["vp2"][:M]
+        ao = P["ao2"][:M]
+        for j in range(3):
+            nm = f"{name}.blk{j}"
+            K.dwconv_ln([{"x": x, "mask_out": mask,
+                          "outs": [{"dw": w[f"{nm}.{key}.dw"], "ln_w": w[f"{nm}.{key}.nw"], "ln_b": w[f"{nm}.{key}.nb"], "out_op": buf}
+                                   for key, buf in (("query", q2), ("key", k2), ("value", v2))]}], NB, Tl, 1, Ch, op)
+            self._gemm([{"A": a, "W": w[f"{nm}.{key}"], "bias": w[f"{nm}.{key}.b"], "out_f32": o}
+                        for a, o, key in ((q2, qp, "query"), (k2, kp, "key"), (v2, vp, "value"))], M, Ch, Ch)
+            K.attention([{"q": qp, "k": kp, "v": vp, "kmask": mask, "out": ao}], NB, Tl, Tl, 4, Ch // 4, 1.0 / math.sqrt(Ch // 4), op)
+            cj = P["c"][j][:M]
+            self._gemm([{"A": ao, "W": w[f"{nm}.proj"], "bias": w[f"{nm}.proj.b"], "rowmask": mask, "out_f32": cj,
+                         "out_op": View(CAT, C + j * Ch, Ch)}], M, Ch, Ch)
+            x = cj
+        c3 = P["c"][2][:M]
+        hc = Ch // heads
+        gate = P["gate"].view(-1)[:M * heads].view(M, heads)
+        K.maxsig_gate(c3, View(G, g_off, Ch), w[name + ".hb"], gate, NB, Tl, C, heads, hc)
+        K.rowcopy([{"src": c3, "dst": P["c3i"][:M], "nseg": NB, "seg_len_in": Tl, "seg_len_out": Tl, "ntaps": 3,
+                    "tap_stride": Ch, "C": Ch}], op)
+        self._gemm([{"A": P["c3i"][:M], "W": w[name + ".proj"], "bias": w[name + ".proj.b"], "rowmask": mask, "gate": gate,
+                     "gate_groups": heads, "gate_width": hc, "out_op": View(CAT, C + 3 * Ch, Ch)}], M, Ch, 3 * Ch)
+        d = {"A": CAT, "W": w[name + ".final"], "bias": w[name + ".final.b"], "rowmask": mask, "out_f32": out_f32}
+        if out_op is not None:
+            d["out_op"] = out_op
+        self._gemm([d], M, C, 3 * C)
+
+    # ------------------------------------------------------------------------------ public
+    @torch.no_grad()
+    def run(self, visual: torch.Tensor, audio: torch.Tensor, mask: torch.Tensor, vid_meta: torch.Tensor):
+        """visual [B,2048,T] f32, audio [B,128,T] f32, mask [B,1,T] bool, vid_meta [B,4] f32
+        (feat_stride, feat_num_frames, fps, duration) — any device; copied into the plan's static inputs.
+        Returns the plan dict (device-resident outputs: out_segs/out_scores/out_labels/out_counts, logits, offsets)."""
+        B = visual.shape[0]
+        assert visual.shape[2] == self.T and audio.shape[2] == self.T, "sequence length must equal max_seq_len"
+        P = self._plan(B)
+        with torch.cuda.device(self.dev):
+            P["visual"].copy_(visual, non_blocking=True)
+            P["audio"].copy_(audio, non_blocking=True)
+            P["mask_in"].copy_(mask.reshape(B, self.T), non_blocking=True)
+            P["vid_meta"].copy_(vid_meta, non_blocking=True)
+            if not self.use_graph:
+                self._launch_all(P)
+            else:
+                if P["graph"] is None:
+                    self._launch_all(P)                     # warm-up (sets function attributes, fills constants)
+                    torch.cuda.current_stream().synchronize()
+                    n0 = K.launch_count()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._launch_all(P)
+                    P["launches_per_step"] = K.launch_count() - n0
+                    P["graph"] = g
+                P["graph"].replay()
+        return P

@@ -1,0 +1,276 @@
+"""Thin Python wrappers over the C ABI: torch tensors in, raw device pointers + leading dimensions out.
+
+Every function launches hand-written sm_100a kernels from ``libunav_b200.so`` on torch's *current* CUDA
+stream (so calls can be captured into a CUDA graph).  Tensors are only used as memory handles.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _cabi as A
+from ._cabi import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, BF16, BF16X2, F32, GEMM_SIMT, GEMM_TCGEN05  # noqa: F401
+
+OP_TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, BF16X2: torch.bfloat16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t) -> Optional[int]:
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def _ld(t) -> int:
+    if t is None:
+        return 0
+    if t.dim() == 1:
+        return t.shape[0]
+    assert t.stride(-1) == 1, "innermost dimension must be contiguous"
+    return t.stride(-2)
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def op_cols(K: int, op_dtype: int) -> int:
+    """Physical row length (elements) of an operand buffer with K logical columns."""
+    if op_dtype == F32:
+        return round_up(K, 4)
+    kp = round_up(K, 8)
+    return 2 * kp if op_dtype == BF16X2 else kp
+
+
+def new_operand(rows: int, K: int, op_dtype: int, device) -> torch.Tensor:
+    return torch.zeros(rows, op_cols(K, op_dtype), dtype=OP_TORCH_DTYPE[op_dtype], device=device)
+
+
+def pack_operand(w: torch.Tensor, op_dtype: int) -> torch.Tensor:
+    """[N, K] FP32 -> operand buffer (weight packing at load time; not on the per-batch path)."""
+    N, K = w.shape
+    w = w.detach().float()
+    out = new_operand(N, K, op_dtype, w.device)
+    if op_dtype == F32:
+        out[:, :K] = w
+    else:
+        hi = w.to(torch.bfloat16)
+        out[:, :K] = hi
+        if op_dtype == BF16X2:
+            half = out.shape[1] // 2
+            out[:, half:half + K] = (w - hi.float()).to(torch.bfloat16)
+    return out
+
+
+class View:
+    """A column window of an operand / FP32 buffer: base tensor, first column, (logical) width."""
+
+    __slots__ = ("t", "col", "width")
+
+    def __init__(self, t: torch.Tensor, col: int = 0, width: Optional[int] = None):
+        self.t, self.col = t, col
+        self.width = width if width is not None else t.shape[1] - col
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + self.col * self.t.element_size()
+
+    @property
+    def ld(self) -> int:
+        return self.t.stride(0)
+
+    def rows(self, r0: int, r1: Optional[int] = None) -> "View":
+        return View(self.t[r0:r1], self.col, self.width)
+
+
+def _vp(v) -> Optional[int]:
+    if v is None:
+        return None
+    return v.ptr if isinstance(v, View) else _p(v)
+
+
+def _vld(v) -> int:
+    if v is None:
+        return 0
+    return v.ld if isinstance(v, View) else _ld(v)
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+def gemm(groups: Sequence[dict], M: int, N: int, K: int, op_dtype: int, act: int = ACT_NONE,
+         res_masked: bool = False, backend: int = GEMM_TCGEN05) -> None:
+    """groups: dicts with keys A, W (required) and bias, rowmask, rowscale, gate, gate_groups, gate_width,
+    res, colscale, out_f32, out_op (tensors or Views)."""
+    n = len(groups)
+    arr = (A.GemmGroup * n)()
+    for i, g in enumerate(groups):
+        s = arr[i]
+        s.A, s.lda = _vp(g["A"]), _vld(g["A"])
+        s.W, s.ldw = _vp(g["W"]), _vld(g["W"])
+        s.bias = _vp(g.get("bias"))
+        s.rowmask = _vp(g.get("rowmask"))
+        s.rowscale = _vp(g.get("rowscale"))
+        s.gate = _vp(g.get("gate"))
+        s.gate_groups = g.get("gate_groups", 1)
+        s.gate_width = g.get("gate_width", 1)
+        s.res, s.ldres = _vp(g.get("res")), _vld(g.get("res"))
+        s.colscale = _vp(g.get("colscale"))
+        s.out_f32, s.ld_f32 = _vp(g.get("out_f32")), _vld(g.get("out_f32"))
+        s.out_op, s.ld_op = _vp(g.get("out_op")), _vld(g.get("out_op"))
+    lib = A.load()
+    A.check(lib.unav_gemm(arr, n, M, N, K, op_dtype, act, int(res_masked), backend, _stream()), "unav_gemm")
+
+
+# -------------------------------------------------------------------------------------- LayerNorm
+def layernorm_rows(groups: Sequence[dict], M: int, C_: int, op_dtype: int, act: int = ACT_NONE,
+                   eps: float = 1e-5) -> None:
+    n = len(groups)
+    arr = (A.LnGroup * n)()
+    for i, g in enumerate(groups):
+        s = arr[i]
+        s.x, s.ldx = _vp(g["x"]), _vld(g["x"])
+        s.add, s.ldadd = _vp(g.get("add")), _vld(g.get("add"))
+        s.w, s.b = _p(g["w"]), _p(g["b"])
+        s.post = _p(g.get("post"))
+        s.post_rows = g.get("post_rows", 0)
+        s.rowmask = _p(g.get("rowmask"))
+        s.edge = _p(g.get("edge"))
+        s.out_f32, s.ld_f32 = _vp(g.get("out_f32")), _vld(g.get("out_f32"))
+        s.out_op, s.ld_op = _vp(g.get("out_op")), _vld(g.get("out_op"))
+        s.out_im2col, s.ld_im2col = _vp(g.get("out_im2col")), _vld(g.get("out_im2col"))
+        s.x_seg_rows = g.get("x_seg_rows", 0)
+        s.x_seg_stride = g.get("x_seg_stride", 0)
+        s.x_row_off = g.get("x_row_off", 0)
+    lib = A.load()
+    A.check(lib.unav_layernorm_rows(arr, n, M, C_, eps, act, op_dtype, _stream()), "unav_layernorm_rows")
+
+
+# ---------------------------------------------------------------------------- depthwise conv + LN
+def dwconv_ln(groups: Sequence[dict], nseg: int, seg_len_in: int, stride: int, C_: int, op_dtype: int,
+              eps: float = 1e-5) -> None:
+    """groups: dicts with x, mask_out, pre (list of (w, b), <= 2) and outs (list of dicts: dw, ln_w, ln_b,
+    src, out_f32, out_op)."""
+    n = len(groups)
+    arr = (A.DwLnGroup * n)()
+    n_pre = len(groups[0].get("pre", []))
+    n_out = len(groups[0]["outs"])
+    for i, g in enumerate(groups):
+        s = arr[i]
+        s.x, s.ldx = _vp(g["x"]), _vld(g["x"])
+        s.mask_out = _p(g.get("mask_out"))
+        for j, (w, b) in enumerate(g.get("pre", [])):
+            s.pre_w[j], s.pre_b[j] = _p(w), _p(b)
+        assert len(g["outs"]) == n_out and len(g.get("pre", [])) == n_pre
+        for j, o in enumerate(g["outs"]):
+            d = s.out[j]
+            d.dw, d.ln_w, d.ln_b = _p(o["dw"]), _p(o["ln_w"]), _p(o["ln_b"])
+            d.src = o.get("src", -1)
+            d.out_f32, d.ld_f32 = _vp(o.get("out_f32")), _vld(o.get("out_f32"))
+            d.out_op, d.ld_op = _vp(o.get("out_op")), _vld(o.get("out_op"))
+    lib = A.load()
+    A.check(lib.unav_dwconv_ln(arr, n, nseg, seg_len_in, stride, C_, n_pre, n_out, eps, op_dtype, _stream()),
+            "unav_dwconv_ln")
+
+
+# -------------------------------------------------------------------------------------- attention
+def attention(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs: int, scale: float,
+              op_dtype: int) -> None:
+    n = len(groups)
+    arr = (A.AttnGroup * n)()
+    for i, g in enumerate(groups):
+        s = arr[i]
+        s.q, s.ldq = _vp(g["q"]), _vld(g["q"])
+        s.k, s.ldk = _vp(g["k"]), _vld(g["k"])
+        s.v, s.ldv = _vp(g["v"]), _vld(g["v"])
+        s.kmask = _p(g.get("kmask"))
+        s.xk, s.xv = _vp(g.get("xk")), _vp(g.get("xv"))
+        s.ldx = _vld(g.get("xk"))
+        s.x_first = g.get("x_first", 0)
+        s.out, s.ldo = _vp(g["out"]), _vld(g["out"])
+    lib = A.load()
+    A.check(lib.unav_attention(arr, n, nb, Tq, Tk, nh, hs, scale, op_dtype, _stream()), "unav_attention")
+
+
+def maxsig_gate(x, G, head_bias, gate, nb: int, T: int, nwords: int, H: int, hc: int) -> None:
+    lib = A.load()
+    A.check(lib.unav_maxsig_gate(_vp(x), _vld(x), _vp(G), _vld(G), _p(head_bias), _p(gate), nb, T, nwords, H,
+                                 hc, _stream()), "unav_maxsig_gate")
+
+
+def pool_match(u0, u1, u2, T0: int, T1: int, T2: int, Wm, bm, q, nb: int, C_: int, Tq: int, P: int = 4) -> None:
+    lib = A.load()
+    A.check(lib.unav_pool_match(_p(u0), _p(u1), _p(u2), T0, T1, T2, _ld(u0), _p(Wm), _p(bm), _p(q), _ld(q), nb,
+                                C_, Tq, P, _stream()), "unav_pool_match")
+
+
+def rowcopy(jobs: Sequence[dict], op_dtype: int) -> None:
+    n = len(jobs)
+    arr = (A.CopyJob * n)()
+    for i, j in enumerate(jobs):
+        s = arr[i]
+        s.src, s.ld_src = _vp(j["src"]), _vld(j["src"])
+        s.dst, s.ld_dst = _vp(j["dst"]), _vld(j["dst"])
+        s.nseg, s.seg_len_in, s.seg_len_out = j["nseg"], j["seg_len_in"], j["seg_len_out"]
+        s.dst_seg_stride = j.get("dst_seg_stride", j["seg_len_out"])
+        s.dst_row_off = j.get("dst_row_off", 0)
+        s.num, s.den = j.get("num", 1), j.get("den", 1)
+        s.ntaps = j.get("ntaps", 1)
+        s.tap_stride = j.get("tap_stride", j["C"])
+        s.C = j["C"]
+    lib = A.load()
+    A.check(lib.unav_rowcopy(arr, n, op_dtype, _stream()), "unav_rowcopy")
+
+
+def transpose_cast(inp, ld_in: int, out, nb: int, R: int, Cc: int, op_dtype: int) -> None:
+    lib = A.load()
+    A.check(lib.unav_transpose_cast(_vp(inp), ld_in, _vp(out), _vld(out), nb, R, Cc, op_dtype, _stream()),
+            "unav_transpose_cast")
+
+
+def align_embed(x0, cls_v, cls_a, pos_v, pos_a, type_v, type_a, tokens, nb: int, T: int, C_: int) -> None:
+    lib = A.load()
+    A.check(lib.unav_align_embed(_p(x0), _p(cls_v), _p(cls_a), _p(pos_v), _p(pos_a), _p(type_v), _p(type_a),
+                                 _p(tokens), nb, T, C_, _stream()), "unav_align_embed")
+
+
+def build_masks(mask, out_true, out_up, out_cls, out_heads, nb: int, nb_src: int, T: int, L: int) -> None:
+    lib = A.load()
+    A.check(lib.unav_build_masks(_p(mask), _p(out_true), _p(out_up), _p(out_cls), _p(out_heads), nb, nb_src, T, L,
+                                 _stream()),
+            "unav_build_masks")
+
+
+def decode(logits, offsets, masks, points, level_off: List[int], B: int, ncls: int, class_aware: bool,
+           pre_nms_thresh: float, pre_nms_topk: int, duration_thresh: float, cand_segs, cand_scores,
+           cand_labels, cap: int) -> None:
+    L = len(level_off) - 1
+    arr = (C.c_int * (L + 1))(*level_off)
+    lib = A.load()
+    A.check(lib.unav_decode(_p(logits), _p(offsets), _p(masks), _p(points), arr, B, L, ncls, int(class_aware),
+                            pre_nms_thresh, pre_nms_topk, duration_thresh, _p(cand_segs), _p(cand_scores),
+                            _p(cand_labels), cap, _stream()), "unav_decode")
+
+
+def softnms_workspace_bytes(B: int, ncls: int, max_seg_num: int) -> int:
+    return int(A.load().unav_softnms_workspace_bytes(B, ncls, max_seg_num))
+
+
+def softnms_batched(cand_segs, cand_scores, cand_labels, B: int, cap: int, ncls: int, iou_threshold: float,
+                    sigma: float, min_score: float, method: int, max_seg_num: int, max_per_class: int,
+                    vid_meta, out_segs, out_scores, out_labels, out_counts, workspace) -> None:
+    lib = A.load()
+    A.check(lib.unav_softnms_batched(_p(cand_segs), _p(cand_scores), _p(cand_labels), B, cap, ncls,
+                                     iou_threshold, sigma, min_score, method, max_seg_num, max_per_class,
+                                     _p(vid_meta), _p(out_segs), _p(out_scores), _p(out_labels),
+                                     _p(out_counts), _p(workspace), workspace.numel() * workspace.element_size(),
+                                     _stream()), "unav_softnms_batched")
+
+
+def launch_count() -> int:
+    return int(A.load().unav_launch_count())

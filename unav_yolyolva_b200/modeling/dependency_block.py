@@ -1,0 +1,30 @@
+"""``DependencyBlock`` registry entry (/root/reference/libs/modeling/dependency_block.py:6-70).
+
+The block is disabled in both reference configs (``use_dependency: False``,
+configs/avel_unav100.yaml:15) and is listed as "next" in SURVEY.md §8(f) rank 3.  The class keeps the
+constructor and parameter names so that a ``use_dependency=True`` checkpoint loads; its forward is not
+implemented on the CUDA path yet and says so loudly.
+"""
+from torch import nn
+
+from .blocks import MaskedConv1D, TransformerBlock
+from .models import register_dependency_block
+
+
+@register_dependency_block("DependencyBlock")
+class Dependency_Block(nn.Module):
+    def __init__(self, in_channel, n_embd, n_embd_ks, num_classes, path_pdrop, n_head=1):
+        super().__init__()
+        self.num_classes = num_classes
+        self.relu = nn.ReLU(inplace=True)
+        self.feature_expand = MaskedConv1D(in_channel, n_embd * num_classes, n_embd_ks, stride=1,
+                                           padding=n_embd_ks // 2, bias=False)
+        self.cooccur_branch = TransformerBlock(n_embd, n_head, n_hidden=n_embd, path_pdrop=path_pdrop)
+        self.temporal_branch = TransformerBlock(n_embd, n_head, n_hidden=n_embd, path_pdrop=path_pdrop)
+        self.feature_squeeze = MaskedConv1D(n_embd * num_classes, in_channel, n_embd_ks, stride=1,
+                                            padding=n_embd_ks // 2, bias=False)
+
+    def forward(self, fpn_feats, fpn_masks):
+        raise NotImplementedError(
+            "Dependency_Block.forward is not on the B200 hot path yet (use_dependency=False in the reference "
+            "configs; SURVEY.md §8f rank 3)")

@@ -1,0 +1,4 @@
+"""``libs.utils`` operator surface on the hot path (/root/reference/libs/utils/__init__.py:1)."""
+from .nms import batched_nms
+
+__all__ = ["batched_nms"]
