@@ -64,7 +64,8 @@ def _run(cuda, M, N, Kd, op, backend, act=K.ACT_NONE, full_epi=False, groups=1, 
     torch.cuda.synchronize()
     for (out, out_op), ref in zip(outs, refs):
         scale = ref.abs().max().item() + 1e-6
-        tol = 2e-5 if op != K.BF16 or backend == K.GEMM_SIMT else 2e-5
+        # BF16X2 on tcgen05 drops the lo.lo term (3 of 4 partial products): ~2^-17 relative per product
+        tol = 6e-5 if (op == K.BF16X2 and backend == K.GEMM_TCGEN05) else 2e-5
         err = (out.cpu() - ref).abs().max().item() / scale
         assert err < tol, f"out_f32 err {err}"
         if op == K.F32:
@@ -74,7 +75,7 @@ def _run(cuda, M, N, Kd, op, backend, act=K.ACT_NONE, full_epi=False, groups=1, 
             got = out_op[:, :N].float().cpu()
             if op == K.BF16X2:
                 got = got + out_op[:, half:half + N].float().cpu()
-        tol_op = 1e-5 if op != K.BF16 else 5e-3
+        tol_op = (6e-5 if backend == K.GEMM_TCGEN05 else 1e-5) if op != K.BF16 else 5e-3
         assert (got - ref).abs().max().item() / scale < tol_op
 
 

@@ -24,15 +24,11 @@ def batched_nms(segs, scores, cls_idxs, iou_threshold, min_score, max_seg_num, u
     dev = in_dev if in_dev.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
     segs_d = segs.detach().to(dev, torch.float32).contiguous()
     scores_d = scores.detach().to(dev, torch.float32).contiguous()
-    if multiclass:
-        labels_d = cls_idxs.detach().to(dev, torch.int32).contiguous()
-        ncls = int(cls_idxs.max().item()) + 1
-    else:
-        if voting_thresh > 0:
-            raise NotImplementedError("class-agnostic seg voting (nms.py:67-101) is not on the hot path "
-                                      "(multiclass_nms=True in the reference configs)")
-        labels_d = torch.zeros(num_segs, dtype=torch.int32, device=dev)
-        ncls = 1
+    if not multiclass:
+        raise NotImplementedError("class-agnostic NMS + seg voting (nms.py:67-101, :161-180) is not on the hot "
+                                  "path: multiclass_nms=True in the reference configs")
+    labels_d = cls_idxs.detach().to(dev, torch.int32).contiguous()
+    ncls = int(cls_idxs.max().item()) + 1
     K_out = int(max_seg_num)
     out_segs = torch.empty(1, K_out, 2, dtype=torch.float32, device=dev)
     out_scores = torch.empty(1, K_out, dtype=torch.float32, device=dev)
@@ -46,6 +42,4 @@ def batched_nms(segs, scores, cls_idxs, iou_threshold, min_score, max_seg_num, u
                           ws)
     n = int(out_counts.item())
     r_segs, r_scores, r_labels = out_segs[0, :n], out_scores[0, :n], out_labels[0, :n]
-    if not multiclass:
-        r_labels = cls_idxs.new_zeros(n) if n else r_labels
     return r_segs.to(in_dev), r_scores.to(in_dev), r_labels.to(in_dev, cls_idxs.dtype)
