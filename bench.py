@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Headline benchmark: videos/s of the PtTransformer inference hot path (Alignment + backbone + heads + decode
++ per-class soft-NMS + seconds) on synthetic avel_unav100 batches, B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bf16x3|bf16|fp32] [--batch 16]
+
+A step = one pass of the hot path over one batch of `--batch` (default 16 = BASELINE.json configs[1]) synthetic
+videos (T=224, random-init "trained-like" weights, see unav_yolyolva_b200/synth.py).  One JSON line on rank 0:
+
+  value        videos/s, inputs already resident in HBM, CUDA-graph replay of the whole path (device timed)
+  e2e          videos/s through the public API `model(batch)` with PINNED HOST inputs (H2D inside the timed region)
+               and a D2H read of the detections every step
+  roofline     the kernel class with the largest share of the step, timed live with CUDA events
+  cpu_baseline the oracle port (PyTorch FP32 restatement + the reference's compiled nms_1d_cpu / the C oracle)
+               on this box's host cores, bounded sample
+  --impl reference   times that same CPU path as the reference arm (no GPU work)
+
+N > 1 (torchrun): every rank runs its own replica on its own shard (weak scaling: per-GPU work fixed); the only
+collective is one all-gather of the detections at the end of the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "videos_per_sec_inference_plus_softnms"
+UNIT = "videos/s"
+GFLOP_PER_VIDEO = 29.1          # SURVEY.md §8d, T=224, loss-only heads excluded
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step(sd, batch, use_ref_ext):
+    """The reference's CPU path, restated (oracle/model_ref.py) + its own compiled NMS where available."""
+    import numpy as np
+    import torch
+    from oracle import model_ref as R
+    from oracle import nms_ref
+    from unav_yolyolva_b200.config import TEST_CFG
+    with torch.no_grad():
+        logits, offsets, masks = R.forward_logits(sd, batch["visual"], batch["audio"], batch["mask"])
+        pts = R.make_points(batch["visual"].shape[-1])
+        out = []
+        for i in range(batch["visual"].shape[0]):
+            segs, scores, labels, _ = R.decode_single_video(pts, [m[i] for m in masks], [x[i] for x in logits], [x[i] for x in offsets],
+                                                            stable=False)
+            if use_ref_ext is not None:
+                out.append(_ref_batched_nms(use_ref_ext, segs, scores, labels, TEST_CFG))
+            else:
+                out.append(nms_ref.batched_nms(segs.numpy(), scores.numpy(), labels.numpy(), TEST_CFG["iou_threshold"],
+                                               TEST_CFG["min_score"], TEST_CFG["max_seg_num"], True, TEST_CFG["nms_sigma"]))
+    return out
+
+
+def _ref_batched_nms(ext, segs, scores, labels, tc):
+    """Per-class loop over the reference's compiled extension (what libs/utils/nms.py:126-159 does)."""
+    import torch
+    outs = []
+    for c in torch.unique(labels):
+        idx = torch.where(labels == c)[0]
+        s, sc = segs[idx].contiguous(), scores[idx].contiguous()
+        dets = torch.empty(s.shape[0], 3)
+        inds = ext.softnms(s, sc, dets, iou_threshold=float(tc["iou_threshold"]), sigma=float(tc["nms_sigma"]),
+                           min_score=float(tc["min_score"]), method=2)
+        n = min(len(inds), tc["max_seg_num"])
+        outs.append(dets[:n])
+    allc = torch.cat(outs)
+    _, order = allc[:, 2].sort(descending=True)
+    return allc[order[:tc["max_seg_num"]]]
+
+
+def run_cpu_arm(batch_size, steps, warmup):
+    import torch
+    from oracle.ref_harness import load_ref_nms
+    from unav_yolyolva_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.trained_like_state_dict()
+    ext = load_ref_nms()
+    batches = [synth.make_batch(batch_size, 224, first_index=i * batch_size, with_gt=False) for i in range(2)]
+    for i in range(warmup):
+        cpu_reference_step(sd, batches[i % 2], ext)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cpu_reference_step(sd, batches[i % 2], ext)
+    dt = time.perf_counter() - t0
+    return {"value": batch_size * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": cores,
+            "kind": "port", "nms": "reference nms_1d_cpu (oracle/_ref)" if ext is not None else "oracle/nms_ref.c",
+            "sample": f"{steps} batches of {batch_size} videos after {warmup} warm-up, torch FP32 oracle port, {cores} threads"}
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace-out", default=None, help="write the per-launch CUDA-event trace of one eager pass (JSON)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"avel_unav100 inference batch {args.batch}, T=224, 6 FPN levels, full decode + soft-NMS (configs[1])",
+              "batch_per_gpu": args.batch, "seq_len": 224, "precision_mode": args.mode}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 5))
+        r = run_cpu_arm(args.batch, steps, min(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+                "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(config, precision_mode="fp32 (CPU)"),
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "nms": r["nms"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from unav_yolyolva_b200 import kernels as K
+    from unav_yolyolva_b200 import runner, synth
+    from unav_yolyolva_b200.config import default_model_cfg
+    from unav_yolyolva_b200.modeling import make_multimodal_meta_arch
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, Kst, W = args.batch, args.steps, max(args.warmup, 3)
+    model = make_multimodal_meta_arch("LocPointTransformer", **default_model_cfg())
+    model.load_state_dict(synth.trained_like_state_dict(), strict=True)
+    model = model.to(dev).eval()
+    model.precision = args.mode
+    model.use_cuda_graph = True
+
+    # each rank owns a different shard of the synthetic video stream (video index = global)
+    n_rot = 4
+    host_batches = []
+    for j in range(n_rot):
+        b = synth.make_batch(B, 224, first_index=(j * world + rank) * B, with_gt=False)
+        for k in ("visual", "audio", "mask"):
+            b[k] = b[k].pin_memory()
+        host_batches.append(b)
+    dev_inputs = [(b["visual"].to(dev), b["audio"].to(dev), b["mask"].to(dev)) for b in host_batches]
+    meta = [torch.tensor([[float(b["feat_stride"][i]), float(b["feat_num_frames"][i]), float(b["fps"][i]), float(b["duration"][i])]
+                          for i in range(B)], dtype=torch.float32, device=dev) for b in host_batches]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
+
+    eng = model.engine
+    plan = eng.run(*dev_inputs[0], meta[0])            # builds buffers, captures the graph
+    torch.cuda.synchronize()
+    launches_per_step = plan.get("launches_per_step", 0)
+
+    def device_step(j):
+        eng.run(*dev_inputs[j % n_rot], meta[j % n_rot])
+
+    # ---------------- value: device-resident inputs
+    for j in range(W):
+        device_step(j)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kst)]
+    all_dets = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for j in range(Kst):
+        flush.zero_()                                   # L2 flush, outside the timed events
+        ev[j][0].record()
+        device_step(j)
+        ev[j][1].record()
+        all_dets.append(runner.pack_detections(plan["out_segs"], plan["out_scores"], plan["out_labels"]).clone())
+    ga = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ga[0].record()
+    local = torch.cat(all_dets)
+    # global video id of row i of step j on this rank: unique across steps and ranks
+    vid_index = torch.cat([torch.arange(B, device=dev) + (j * world + rank) * B for j in range(Kst)])
+    gathered, valid = runner.gather_detections(local, vid_index, Kst * world * B)
+    ga[1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev) + ga[0].elapsed_time(ga[1])
+    t = torch.tensor([dev_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = world * B * Kst / (dev_ms / 1e3)
+
+    # ---------------- e2e: pinned host inputs -> model(batch) -> detections on the host
+    def e2e_step(j):
+        res, _ = model(host_batches[j % n_rot])
+        return res["segments"].cpu(), res["scores"].cpu(), res["labels"].cpu()
+
+    for j in range(W):
+        e2e_step(j)
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kst)]
+    for j in range(Kst):
+        flush.zero_()
+        ev2[j][0].record()
+        out = e2e_step(j)
+        ev2[j][1].record()
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    hb = host_batches[0]
+    h2d = sum(hb[k].numel() * hb[k].element_size() for k in ("visual", "audio", "mask")) + B * 16
+    d2h = sum(o.numel() * o.element_size() for o in out) + B * 4
+    e2e = {"value": world * B * Kst / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_ms / Kst}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel class (eager pass with CUDA events around every launch)
+    peaks = load_peaks()
+    model.use_cuda_graph = False
+    eng_eager = model.engine
+    eng_eager.run(*dev_inputs[0], meta[0])
+    torch.cuda.synchronize()
+    agg = {}
+    reps = 3
+    for rep in range(reps):
+        flush.zero_()
+        K.start_trace()
+        eng_eager.run(*dev_inputs[1], meta[1])
+        tr = K.stop_trace()
+        if args.trace_out and rep == reps - 1:
+            with open(args.trace_out, "w") as f:
+                json.dump([{"kernel": n, "us": ms * 1e3, "flops": fl, "bytes": by, "shape": note} for n, ms, fl, by, note in tr], f)
+        for name, ms, fl, by, note in tr:
+            a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+            a[0] += ms; a[1] += fl; a[2] += by; a[3] += 1
+    tot_ms = sum(a[0] for a in agg.values())
+    shares = {k: round(a[0] / tot_ms, 4) for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+    top = max(agg, key=lambda k: agg[k][0])
+    a = agg[top]
+    if a[1] > 0:   # FLOP-carrying kernel class: tensor roofline (algorithmic FLOPs / summed launch time)
+        ach = a[1] / (a[0] / 1e3) / 1e12
+        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tf_sustained"], "traffic": None}
+    else:
+        ach = a[2] / (a[0] / 1e3) / 1e9
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None}
+    roof.update({"peak_source": peaks["source"], "launches_timed": a[3] // reps, "avg_launch_us": a[0] / a[3] * 1e3,
+                 "share_of_step": shares[top], "kernel_time_shares": shares,
+                 "whole_path_tflops": GFLOP_PER_VIDEO * 1e9 * value / world / 1e12,
+                 "whole_path_frac_of_bf16_sustained": GFLOP_PER_VIDEO * 1e9 * value / world / 1e12 / peaks["tf_sustained"]})
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = run_cpu_arm(B, 3, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "nms": r["nms"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Kst, "warmup": W,
+            "ms_per_step": dev_ms / Kst, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.mode != "fp32" else "f32", "data": "synthetic",
+            "config": dict(config, parallelism=f"dp{world} (videos sharded by index, one all-gather of detections)",
+                           l2="256 MiB memset between steps (outside the timed events)",
+                           gathered_videos=int(valid.sum().item())),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * Kst, "launches_per_step": launches_per_step,
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

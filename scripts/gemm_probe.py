@@ -1,0 +1,30 @@
+"""Launch a list of hot-path GEMM shapes through the C ABI (for ncu): python scripts/gemm_probe.py [shape-index]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from unav_yolyolva_b200 import kernels as K
+
+SHAPES = [(2, 3584, 2048, 512, K.ACT_GELU), (1, 448, 256, 256, 0), (6, 3584, 512, 512, 0), (1, 7056, 1024, 3072, 0),
+          (3, 3584, 256, 256, 0), (1, 16384, 1280, 224, 0), (2, 3584, 512, 2048, 0)]
+dev = torch.device("cuda", 0)
+only = int(sys.argv[1]) if len(sys.argv) > 1 else None
+op = K.BF16X2 if (len(sys.argv) < 3 or sys.argv[2] == "x3") else K.BF16
+for si, (G, M, N, Kd, act) in enumerate(SHAPES):
+    if only is not None and si != only:
+        continue
+    groups = []
+    for g in range(G):
+        A = K.new_operand(M, Kd, op, dev); A.normal_()
+        W = K.new_operand(N, Kd, op, dev); W.normal_()
+        groups.append({"A": A, "W": W, "bias": torch.zeros(N, device=dev), "out_f32": torch.empty(M, N, device=dev),
+                       "out_op": K.new_operand(M, N, op, dev)})
+    for _ in range(3):
+        K.gemm(groups, M, N, Kd, op, act, False, K.GEMM_TCGEN05)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        K.gemm(groups, M, N, Kd, op, act, False, K.GEMM_TCGEN05)
+    b.record(); torch.cuda.synchronize()
+    us = a.elapsed_time(b) / 20 * 1e3
+    print(f"{G}x[{M},{N},{Kd}] act={act} {us:8.1f} us/launch  {2.0*G*M*N*Kd/us/1e6:7.1f} TF/s alg", flush=True)

@@ -9,8 +9,11 @@
 //               k-block into a 4-stage ring, completion on mbarriers (complete_tx::bytes)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16),
 //               tcgen05.commit releases ring slots / signals the accumulator
-//   warps 2..5  epilogue: tcgen05.ld 32x32b (one accumulator row per thread), bias / mask / gate /
-//               activation / scaled residual, FP32 and/or BF16(-split) stores
+//   warps 2..9  epilogue: tcgen05.ld 32x32b (one accumulator row per thread) -> smem staging tile -> row-
+//               contiguous bias / mask / gate / activation / scaled residual, FP32 and/or BF16(-split) stores
+// Two CTAs are resident per SM (3 stages, <= 102 registers) so that one CTA's epilogue overlaps the other's
+// mainloop; the first ncu capture showed the 4-warp, 1-CTA/SM version spending ~3x longer in the epilogue
+// than in the k-loop (profiles/r01_gemm_epilogue.md).
 //
 // Split mode (UNAV_BF16X2 operands): rows hold hi = bf16(x) and lo = bf16(x - hi) at column ld/2; the
 // k-loop runs three segments (Ahi,Whi), (Alo,Whi), (Ahi,Wlo) into the same TMEM accumulator, which
@@ -24,8 +27,8 @@ namespace unav {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B span
-constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_STAGES = 3;          // 3 x 32 KB (BN = 128): two CTAs per SM, one's epilogue overlaps the other's mainloop
+constexpr int TC_THREADS = 320;       // TMA warp + MMA warp + 8 epilogue warps
 constexpr long long TC_SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks, then trap instead of hanging
 
 struct TcGroup {
@@ -129,7 +132,7 @@ struct TcSmem {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const TcGroup& g = p.g[blockIdx.z];
@@ -204,69 +207,101 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       tc_commit(accum_bar);             // accumulator complete
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-    const int q = warp & 3;
-    const long long m = static_cast<long long>(m0) + q * 32 + lane;
+    // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+    // Phase A: tcgen05.ld (one accumulator row per thread) -> padded FP32 staging tile in the (now idle)
+    //          pipeline smem; phase B: each warp walks its 32 rows x BN/2 columns with lanes across columns, so
+    //          residual loads and all stores are row-contiguous 128-bit accesses.  Eight warps (two per
+    //          scheduler) and two rows in flight per lane hide the ALU / memory latency of the epilogue math.
+    constexpr int PITCH = BN + 4;              // floats; 16-byte groups of consecutive rows fall in distinct banks
+    constexpr int HALF = BN / 2;               // columns per warp
+    constexpr int LPR = HALF / 4;              // lanes per row in phase B (16 | 8)
+    constexpr int RPP = 32 / LPR;              // rows per pass (2 | 4)
+    const int q = warp & 3, half = (warp - 2) >> 2;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const EpiParams& e = g.epi;
-    const bool row_ok = m < p.M;
-    float mk = 1.f, rs = 1.f;
-    if (row_ok) {
-      if (e.rowmask) mk = e.rowmask[m] ? 1.f : 0.f;
-      if (e.rowscale) rs = e.rowscale[m];
-    }
-    const size_t es = 2;
-    const long long op_split = e.ld_op / 2;
+    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * 32 * PITCH + half * HALF;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = 0; c < HALF / 32; ++c) {
       uint32_t r[32];
-      tc_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      tc_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * HALF + c * 32, r);
       tc_wait_ld();
-      const int nb = n0 + c * 32;
-      if (!row_ok || nb >= p.N) continue;
-      float v[32];
+      float* dst = stg + lane * PITCH + c * 32;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = nb + j;
-        float x = __uint_as_float(r[j]);
-        if (n < p.N) {
-          if (e.bias) x += __ldg(e.bias + n);
-          x *= mk;
-          x *= rs;
-          if (e.gate) x *= __ldg(e.gate + m * e.gate_groups + n / e.gate_width);
-          x = apply_act(x, p.act);
-          if (e.res) {
-            float rr = e.res[m * e.ldres + n];
-            if (p.res_masked) rr *= mk;
-            const float cs = e.colscale ? __ldg(e.colscale + n) : 1.f;
-            x = rr + cs * x;
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    }
+    __syncwarp();
+    const EpiParams& e = g.epi;
+    const int cl = lane % LPR, rsub = lane / LPR;
+    const int n = n0 + half * HALF + cl * 4;
+    const int nvalid = min(4, p.N - n);        // <= 0: this lane's columns are past N
+    const long long op_split = e.ld_op / 2;
+    const bool has_res = e.res != nullptr, has_gate = e.gate != nullptr;
+    const int act = p.act;
+    float bias[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < nvalid) {
+        if (e.bias) bias[i] = __ldg(e.bias + n + i);
+        if (e.colscale) cs[i] = __ldg(e.colscale + n + i);
+      }
+    }
+    const bool vec_f32 = nvalid == 4 && e.out_f32 && ((reinterpret_cast<uintptr_t>(e.out_f32 + n) & 15) == 0) && (e.ld_f32 % 4 == 0);
+    const bool vec_res = nvalid == 4 && has_res && ((reinterpret_cast<uintptr_t>(e.res + n) & 15) == 0) && (e.ldres % 4 == 0);
+    const bool vec_op = nvalid == 4 && e.out_op && (((reinterpret_cast<uintptr_t>(e.out_op) + static_cast<size_t>(n) * 2) & 7) == 0) &&
+                        (e.ld_op % 4 == 0) && (op_split % 4 == 0);
+    if (nvalid > 0) {
+#pragma unroll 2
+      for (int r = rsub; r < 32; r += RPP) {
+        const long long m = static_cast<long long>(m0) + q * 32 + r;
+        if (m >= p.M) break;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * PITCH + cl * 4);
+        float v[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float mk = e.rowmask ? (e.rowmask[m] ? 1.f : 0.f) : 1.f;
+        const float rs = e.rowscale ? __ldg(e.rowscale + m) : 1.f;
+        const float mrs = mk * rs;
+        float rr[4] = {0.f, 0.f, 0.f, 0.f};
+        if (has_res) {
+          const float* rp = e.res + m * e.ldres + n;
+          if (vec_res) {
+            const float4 t = *reinterpret_cast<const float4*>(rp);
+            rr[0] = t.x; rr[1] = t.y; rr[2] = t.z; rr[3] = t.w;
+          } else {
+            for (int i = 0; i < nvalid; ++i) rr[i] = rp[i];
           }
         }
-        v[j] = x;
-      }
-      const bool full = nb + 32 <= p.N;
-      if (e.out_f32) {
-        float* o = e.out_f32 + m * e.ld_f32 + nb;
-        if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) o[j] = v[j];
+        for (int i = 0; i < 4; ++i) v[i] = (v[i] + bias[i]) * mrs;
+        if (has_gate) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < nvalid) v[i] *= __ldg(e.gate + m * e.gate_groups + (n + i) / e.gate_width);
         }
-      }
-      if (e.out_op) {
-        char* row = reinterpret_cast<char*>(e.out_op) + static_cast<size_t>(m) * e.ld_op * es;
-        if (full && (((reinterpret_cast<uintptr_t>(row) + static_cast<size_t>(nb) * es) & 7) == 0) &&
-            ((op_split & 3) == 0)) {
+        if (act != UNAV_ACT_NONE) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            store_op4(row, p.op_dtype, nb + j, op_split, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) store_op(row, p.op_dtype, nb + j, op_split, v[j]);
+          for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], act);
+        }
+        if (has_res) {
+          const float rm = p.res_masked ? mk : 1.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = rr[i] * rm + cs[i] * v[i];
+        }
+        if (e.out_f32) {
+          float* o = e.out_f32 + m * e.ld_f32 + n;
+          if (vec_f32) {
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+            for (int i = 0; i < nvalid; ++i) o[i] = v[i];
+          }
+        }
+        if (e.out_op) {
+          char* row = reinterpret_cast<char*>(e.out_op) + static_cast<size_t>(m) * e.ld_op * 2;
+          if (vec_op) {
+            store_op4(row, p.op_dtype, n, op_split, make_float4(v[0], v[1], v[2], v[3]));
+          } else {
+            for (int i = 0; i < nvalid; ++i) store_op(row, p.op_dtype, n + i, op_split, v[i]);
+          }
         }
       }
     }
@@ -343,7 +378,7 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
   p.nseg = (op_dtype == UNAV_BF16X2) ? 3 : 1;
   // tile width: prefer more CTAs when the problem cannot fill the 148 SMs
   const long long tiles128 = static_cast<long long>((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128) * ngroups;
-  const int bn = (N <= 64 || tiles128 < 120) ? 64 : 128;
+  const int bn = (N <= 64 || tiles128 < 240) ? 64 : 128;   // 2 CTAs/SM x 148 SMs = 296 slots
   for (int i = 0; i < ngroups; ++i) {
     const UnavGemmGroup& g = groups[i];
     UNAV_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.W) & 15) == 0,

@@ -20,6 +20,43 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- optional per-launch tracing (bench.py's roofline leg): CUDA events on the launching stream around each
+# C-ABI call, plus the algorithmic FLOPs / bytes of the call.  Off (None) on the product path.
+_TRACE: Optional[list] = None
+
+
+def start_trace() -> None:
+    global _TRACE
+    _TRACE = []
+
+
+def stop_trace() -> list:
+    """Returns [(kernel, ms, flops, bytes, note)] for the calls issued since start_trace()."""
+    global _TRACE
+    rec, _TRACE = _TRACE or [], None
+    torch.cuda.synchronize()
+    return [(name, a.elapsed_time(b), fl, by, note) for name, a, b, fl, by, note in rec]
+
+
+class _Span:
+    def __init__(self, name, flops=0, nbytes=0, note=""):
+        self.args = (name, flops, nbytes, note)
+
+    def __enter__(self):
+        if _TRACE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _TRACE is not None and exc[0] is None:
+            self.b.record()
+            name, fl, by, note = self.args
+            _TRACE.append((name, self.a, self.b, fl, by, note))
+        return False
+
+
 def _p(t) -> Optional[int]:
     if t is None:
         return None
@@ -124,7 +161,11 @@ def gemm(groups: Sequence[dict], M: int, N: int, K: int, op_dtype: int, act: int
         s.out_f32, s.ld_f32 = _vp(g.get("out_f32")), _vld(g.get("out_f32"))
         s.out_op, s.ld_op = _vp(g.get("out_op")), _vld(g.get("out_op"))
     lib = A.load()
-    A.check(lib.unav_gemm(arr, n, M, N, K, op_dtype, act, int(res_masked), backend, _stream()), "unav_gemm")
+    es = 4 if op_dtype == F32 else (4 if op_dtype == BF16X2 else 2)
+    out_b = sum((4 if g.get("out_f32") is not None else 0) + (es if g.get("out_op") is not None else 0) for g in groups)
+    with _Span("gemm_tcgen05" if backend == GEMM_TCGEN05 else "gemm_simt", 2.0 * M * N * K * n,
+               n * (M * K + N * K) * es + M * N * out_b, f"{n}x[{M},{N},{K}]"):
+        A.check(lib.unav_gemm(arr, n, M, N, K, op_dtype, act, int(res_masked), backend, _stream()), "unav_gemm")
 
 
 # -------------------------------------------------------------------------------------- LayerNorm
@@ -148,7 +189,8 @@ def layernorm_rows(groups: Sequence[dict], M: int, C_: int, op_dtype: int, act: 
         s.x_seg_stride = g.get("x_seg_stride", 0)
         s.x_row_off = g.get("x_row_off", 0)
     lib = A.load()
-    A.check(lib.unav_layernorm_rows(arr, n, M, C_, eps, act, op_dtype, _stream()), "unav_layernorm_rows")
+    with _Span("layernorm_rows", 8.0 * M * C_ * n, n * M * C_ * 8, f"{n}x[{M},{C_}]"):
+        A.check(lib.unav_layernorm_rows(arr, n, M, C_, eps, act, op_dtype, _stream()), "unav_layernorm_rows")
 
 
 # ---------------------------------------------------------------------------- depthwise conv + LN
@@ -174,8 +216,10 @@ def dwconv_ln(groups: Sequence[dict], nseg: int, seg_len_in: int, stride: int, C
             d.out_f32, d.ld_f32 = _vp(o.get("out_f32")), _vld(o.get("out_f32"))
             d.out_op, d.ld_op = _vp(o.get("out_op")), _vld(o.get("out_op"))
     lib = A.load()
-    A.check(lib.unav_dwconv_ln(arr, n, nseg, seg_len_in, stride, C_, n_pre, n_out, eps, op_dtype, _stream()),
-            "unav_dwconv_ln")
+    rows = nseg * (seg_len_in // stride)
+    with _Span("dwconv_ln", 20.0 * rows * C_ * n * n_out, n * rows * C_ * (4 * stride + 4 * n_out), f"{n}x[{rows},{C_}]x{n_out}"):
+        A.check(lib.unav_dwconv_ln(arr, n, nseg, seg_len_in, stride, C_, n_pre, n_out, eps, op_dtype, _stream()),
+                "unav_dwconv_ln")
 
 
 # -------------------------------------------------------------------------------------- attention
@@ -194,19 +238,22 @@ def attention(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs: in
         s.x_first = g.get("x_first", 0)
         s.out, s.ldo = _vp(g["out"]), _vld(g["out"])
     lib = A.load()
-    A.check(lib.unav_attention(arr, n, nb, Tq, Tk, nh, hs, scale, op_dtype, _stream()), "unav_attention")
+    with _Span("attention", 4.0 * n * nb * nh * Tq * Tk * hs, n * nb * nh * hs * (Tq * 8 + Tk * 8), f"{n}x[{nb},{nh},{Tq},{Tk},{hs}]"):
+        A.check(lib.unav_attention(arr, n, nb, Tq, Tk, nh, hs, scale, op_dtype, _stream()), "unav_attention")
 
 
 def maxsig_gate(x, G, head_bias, gate, nb: int, T: int, nwords: int, H: int, hc: int) -> None:
     lib = A.load()
-    A.check(lib.unav_maxsig_gate(_vp(x), _vld(x), _vp(G), _vld(G), _p(head_bias), _p(gate), nb, T, nwords, H,
-                                 hc, _stream()), "unav_maxsig_gate")
+    with _Span("maxsig_gate", 2.0 * nb * T * nwords * H * hc, nb * (T + nwords) * H * hc * 4, f"[{nb},{T},{nwords},{H}x{hc}]"):
+        A.check(lib.unav_maxsig_gate(_vp(x), _vld(x), _vp(G), _vld(G), _p(head_bias), _p(gate), nb, T, nwords, H,
+                                     hc, _stream()), "unav_maxsig_gate")
 
 
 def pool_match(u0, u1, u2, T0: int, T1: int, T2: int, Wm, bm, q, nb: int, C_: int, Tq: int, P: int = 4) -> None:
     lib = A.load()
-    A.check(lib.unav_pool_match(_p(u0), _p(u1), _p(u2), T0, T1, T2, _ld(u0), _p(Wm), _p(bm), _p(q), _ld(q), nb,
-                                C_, Tq, P, _stream()), "unav_pool_match")
+    with _Span("pool_match", 2.0 * nb * Tq * 3 * P * C_, nb * C_ * (T0 + T1 + T2 + Tq) * 4):
+        A.check(lib.unav_pool_match(_p(u0), _p(u1), _p(u2), T0, T1, T2, _ld(u0), _p(Wm), _p(bm), _p(q), _ld(q), nb,
+                                    C_, Tq, P, _stream()), "unav_pool_match")
 
 
 def rowcopy(jobs: Sequence[dict], op_dtype: int) -> None:
@@ -224,26 +271,31 @@ def rowcopy(jobs: Sequence[dict], op_dtype: int) -> None:
         s.tap_stride = j.get("tap_stride", j["C"])
         s.C = j["C"]
     lib = A.load()
-    A.check(lib.unav_rowcopy(arr, n, op_dtype, _stream()), "unav_rowcopy")
+    es = 4 if op_dtype in (F32, BF16X2) else 2
+    nbytes = sum(j["nseg"] * j["seg_len_out"] * j.get("ntaps", 1) * j["C"] * (4 + es) for j in jobs)
+    with _Span("rowcopy", 0, nbytes, f"{n} jobs"):
+        A.check(lib.unav_rowcopy(arr, n, op_dtype, _stream()), "unav_rowcopy")
 
 
 def transpose_cast(inp, ld_in: int, out, nb: int, R: int, Cc: int, op_dtype: int) -> None:
     lib = A.load()
-    A.check(lib.unav_transpose_cast(_vp(inp), ld_in, _vp(out), _vld(out), nb, R, Cc, op_dtype, _stream()),
-            "unav_transpose_cast")
+    with _Span("transpose_cast", 0, nb * R * Cc * 8, f"[{nb},{R},{Cc}]"):
+        A.check(lib.unav_transpose_cast(_vp(inp), ld_in, _vp(out), _vld(out), nb, R, Cc, op_dtype, _stream()),
+                "unav_transpose_cast")
 
 
 def align_embed(x0, cls_v, cls_a, pos_v, pos_a, type_v, type_a, tokens, nb: int, T: int, C_: int) -> None:
     lib = A.load()
-    A.check(lib.unav_align_embed(_p(x0), _p(cls_v), _p(cls_a), _p(pos_v), _p(pos_a), _p(type_v), _p(type_a),
-                                 _p(tokens), nb, T, C_, _stream()), "unav_align_embed")
+    with _Span("align_embed", 0, 2 * nb * (T + 1) * C_ * 12):
+        A.check(lib.unav_align_embed(_p(x0), _p(cls_v), _p(cls_a), _p(pos_v), _p(pos_a), _p(type_v), _p(type_a),
+                                     _p(tokens), nb, T, C_, _stream()), "unav_align_embed")
 
 
 def build_masks(mask, out_true, out_up, out_cls, out_heads, nb: int, nb_src: int, T: int, L: int) -> None:
     lib = A.load()
-    A.check(lib.unav_build_masks(_p(mask), _p(out_true), _p(out_up), _p(out_cls), _p(out_heads), nb, nb_src, T, L,
-                                 _stream()),
-            "unav_build_masks")
+    with _Span("build_masks", 0, nb * T * 4):
+        A.check(lib.unav_build_masks(_p(mask), _p(out_true), _p(out_up), _p(out_cls), _p(out_heads), nb, nb_src, T, L,
+                                     _stream()), "unav_build_masks")
 
 
 def decode(logits, offsets, masks, points, level_off: List[int], B: int, ncls: int, class_aware: bool,
@@ -252,9 +304,12 @@ def decode(logits, offsets, masks, points, level_off: List[int], B: int, ncls: i
     L = len(level_off) - 1
     arr = (C.c_int * (L + 1))(*level_off)
     lib = A.load()
-    A.check(lib.unav_decode(_p(logits), _p(offsets), _p(masks), _p(points), arr, B, L, ncls, int(class_aware),
-                            pre_nms_thresh, pre_nms_topk, duration_thresh, _p(cand_segs), _p(cand_scores),
-                            _p(cand_labels), cap, _stream()), "unav_decode")
+    rows = level_off[-1]
+    # algorithmic bytes: logits + offsets in, 20 B per candidate slot out
+    with _Span("decode", 0, B * (rows * ncls * 12 + cap * 20), f"[{B},{rows},{ncls}]"):
+        A.check(lib.unav_decode(_p(logits), _p(offsets), _p(masks), _p(points), arr, B, L, ncls, int(class_aware),
+                                pre_nms_thresh, pre_nms_topk, duration_thresh, _p(cand_segs), _p(cand_scores),
+                                _p(cand_labels), cap, _stream()), "unav_decode")
 
 
 def softnms_workspace_bytes(B: int, ncls: int, max_seg_num: int) -> int:
@@ -265,7 +320,9 @@ def softnms_batched(cand_segs, cand_scores, cand_labels, B: int, cap: int, ncls:
                     sigma: float, min_score: float, method: int, max_seg_num: int, max_per_class: int,
                     vid_meta, out_segs, out_scores, out_labels, out_counts, workspace) -> None:
     lib = A.load()
-    A.check(lib.unav_softnms_batched(_p(cand_segs), _p(cand_scores), _p(cand_labels), B, cap, ncls,
+    # algorithmic bytes: 20 B per candidate in (seg 8 + score 4 + label 8) + 20 B per kept detection
+    with _Span("softnms", 0, B * (cap * 20 + max_seg_num * 20), f"[{B},{cap},{ncls}]"):
+      A.check(lib.unav_softnms_batched(_p(cand_segs), _p(cand_scores), _p(cand_labels), B, cap, ncls,
                                      iou_threshold, sigma, min_score, method, max_seg_num, max_per_class,
                                      _p(vid_meta), _p(out_segs), _p(out_scores), _p(out_labels),
                                      _p(out_counts), _p(workspace), workspace.numel() * workspace.element_size(),

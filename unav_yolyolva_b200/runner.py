@@ -1,0 +1,72 @@
+"""Multi-GPU plumbing: one process per GPU, videos sharded by index, one all-gather of the detections.
+
+The hot path has no cross-video operation, so ranks never exchange activations; the only
+collective is the final all-gather of the fixed-shape detection tensor for mAP (reference behaviour for
+comparison: ``nn.DataParallel`` re-broadcasts all 97 M parameters every forward, /root/reference/eval.py:61).
+Works with the ``nccl`` backend on GPUs and with ``gloo`` on CPU tensors (tests/test_multirank_cpu.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_videos: int, rank: int, world: int) -> List[int]:
+    """Videos {i : i % world == rank} (strided so every rank sees the same length distribution)."""
+    return list(range(rank, n_videos, world))
+
+
+def padded_shard_len(n_videos: int, world: int) -> int:
+    return (n_videos + world - 1) // world
+
+
+def pack_detections(segments: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """[n,K,2], [n,K], [n,K] -> [n,K,4] float32 (seg0, seg1, score, label); labels < 2^24 are exact in f32."""
+    return torch.cat([segments.float(), scores.float()[..., None], labels.float()[..., None]], dim=-1)
+
+
+def gather_detections(local: torch.Tensor, video_index: torch.Tensor, n_videos: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather per-rank detections.
+
+    local [n_local, K, 4] and video_index [n_local] (int32/64) live on the rank's device.  Every rank pads to
+    ceil(n_videos / world) rows (index -1), one all_gather moves [world, n_pad, K, 4] + [world, n_pad]; returns
+    (detections [n_videos, K, 4] ordered by video index, valid mask [n_videos]).
+    """
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    n_pad = padded_shard_len(n_videos, world)
+    K = local.shape[1]
+    buf = torch.zeros(n_pad, K, 4, dtype=torch.float32, device=local.device)
+    idx = torch.full((n_pad,), -1, dtype=torch.int64, device=local.device)
+    n_local = local.shape[0]
+    buf[:n_local] = local
+    idx[:n_local] = video_index.to(torch.int64)
+    if world > 1:
+        all_buf = torch.empty(world * n_pad, K, 4, dtype=torch.float32, device=local.device)
+        all_idx = torch.empty(world * n_pad, dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(all_buf, buf)
+        dist.all_gather_into_tensor(all_idx, idx)
+    else:
+        all_buf, all_idx = buf, idx
+    out = torch.zeros(n_videos, K, 4, dtype=torch.float32, device=local.device)
+    valid = torch.zeros(n_videos, dtype=torch.bool, device=local.device)
+    flat_idx = all_idx.reshape(-1)
+    keep = flat_idx >= 0
+    out[flat_idx[keep]] = all_buf.reshape(-1, K, 4)[keep]
+    valid[flat_idx[keep]] = True
+    return out, valid
+
+
+def detections_to_anet(dets: torch.Tensor, video_ids: List[str]) -> Dict[str, object]:
+    """[n,K,4] -> the flat result dict ``valid_one_epoch`` hands to ``ANETdetection.evaluate``
+    (/root/reference/libs/utils/train_utils.py:400-449)."""
+    d = dets.cpu()
+    n, K = d.shape[:2]
+    return {
+        "video-id": [v for v in video_ids for _ in range(K)],
+        "t-start": d[..., 0].reshape(-1).numpy(),
+        "t-end": d[..., 1].reshape(-1).numpy(),
+        "score": d[..., 2].reshape(-1).numpy(),
+        "label": d[..., 3].reshape(-1).long().numpy(),
+    }
