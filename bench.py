@@ -221,6 +221,9 @@ def main():
     # ---------------- value: device-resident inputs
     for j in range(W):
         device_step(j)
+    # warm the (torch) packing / gather plumbing once so its first-use module loads are not in the timed region
+    _w = runner.pack_detections(plan["out_segs"], plan["out_scores"], plan["out_labels"])
+    runner.gather_detections(_w, torch.arange(B, device=dev) + rank * B, world * B)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -244,7 +247,8 @@ def main():
     ga[1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev) + ga[0].elapsed_time(ga[1])
+    step_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    dev_ms = sum(step_ms) + ga[0].elapsed_time(ga[1])
     t = torch.tensor([dev_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -330,7 +334,9 @@ def main():
                            l2="256 MiB memset between steps (outside the timed events)",
                            gathered_videos=int(valid.sum().item())),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * Kst, "launches_per_step": launches_per_step,
-            "roofline": roof, "cpu_baseline": cpu}
+            "roofline": roof, "cpu_baseline": cpu,
+            "step_ms_min_med_max": [round(step_ms[0], 3), round(step_ms[len(step_ms) // 2], 3), round(step_ms[-1], 3)],
+            "gather_ms": round(ga[0].elapsed_time(ga[1]), 3)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -24,6 +24,7 @@
  *   unav_attention         blocks.py:218-240 (MaskedMHCA core) and
  *                          multimodal_backbones.py:899-918 (MultiHeadAttention core with the
  *                          fused mask of :1173-1183)
+ *   unav_attention_tc      same as unav_attention, tcgen05/TMEM version for key lengths <= 256
  *   unav_maxsig_gate       multimodal_backbones.py:170-191 (MaxSigmoidAttnBlock weight)
  *   unav_pool_match        multimodal_backbones.py:591-598 (avg-pool(4) x3 + match_projection)
  *   unav_rowcopy           torch.cat / nn.Upsample(nearest) / im2col glue:
@@ -171,6 +172,26 @@ typedef struct UnavAttnGroup {
 
 int unav_attention(const UnavAttnGroup* groups, int ngroups, int nb, int Tq, int Tk,
                    int nh, int hs, float scale, int op_dtype, void* stream);
+
+/* ---- fused attention on the tensor cores (tcgen05 / TMEM), key length <= 256 ------------------------ */
+/* Same math as unav_attention.  q, k: operand-dtype (UNAV_BF16 | UNAV_BF16X2) token-major rows [nb*T, ld] with
+ * head h at columns [h*hs, (h+1)*hs); vt: the values TRANSPOSED per batch item, operand dtype [nb*nh*hs, ldvt >= Tk]
+ * (row = item*C + channel, column = key), e.g. unav_transpose_cast(v, nb, R = Tk, Cc = C).  The optional extra key uses FP32 rows q32 / xk / xv
+ * (token-major, ld = ldq32 / ldx).  out has operand dtype.  S = Q.K^T and O = P.V run as tcgen05.mma with the
+ * accumulators and P in tensor memory; BF16X2 operands use the 3-pass split for FP32-level accuracy. */
+typedef struct UnavAttnTcGroup {
+  const void* q;  long long ldq;
+  const void* k;  long long ldk;
+  const void* vt; long long ldvt;
+  const uint8_t* kmask;
+  const float* q32; long long ldq32;
+  const float* xk; const float* xv; long long ldx;
+  void* out; long long ldo;
+  int x_first; int pad_;
+} UnavAttnTcGroup;
+
+int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int nb, int Tq, int Tk,
+                      int nh, int hs, float scale, int op_dtype, void* stream);
 
 /* ---- MaxSigmoid gate ----------------------------------------------------------------------- */
 /* gate[r, h] = sigmoid( max_{n<nwords} <x[r, h*hc:(h+1)*hc], G[(r/T)*nwords + n, h*hc:...]> / sqrt(hc)

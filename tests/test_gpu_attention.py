@@ -65,3 +65,78 @@ def test_alignment_attention_with_cross_key(cuda):
         xk, xv = qkv[1 - m, ..., C:2 * C], qkv[1 - m, ..., 2 * C:]
         ref = _ref(q, k, v, kmask, nh, hs, 0.125, xk, xv, 1)
         assert (out[m * hm:(m + 1) * hm].cpu().view(nb, N, C) - ref).abs().max() < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# tcgen05 / TMEM version
+def _tc_inputs(cuda, q, k, v, op):
+    """operand-dtype q, k rows + transposed values [C, nb*T]."""
+    nb, T, C = q.shape
+    qo = K.pack_operand(q.reshape(-1, C).to(cuda), op)
+    ko = K.pack_operand(k.reshape(-1, C).to(cuda), op)
+    vt = K.new_operand(nb * C, T, op, cuda)
+    K.transpose_cast(v.reshape(-1, C).to(cuda).contiguous(), C, vt, nb, T, C, op)
+    return qo, ko, vt
+
+
+def _rt(x, op):
+    hi = x.to(torch.bfloat16).float()
+    return hi + ((x - hi).to(torch.bfloat16).float() if op == K.BF16X2 else 0)
+
+
+def _read(buf, C, op):
+    v = buf[:, :C].float()
+    if op == K.BF16X2:
+        v = v + buf[:, buf.shape[1] // 2: buf.shape[1] // 2 + C].float()
+    return v.cpu()
+
+
+@pytest.mark.parametrize("nb,T,nh,hs", [(3, 224, 4, 128), (2, 224, 4, 64), (2, 112, 4, 64), (3, 56, 4, 64), (2, 28, 4, 64),
+                                         (5, 14, 4, 64), (5, 7, 4, 64), (2, 200, 2, 128)])
+@pytest.mark.parametrize("op,tol", [(K.BF16X2, 4e-5), (K.BF16, 2e-2)])
+def test_tc_attention(cuda, nb, T, nh, hs, op, tol):
+    g = torch.Generator().manual_seed(T + hs)
+    C = nh * hs
+    q, k, v = (torch.randn(nb, T, C, generator=g) for _ in range(3))
+    lens = torch.randint(1, T + 1, (nb,), generator=g)
+    kmask = (torch.arange(T)[None] < lens[:, None]).to(torch.uint8)
+    qo, ko, vt = _tc_inputs(cuda, q, k, v, op)
+    out = K.new_operand(nb * T, C, op, cuda)
+    K.attention_tc([{"q": qo, "k": ko, "vt": vt, "kmask": kmask.to(cuda), "out": out}], nb, T, T, nh, hs, 1 / math.sqrt(hs), op)
+    torch.cuda.synchronize()
+    ref = _ref(_rt(q, op), _rt(k, op), _rt(v, op), kmask, nh, hs, 1 / math.sqrt(hs))
+    err = (_read(out, C, op).view(nb, T, C) - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("op,tol", [(K.BF16X2, 4e-5), (K.BF16, 2e-2)])
+def test_tc_alignment_attention_with_cross_key(cuda, op, tol):
+    g = torch.Generator().manual_seed(3)
+    nb, N, nh, hs = 2, 225, 8, 64
+    C = nh * hs
+    qkv = torch.randn(2, nb, N, 3 * C, generator=g)
+    lens = torch.tensor([180, 61])
+    kmask = torch.cat([torch.ones(nb, 1), (torch.arange(N - 1)[None] < lens[:, None]).float()], 1).to(torch.uint8)
+    d32 = qkv.reshape(2 * nb * N, 3 * C).to(cuda)
+    dop = K.pack_operand(d32, op)
+    hm = nb * N
+    out = K.new_operand(2 * hm, C, op, cuda)
+    vts = []
+    for m in range(2):
+        vt = K.new_operand(nb * C, N, op, cuda)
+        K.transpose_cast(K.View(d32[m * hm:(m + 1) * hm], 2 * C, C), 3 * C, vt, nb, N, C, op)
+        vts.append(vt)
+    groups = []
+    for m in range(2):
+        own, oth = dop[m * hm:(m + 1) * hm], d32[(1 - m) * hm:(2 - m) * hm]
+        groups.append({"q": K.View(own, 0, C), "k": K.View(own, C, C), "vt": vts[m], "kmask": kmask.to(cuda),
+                       "q32": K.View(d32[m * hm:(m + 1) * hm], 0, C), "xk": K.View(oth, C, C), "xv": K.View(oth, 2 * C, C),
+                       "x_first": 1, "out": out[m * hm:(m + 1) * hm]})
+    K.attention_tc(groups, nb, N, N, nh, hs, 0.125, op)
+    torch.cuda.synchronize()
+    for m in range(2):
+        q, k, v = qkv[m, ..., :C], qkv[m, ..., C:2 * C], qkv[m, ..., 2 * C:]
+        xk, xv = qkv[1 - m, ..., C:2 * C], qkv[1 - m, ..., 2 * C:]
+        ref = _ref(_rt(q, op), _rt(k, op), _rt(v, op), kmask, nh, hs, 0.125, xk, xv, 1)
+        err = (_read(out[m * hm:(m + 1) * hm], C, op).view(nb, N, C) - ref).abs().max().item()
+        assert err < tol * 4, err

@@ -55,6 +55,12 @@ class AttnGroup(C.Structure):
                 ("x_first", c_i), ("pad_", c_i)]
 
 
+class AttnTcGroup(C.Structure):
+    _fields_ = [("q", c_vp), ("ldq", c_ll), ("k", c_vp), ("ldk", c_ll), ("vt", c_vp), ("ldvt", c_ll), ("kmask", c_vp),
+                ("q32", c_vp), ("ldq32", c_ll), ("xk", c_vp), ("xv", c_vp), ("ldx", c_ll), ("out", c_vp), ("ldo", c_ll),
+                ("x_first", c_i), ("pad_", c_i)]
+
+
 class CopyJob(C.Structure):
     _fields_ = [("src", c_vp), ("ld_src", c_ll), ("dst", c_vp), ("ld_dst", c_ll), ("nseg", c_i),
                 ("seg_len_in", c_i), ("seg_len_out", c_i), ("dst_seg_stride", c_i), ("dst_row_off", c_i),
@@ -70,6 +76,7 @@ _PROTOS = {
     "unav_layernorm_rows": (c_i, [C.POINTER(LnGroup), c_i, c_i, c_i, c_f, c_i, c_i, c_vp]),
     "unav_dwconv_ln": (c_i, [C.POINTER(DwLnGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp]),
     "unav_attention": (c_i, [C.POINTER(AttnGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp]),
+    "unav_attention_tc": (c_i, [C.POINTER(AttnTcGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp]),
     "unav_maxsig_gate": (c_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "unav_pool_match": (c_i, [c_vp, c_vp, c_vp, c_i, c_i, c_i, c_ll, c_vp, c_vp, c_vp, c_ll, c_i, c_i, c_i, c_i, c_vp]),
     "unav_rowcopy": (c_i, [C.POINTER(CopyJob), c_i, c_i, c_vp]),

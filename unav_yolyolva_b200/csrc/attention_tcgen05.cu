@@ -1,0 +1,399 @@
+// attention_tcgen05.cu — fused masked attention on the sm_100a tensor cores for key lengths up to 256
+// (every call of the T=224 configuration; longer sequences use the chunked CUDA-core kernel in attention.cu).
+//
+// One CTA = 128 queries of one (batch item, head).  192 threads:
+//   warp 0      TMA: Q tile + whole K of the head (SWIZZLE_128B boxes) -> smem; after S is done, V^T of the head
+//               into the same smem (K is dead by then).  V^T is stored per item, [nb][C][Tk], so that every TMA
+//               box starts 16-byte aligned for any Tk (a [C][nb*Tk] layout faulted for Tk % 8 != 0)
+//   warp 1      tcgen05.mma issuer: S[128 x Tk] = Q.K^T  (A, B from smem)  into TMEM columns [0, Tk);
+//               then O[128 x hs] = P.V  with P read from TMEM (A operand in tensor memory) and V^T from smem
+//   warps 2..5  one query row per thread: tcgen05.ld S -> key-validity mask + optional per-query extra key
+//               (Alignment's time-aligned cross-modal token) -> row max / exp / row sum in registers ->
+//               P packed to BF16 (hi [+ lo]) and written back to TMEM with tcgen05.st -> after the PV MMAs,
+//               tcgen05.ld O -> 1/rowsum -> operand-dtype store
+// The banded/valid-length mask never exists in memory: it is a per-key byte vector staged in smem and applied
+// in-register.  With BF16X2 operands both GEMMs run the 3-pass split (hi.hi + lo.hi + hi.lo), so the result
+// matches the FP32 reference to ~1e-5 (tests/test_gpu_attention.py).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace unav {
+
+// PTX wrappers shared with gemm_tcgen05.cu (kept local: both files are self-contained translation units)
+namespace atc {
+
+constexpr long long SPIN_LIMIT = 4000000000LL;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {     // K-major, SWIZZLE_128B (see gemm_tcgen05.cu)
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+}  // namespace atc
+
+struct AttnTcGroup {
+  CUtensorMap tmQ[2], tmK[2], tmV[2];     // [0] = hi / plain, [1] = lo
+  const uint8_t* kmask;
+  const float* q32; const float* xk; const float* xv;   // FP32 rows for the optional extra key
+  long long ldq32, ldx;
+  void* out; long long ldo;
+  int x_first;
+};
+struct AttnTcParams {
+  AttnTcGroup g[4];
+  int nb, Tq, Tk, Tkp, nh, hs, op_dtype, nseg, ncols;
+  int q_bytes, kv_bytes;      // smem region sizes
+  float scale;
+};
+
+__global__ void __launch_bounds__(192, 1)
+attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
+  using namespace atc;
+  extern __shared__ uint8_t smem_raw[];
+  const int gi = blockIdx.z / p.nb, b = blockIdx.z % p.nb;
+  const AttnTcGroup& g = p.g[gi];
+  const int h = blockIdx.y, q0 = blockIdx.x * 128;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = base, kv_smem = base + p.q_bytes;
+  const uint32_t bar_base = kv_smem + p.kv_bytes;
+  const uint32_t bar_qk = bar_base, bar_s = bar_base + 8, bar_v = bar_base + 16, bar_p = bar_base + 24, bar_o = bar_base + 32;
+  const uint32_t tmem_slot = bar_base + 40;
+  uint8_t* mask_s = smem_raw + (bar_base - smem_u32(smem_raw)) + 64;     // [Tkp] key validity bytes
+  const int hs = p.hs, Tkp = p.Tkp;
+  const int nparts = p.nseg > 1 ? 2 : 1;
+  const int kq = hs / 64;                       // 64-column boxes along the head dim
+  const int nkv = (Tkp + 63) / 64;              // 64-key boxes of V^T
+  const int q_box = 128 * 128, k_box = Tkp * 128, v_box = hs * 128;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar_qk, 1); mbar_init(bar_s, 1); mbar_init(bar_v, 1); mbar_init(bar_p, 4); mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int j = threadIdx.x; j < Tkp; j += blockDim.x)
+    mask_s[j] = (j < p.Tk && (!g.kmask || g.kmask[static_cast<long long>(b) * p.Tk + j])) ? 1 : 0;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  const uint32_t tm_s = tmem_base, tm_p = tmem_base + p.ncols / 2, tm_o = tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- Q tile + K of this (item, head)
+      mbar_expect_tx(bar_qk, nparts * kq * (q_box + k_box));
+      for (int pt = 0; pt < nparts; ++pt)
+        for (int kb = 0; kb < kq; ++kb) {
+          tma_load_2d(q_smem + (pt * kq + kb) * q_box, &g.tmQ[pt], bar_qk, h * hs + kb * 64, b * p.Tq + q0);
+          tma_load_2d(kv_smem + (pt * kq + kb) * k_box, &g.tmK[pt], bar_qk, h * hs + kb * 64, b * p.Tk);
+        }
+      // ---- V^T once the QK^T MMAs have finished reading K
+      mbar_wait(bar_s, 0);
+      mbar_expect_tx(bar_v, nparts * nkv * v_box);
+      for (int pt = 0; pt < nparts; ++pt)
+        for (int kb = 0; kb < nkv; ++kb)
+          tma_load_2d(kv_smem + (pt * nkv + kb) * v_box, &g.tmV[pt], bar_v, kb * 64, b * p.nh * hs + h * hs);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- S = Q.K^T : segments (Qhi,Khi), (Qlo,Khi), (Qhi,Klo)
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      const uint32_t id_s = idesc_bf16(128, Tkp);
+      uint32_t acc = 0;
+      for (int seg = 0; seg < p.nseg; ++seg) {
+        const int pa = seg == 1 ? 1 : 0, pb = seg == 2 ? 1 : 0;
+        for (int ks = 0; ks < hs / 16; ++ks) {
+          const uint64_t ad = smem_desc(q_smem + (pa * kq + ks / 4) * q_box) + 2u * (ks % 4);
+          const uint64_t bd = smem_desc(kv_smem + (pb * kq + ks / 4) * k_box) + 2u * (ks % 4);
+          mma_ss(tm_s, ad, bd, id_s, acc);
+          acc = 1;
+        }
+      }
+      tc_commit(bar_s);
+      // ---- O = P.V : segments (Phi,Vhi), (Plo,Vhi), (Phi,Vlo); P is the A operand in tensor memory
+      mbar_wait(bar_p, 0);
+      mbar_wait(bar_v, 0);
+      tc_fence_after();
+      const uint32_t id_o = idesc_bf16(128, hs);
+      acc = 0;
+      for (int seg = 0; seg < p.nseg; ++seg) {
+        const int pa = seg == 1 ? 1 : 0, pb = seg == 2 ? 1 : 0;
+        for (int ks = 0; ks < Tkp / 16; ++ks) {
+          const uint32_t a_t = tm_p + pa * (Tkp / 2) + ks * 8;        // 16 bf16 = 8 packed 32-bit columns
+          const uint64_t bd = smem_desc(kv_smem + (pb * nkv + ks / 4) * v_box) + 2u * (ks % 4);
+          mma_ts(tm_o, a_t, bd, id_o, acc);
+          acc = 1;
+        }
+      }
+      tc_commit(bar_o);
+    }
+  } else {
+    // ===== softmax / epilogue warps: one query row per thread =====
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const int qi = q0 + row;
+    const bool row_ok = qi < p.Tq;
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const float sc = p.scale;
+    // optional extra key: s_x = scale * <q_i, xk_i>
+    const bool has_x = g.xk != nullptr && row_ok && qi >= g.x_first;
+    float s_x = -CUDART_INF_F;
+    if (has_x) {
+      const float* qr = g.q32 + (static_cast<long long>(b) * p.Tq + qi) * g.ldq32 + h * hs;
+      const float* kr = g.xk + (static_cast<long long>(b) * p.Tq + qi) * g.ldx + h * hs;
+      float a = 0.f;
+      for (int d = 0; d < hs; d += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(qr + d);
+        const float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+        a = fmaf(q4.x, k4.x, a); a = fmaf(q4.y, k4.y, a); a = fmaf(q4.z, k4.z, a); a = fmaf(q4.w, k4.w, a);
+      }
+      s_x = a * sc;
+    }
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    // ---- pass 1: row max over valid keys
+    float mx = s_x;
+#pragma unroll 1
+    for (int c = 0; c < Tkp; c += 16) {
+      uint32_t r[16];
+      ld16(tm_s + lane_addr + c, r);
+      wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (mask_s[c + j]) mx = fmaxf(mx, __uint_as_float(r[j]) * sc);
+    }
+    if (mx == -CUDART_INF_F) mx = 0.f;         // fully masked row: all probabilities are 0 (0/0 = NaN as in the reference)
+    // ---- pass 2: p = exp(s*scale - max), row sum, P -> TMEM as packed BF16 (hi, lo)
+    float l = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < Tkp; c += 16) {
+      uint32_t r[16];
+      ld16(tm_s + lane_addr + c, r);
+      wait_ld();
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        float p0 = mask_s[c + j] ? __expf(__uint_as_float(r[j]) * sc - mx) : 0.f;
+        float p1 = mask_s[c + j + 1] ? __expf(__uint_as_float(r[j + 1]) * sc - mx) : 0.f;
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+        const float2 hf = __bfloat1622float2(h2);
+        if (p.nseg > 1) {
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(p0 - hf.x, p1 - hf.y);
+          lo[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+          l += p0 + p1;                                         // hi + lo carries (almost) the full FP32 value
+        } else {
+          l += hf.x + hf.y;                                     // normalise by what the MMA will actually sum
+        }
+        hi[j / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      st8(tm_p + lane_addr + c / 2, hi);
+      if (p.nseg > 1) st8(tm_p + lane_addr + Tkp / 2 + c / 2, lo);
+    }
+    float p_x = 0.f;
+    if (has_x) { p_x = __expf(s_x - mx); l += p_x; }
+    wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p);
+    // ---- epilogue: O / l (+ extra key's value), operand-dtype store
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    const size_t es = op_elem_size(p.op_dtype);
+    char* orow = reinterpret_cast<char*>(g.out) + (static_cast<size_t>(b) * p.Tq + (row_ok ? qi : 0)) * g.ldo * es;
+    const float* xvr = has_x ? g.xv + (static_cast<long long>(b) * p.Tq + qi) * g.ldx + h * hs : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < hs; c += 16) {
+      uint32_t r[16];
+      ld16(tm_o + lane_addr + c, r);
+      wait_ld();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        if (xvr) {
+          const float4 v4 = *reinterpret_cast<const float4*>(xvr + c + j);
+          o.x = fmaf(p_x, v4.x, o.x); o.y = fmaf(p_x, v4.y, o.y); o.z = fmaf(p_x, v4.z, o.z); o.w = fmaf(p_x, v4.w, o.w);
+        }
+        o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
+        store_op4(orow, p.op_dtype, h * hs + c + j, g.ldo / 2, o);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.ncols) : "memory");
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+  if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) {
+    set_error("cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(err));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+static int encode2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return UNAV_ERR_DRIVER;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("attention_tc: cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r, rows, cols, ld, box_rows);
+    return UNAV_ERR_DRIVER;
+  }
+  return 0;
+}
+
+}  // namespace unav
+
+extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int nb, int Tq, int Tk, int nh, int hs,
+                                 float scale, int op_dtype, void* stream) {
+  using namespace unav;
+  UNAV_REQUIRE(groups && ngroups >= 1 && ngroups <= 4, "attention_tc: bad group count %d", ngroups);
+  UNAV_REQUIRE(op_dtype == UNAV_BF16 || op_dtype == UNAV_BF16X2, "attention_tc: operands must be BF16");
+  UNAV_REQUIRE(hs == 64 || hs == 128, "attention_tc: head size %d not in {64,128}", hs);
+  UNAV_REQUIRE(nb > 0 && Tq > 0 && Tk > 0 && Tk <= 256 && nh > 0, "attention_tc: bad shape (Tk must be <= 256)");
+  AttnTcParams p;
+  p.nb = nb; p.Tq = Tq; p.Tk = Tk; p.nh = nh; p.hs = hs; p.op_dtype = op_dtype; p.scale = scale;
+  p.Tkp = (Tk + 15) / 16 * 16;
+  if (p.Tkp < 64) p.Tkp = 64;          // keys beyond Tk are masked; keeps every MMA / TMA box at least 64 wide
+  p.nseg = op_dtype == UNAV_BF16X2 ? 3 : 1;
+  p.ncols = p.Tkp > 128 ? 512 : 256;
+  const int nparts = p.nseg > 1 ? 2 : 1;
+  const int kq = hs / 64, nkv = (p.Tkp + 63) / 64;
+  p.q_bytes = nparts * kq * 128 * 128;
+  const int kbytes = nparts * kq * p.Tkp * 128, vbytes = nparts * nkv * hs * 128;
+  p.kv_bytes = ((kbytes > vbytes ? kbytes : vbytes) + 1023) / 1024 * 1024;
+  const long long C = static_cast<long long>(nh) * hs;
+  for (int i = 0; i < ngroups; ++i) {
+    const UnavAttnTcGroup& s = groups[i];
+    UNAV_REQUIRE(s.q && s.k && s.vt && s.out, "attention_tc: null pointer in group %d", i);
+    UNAV_REQUIRE(!s.xk || (s.xv && s.q32 && Tq == Tk), "attention_tc: extra key needs q32, xv and Tq == Tk");
+    UNAV_REQUIRE(s.ldq % 8 == 0 && s.ldk % 8 == 0 && s.ldvt % 8 == 0, "attention_tc: leading dimensions must be multiples of 8");
+    AttnTcGroup& d = p.g[i];
+    int rc;
+    const long long mq = static_cast<long long>(nb) * Tq, mk = static_cast<long long>(nb) * Tk;
+    for (int pt = 0; pt < nparts; ++pt) {
+      const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(s.q) + (pt ? s.ldq / 2 : 0);
+      const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(s.k) + (pt ? s.ldk / 2 : 0);
+      const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(s.vt) + (pt ? s.ldvt / 2 : 0);
+      if ((rc = encode2d(&d.tmQ[pt], q, mq, C, s.ldq, 128))) return rc;
+      if ((rc = encode2d(&d.tmK[pt], k, mk, C, s.ldk, p.Tkp))) return rc;
+      if ((rc = encode2d(&d.tmV[pt], v, static_cast<long long>(nb) * C, Tk, s.ldvt, hs))) return rc;
+    }
+    if (nparts == 1) { d.tmQ[1] = d.tmQ[0]; d.tmK[1] = d.tmK[0]; d.tmV[1] = d.tmV[0]; }
+    d.kmask = s.kmask; d.q32 = s.q32; d.xk = s.xk; d.xv = s.xv; d.ldq32 = s.ldq32; d.ldx = s.ldx;
+    d.out = s.out; d.ldo = s.ldo; d.x_first = s.x_first;
+  }
+  const int smem = p.q_bytes + p.kv_bytes + 64 + ((p.Tkp + 63) / 64 * 64) + 1024;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("attention_tc: smem %d: %s", smem, cudaGetErrorString(e)); return (int)e; }
+    smem_set = smem;
+  }
+  dim3 grid((Tq + 127) / 128, nh, nb * ngroups);
+  attention_tcgen05_kernel<<<grid, 192, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  count_launch();
+  return finish_launch("attention_tc");
+}

@@ -174,7 +174,7 @@ __constant__ unsigned long long kExp2fTab[32] = {
 
 // glibc expf (sysdeps/ieee754/flt-32/e_expf.c, EXP2F_TABLE_BITS = 5) for |x| small enough that no
 // overflow/underflow path is taken (here x in [-1/sigma, 0]).  Double arithmetic, explicit rounding.
-__device__ __forceinline__ float expf_glibc(float x) {
+__device__ __forceinline__ float expf_glibc(float x, const unsigned long long* tab) {
   const double InvLn2N = 0x1.71547652b82fep+0 * 32.0;
   const double Shift = 0x1.8p+52;
   const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0;
@@ -186,7 +186,7 @@ __device__ __forceinline__ float expf_glibc(float x) {
   const unsigned long long ki = static_cast<unsigned long long>(__double_as_longlong(kd));
   kd = __dsub_rn(kd, Shift);
   const double r = __dsub_rn(z, kd);
-  unsigned long long t = kExp2fTab[ki & 31ULL];
+  unsigned long long t = tab[ki & 31ULL];
   t += ki << (52 - 5);
   const double s = __longlong_as_double(static_cast<long long>(t));
   const double zz = __dadd_rn(__dmul_rn(C0, r), C1);
@@ -217,30 +217,41 @@ __global__ void softnms_kernel(const __grid_constant__ NmsParams p) {
   __shared__ float red_s[8];
   __shared__ int red_i[8];
   __shared__ int s_win;
+  __shared__ unsigned long long s_tab[32];     // exp2f table in smem: lanes index it divergently
   const int c = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  if (tid < 32) s_tab[tid] = kExp2fTab[tid];
 
   // ---- gather (warp 0, ordered)
   if (warp == 0) {
     int n = 0;
     const long long base = static_cast<long long>(b) * p.cap;
-    for (int s0 = 0; s0 < p.cap; s0 += 32) {
-      const int s = s0 + lane;
-      bool hit = s < p.cap && p.cand_labels[base + s] == c;
-      float sv = 0.f;
-      if (hit) {
-        sv = p.cand_scores[base + s];
-        if (p.method == 3 && !(sv > p.min_score)) hit = false;   // NMSop pre-filter (nms.py:15-19)
+    for (int s0 = 0; s0 < p.cap; s0 += 128) {
+      int lab[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {            // four independent label loads in flight per lane
+        const int s = s0 + u * 32 + lane;
+        lab[u] = s < p.cap ? p.cand_labels[base + s] : -1;
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      const int pos = n + __popc(bal & ((1u << lane) - 1u));
-      if (hit && pos < p.maxn) {
-        const float a = p.cand_segs[(base + s) * 2], e = p.cand_segs[(base + s) * 2 + 1];
-        x1[pos] = a; x2[pos] = e;
-        ar[pos] = __fadd_rn(__fsub_rn(e, a), 1e-6f);
-        sc[pos] = sv;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int s = s0 + u * 32 + lane;
+        bool hit = lab[u] == c;
+        float sv = 0.f;
+        if (hit) {
+          sv = p.cand_scores[base + s];
+          if (p.method == 3 && !(sv > p.min_score)) hit = false;   // NMSop pre-filter (nms.py:15-19)
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        const int pos = n + __popc(bal & ((1u << lane) - 1u));
+        if (hit && pos < p.maxn) {
+          const float a = p.cand_segs[(base + s) * 2], e = p.cand_segs[(base + s) * 2 + 1];
+          x1[pos] = a; x2[pos] = e;
+          ar[pos] = __fadd_rn(__fsub_rn(e, a), 1e-6f);
+          sc[pos] = sv;
+        }
+        n += __popc(bal);
       }
-      n += __popc(bal);
     }
     if (lane == 0) s_n = n < p.maxn ? n : p.maxn;
   }
@@ -295,7 +306,7 @@ __global__ void softnms_kernel(const __grid_constant__ NmsParams p) {
       float w = 1.f;
       if (p.method == 0 || p.method == 3) { if (ovr >= p.iou_thr) w = 0.f; }
       else if (p.method == 1) { if (ovr >= p.iou_thr) w = __fsub_rn(1.f, ovr); }
-      else w = expf_glibc(__fdiv_rn(-__fmul_rn(ovr, ovr), p.sigma));
+      else if (inter > 0.f) w = expf_glibc(__fdiv_rn(-__fmul_rn(ovr, ovr), p.sigma), s_tab);   // exp(-0) == 1 exactly
       s = __fmul_rn(s, w);
       if (p.method == 3) { if (w == 0.f) s = -CUDART_INF_F; }   // hard NMS: suppressed, scores otherwise untouched
       else if (s < p.min_score) s = -CUDART_INF_F;
@@ -325,11 +336,13 @@ merge_kernel(const __grid_constant__ MergeParams p) {
   // thread t owns classes t, t + blockDim, ...  (ncls <= 4 * blockDim supported through the loop below)
   constexpr int OWN = 4;
   int head[OWN], cnt[OWN];
+  float cur[OWN];                                  // score at the head of each owned class list
 #pragma unroll
   for (int o = 0; o < OWN; ++o) {
     const int c = tid + o * blockDim.x;
     head[o] = 0;
     cnt[o] = c < p.ncls ? p.ws_counts[b * p.ncls + c] : 0;
+    cur[o] = cnt[o] > 0 ? p.ws_dets[((static_cast<long long>(b) * p.ncls + c) * p.max_seg) * 3 + 2] : 0.f;
   }
   float stride = 1.f, half = 0.f, fps = 1.f, dur = 0.f;
   if (p.vid_meta) {
@@ -340,13 +353,13 @@ merge_kernel(const __grid_constant__ MergeParams p) {
   }
   int produced = 0;
   for (int r = 0; r < p.max_seg; ++r) {
-    float bs = -1.f;
+    float bs = -CUDART_INF_F;
     int bc = 0x7fffffff;
 #pragma unroll
     for (int o = 0; o < OWN; ++o) {
       const int c = tid + o * blockDim.x;
       if (head[o] < cnt[o]) {
-        const float s = p.ws_dets[((static_cast<long long>(b) * p.ncls + c) * p.max_seg + head[o]) * 3 + 2];
+        const float s = cur[o];
         if (s > bs || (s == bs && c < bc)) { bs = s; bc = c; }
       }
     }
@@ -372,6 +385,9 @@ merge_kernel(const __grid_constant__ MergeParams p) {
 #pragma unroll
       for (int k = 0; k < OWN; ++k) if (k == o) { hd = head[k]; head[k]++; }
       const float* d = p.ws_dets + ((static_cast<long long>(b) * p.ncls + win) * p.max_seg + hd) * 3;
+#pragma unroll
+      for (int k = 0; k < OWN; ++k)
+        if (k == o && head[k] < cnt[k]) cur[k] = d[3 + 2];            // next entry of this class list
       float s0 = d[0], s1 = d[1];
       if (p.vid_meta) {
         // (segs * stride + 0.5 * nframes) / fps, then clamp to [0, duration] the way the reference does

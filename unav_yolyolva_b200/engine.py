@@ -63,6 +63,8 @@ class HotPathEngine:
         self.level_off = [0]
         for t in self.Tl:
             self.level_off.append(self.level_off[-1] + t)
+        # fused tcgen05/TMEM attention for the tensor-core modes (key length <= 256); CUDA-core kernel otherwise
+        self.tc_attn = self.backend == GEMM_TCGEN05 and self.T + 1 <= 256
         self.w: Dict[str, torch.Tensor] = {}
         self._pack_weights()
         self._plans: Dict[int, dict] = {}
@@ -218,6 +220,9 @@ class HotPathEngine:
         P["F"] = f32(M_al, C); P["F1"] = f32(M_al, C)
         P["Fn"] = opb(M_al, C)
         P["QKV"] = f32(M_al, 3 * C)
+        if self.tc_attn:
+            P["QKVop"] = opb(M_al, 3 * C)
+            P["VTa"] = [opb(B * C, T + 1) for _ in range(2)]
         P["AOa"] = opb(M_al, C)
         P["Ha"] = opb(M_al, 4 * C)
         P["Z"] = opb(NB * T, C); P["Y"] = f32(NB * T, C)
@@ -228,6 +233,9 @@ class HotPathEngine:
         P["X"] = f32(M0, C); P["X1"] = f32(M0, C)
         P["Qin"] = opb(M0, C); P["Kin"] = opb(M0, C); P["Vin"] = opb(M0, C)
         P["Qp"] = f32(M0, C); P["Kp"] = f32(M0, C); P["Vp"] = f32(M0, C)
+        if self.tc_attn:      # tcgen05 attention: q, k as operand rows, values transposed per item [NB*C, T]
+            P["Qop"] = opb(M0, C); P["Kop"] = opb(M0, C); P["VT"] = opb(NB * C, T)
+            P["q2op"] = opb(M0, C // 2); P["k2op"] = opb(M0, C // 2); P["VT2"] = opb(NB * (C // 2), T)
         P["AO"] = opb(M0, C)
         P["Hn"] = opb(M0, C); P["Hm"] = opb(M0, 4 * C)
         # pyramid / fusion
@@ -288,6 +296,23 @@ class HotPathEngine:
     def _gemm(self, groups, M, N, Kd, act=ACT_NONE, res_masked=False):
         K.gemm(groups, M, N, Kd, self.op, act, res_masked, self.backend)
 
+    def _qkv_outs(self, q32, k32, v32, qop, kop, rows=None):
+        """Output routing of the q / k / v projection GEMMs: operand-dtype q, k for the tensor-core attention."""
+        sl = (lambda t: t) if rows is None else (lambda t: t[rows[0]:rows[1]])
+        if self.tc_attn:
+            return {"out_op": sl(qop)}, {"out_op": sl(kop)}, {"out_f32": sl(v32)}
+        return {"out_f32": sl(q32)}, {"out_f32": sl(k32)}, {"out_f32": sl(v32)}
+
+    def _attend(self, q32, k32, v32, qop, kop, vt, kmask, out, nb, T, nh, hs):
+        """MaskedMHCA core (blocks.py:218-240): tcgen05 kernel on operand q/k + transposed values, or the CUDA-core one."""
+        scale = 1.0 / math.sqrt(hs)
+        if self.tc_attn:
+            Cc = nh * hs
+            K.transpose_cast(v32, v32.stride(0), vt[:nb * Cc], nb, T, Cc, self.op)
+            K.attention_tc([{"q": qop, "k": kop, "vt": vt[:nb * Cc], "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op)
+        else:
+            K.attention([{"q": q32, "k": k32, "v": v32, "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op)
+
     def _mask(self, P, l, kind="true"):
         """u8 view of the level-l mask over the NB-stacked rows."""
         NB = 2 * P["B"]
@@ -319,15 +344,25 @@ class HotPathEngine:
         F, F1 = P["F"], P["F1"]
         for _layer in range(self.model.alignment.num_layers):          # same weights twice (:1009)
             K.layernorm_rows([{"x": F, "w": w["al.n1.w"], "b": w["al.n1.b"], "out_op": P["Fn"]}], Ma, C, op)
-            self._gemm([{"A": P["Fn"], "W": w["al.qkv"], "bias": w["al.qkv.b"], "out_f32": P["QKV"]}], Ma, 3 * C, C)
+            d = {"A": P["Fn"], "W": w["al.qkv"], "bias": w["al.qkv.b"], "out_f32": P["QKV"]}
+            if self.tc_attn:
+                d["out_op"] = P["QKVop"]
+            self._gemm([d], Ma, 3 * C, C)
             qkv = P["QKV"]
             groups = []
             for g in range(2):
                 own, oth = qkv[g * hm:(g + 1) * hm], qkv[(1 - g) * hm:(2 - g) * hm]
-                groups.append({"q": View(own, 0, C), "k": View(own, C, C), "v": View(own, 2 * C, C),
-                               "kmask": P["m_cls"], "xk": View(oth, C, C), "xv": View(oth, 2 * C, C), "x_first": 1,
-                               "out": P["AOa"][g * hm:(g + 1) * hm]})
-            K.attention(groups, B, N1, N1, 8, C // 8, 1.0 / math.sqrt(C // 8), op)
+                if self.tc_attn:
+                    K.transpose_cast(View(own, 2 * C, C), 3 * C, P["VTa"][g], B, N1, C, op)
+                    oop = P["QKVop"][g * hm:(g + 1) * hm]
+                    groups.append({"q": View(oop, 0, C), "k": View(oop, C, C), "vt": P["VTa"][g], "kmask": P["m_cls"],
+                                   "q32": View(own, 0, C), "xk": View(oth, C, C), "xv": View(oth, 2 * C, C), "x_first": 1,
+                                   "out": P["AOa"][g * hm:(g + 1) * hm]})
+                else:
+                    groups.append({"q": View(own, 0, C), "k": View(own, C, C), "v": View(own, 2 * C, C),
+                                   "kmask": P["m_cls"], "xk": View(oth, C, C), "xv": View(oth, 2 * C, C), "x_first": 1,
+                                   "out": P["AOa"][g * hm:(g + 1) * hm]})
+            (K.attention_tc if self.tc_attn else K.attention)(groups, B, N1, N1, 8, C // 8, 1.0 / math.sqrt(C // 8), op)
             self._gemm([{"A": P["AOa"], "W": w["al.m"], "bias": w["al.m.b"], "res": F, "out_f32": F1}], Ma, C, C)
             K.layernorm_rows([{"x": F1[g * hm:(g + 1) * hm], "w": w[f"al.n2.{mod}.w"], "b": w[f"al.n2.{mod}.b"],
                                "out_op": P["Fn"][g * hm:(g + 1) * hm]} for g, mod in enumerate(("video", "text"))], hm, C, op)
@@ -378,13 +413,12 @@ class HotPathEngine:
                          for g, nm in enumerate(names)], B, T, 1, C, op)
             grp = []
             for g, nm in enumerate(names):
-                for xin, xout, key in ((P["Qin"], P["Qp"], "query"), (P["Kin"], P["Kp"], "key"), (P["Vin"], P["Vp"], "value")):
-                    grp.append({"A": xin[g * half:(g + 1) * half], "W": w[f"{nm}.attn.{key}"], "bias": w[f"{nm}.attn.{key}.b"],
-                                "out_f32": xout[g * half:(g + 1) * half]})
+                outs = self._qkv_outs(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"), rows=(g * half, (g + 1) * half))
+                for xin, o, key in ((P["Qin"], outs[0], "query"), (P["Kin"], outs[1], "key"), (P["Vin"], outs[2], "value")):
+                    grp.append(dict({"A": xin[g * half:(g + 1) * half], "W": w[f"{nm}.attn.{key}"], "bias": w[f"{nm}.attn.{key}.b"]}, **o))
             self._gemm(grp, half, C, C)
             hs = C // self.n_head
-            K.attention([{"q": P["Qp"], "k": P["Kp"], "v": P["Vp"], "kmask": m0, "out": P["AO"]}], NB, T, T, self.n_head, hs,
-                        1.0 / math.sqrt(hs), op)
+            self._attend(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"), P.get("VT"), m0, P["AO"], NB, T, self.n_head, hs)
             # out = x*mask + scale_attn * (proj(att)*mask)   (blocks.py:243, :316)
             self._gemm([{"A": P["AO"][g * half:(g + 1) * half], "W": w[nm + ".attn.proj"], "bias": w[nm + ".attn.proj.b"],
                          "rowmask": m0[g * half:(g + 1) * half], "res": X[g * half:(g + 1) * half], "colscale": w[nm + ".sa"],
@@ -433,11 +467,12 @@ class HotPathEngine:
                      {"x": X[:half], "mask_out": m0[half:], "outs": [kv_out("key", P["Kin"][half:]), kv_out("value", P["Vin"][half:])]}],
                     B, T, 1, C, op)
         K.dwconv_ln([{"x": P["qm"], "mask_out": m0, "outs": [kv_out("query", P["Qin"])]}], NB, T, 1, C, op)
-        self._gemm([{"A": xin, "W": w[f"{te}.{key}"], "bias": w[f"{te}.{key}.b"], "out_f32": xout}
-                    for xin, xout, key in ((P["Qin"], P["Qp"], "query"), (P["Kin"], P["Kp"], "key"), (P["Vin"], P["Vp"], "value"))],
+        outs = self._qkv_outs(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"))
+        self._gemm([dict({"A": xin, "W": w[f"{te}.{key}"], "bias": w[f"{te}.{key}.b"]}, **o)
+                    for xin, o, key in ((P["Qin"], outs[0], "query"), (P["Kin"], outs[1], "key"), (P["Vin"], outs[2], "value"))],
                    M0, C, C)
         hs = C // 4
-        K.attention([{"q": P["Qp"], "k": P["Kp"], "v": P["Vp"], "kmask": m0, "out": P["AO"]}], NB, T, T, 4, hs, 1.0 / math.sqrt(hs), op)
+        self._attend(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"), P.get("VT"), m0, P["AO"], NB, T, 4, hs)
         self._gemm([{"A": P["AO"], "W": w[f"{te}.proj"], "bias": w[f"{te}.proj.b"], "rowmask": m0, "out_f32": P["g2"]}], M0, C, C)
         K.transpose_cast(P["g2"], C, P["gT"], NB, T, C, op)
         self._gemm([{"A": P["gT"], "W": w["fu.bu.gfc"], "bias": w["fu.bu.gfc.b"], "out_f32": P["G_bu"]}], NB * C, nG, T)
@@ -505,15 +540,18 @@ class HotPathEngine:
         x = View(h, Ch, Ch)
         q2, k2, v2 = P["q2"][:M], P["k2"][:M], P["v2"][:M]
         qp, kp, vp = P["qp2"][:M], P["kp2"][:M], P["vp2"][:M]
+        q2op = P["q2op"][:M] if self.tc_attn else None
+        k2op = P["k2op"][:M] if self.tc_attn else None
         ao = P["ao2"][:M]
         for j in range(3):
             nm = f"{name}.blk{j}"
             K.dwconv_ln([{"x": x, "mask_out": mask,
                           "outs": [{"dw": w[f"{nm}.{key}.dw"], "ln_w": w[f"{nm}.{key}.nw"], "ln_b": w[f"{nm}.{key}.nb"], "out_op": buf}
                                    for key, buf in (("query", q2), ("key", k2), ("value", v2))]}], NB, Tl, 1, Ch, op)
-            self._gemm([{"A": a, "W": w[f"{nm}.{key}"], "bias": w[f"{nm}.{key}.b"], "out_f32": o}
-                        for a, o, key in ((q2, qp, "query"), (k2, kp, "key"), (v2, vp, "value"))], M, Ch, Ch)
-            K.attention([{"q": qp, "k": kp, "v": vp, "kmask": mask, "out": ao}], NB, Tl, Tl, 4, Ch // 4, 1.0 / math.sqrt(Ch // 4), op)
+            outs = self._qkv_outs(qp, kp, vp, q2op, k2op)
+            self._gemm([dict({"A": a, "W": w[f"{nm}.{key}"], "bias": w[f"{nm}.{key}.b"]}, **o)
+                        for a, o, key in ((q2, outs[0], "query"), (k2, outs[1], "key"), (v2, outs[2], "value"))], M, Ch, Ch)
+            self._attend(qp, kp, vp, q2op, k2op, P.get("VT2"), mask, ao, NB, Tl, 4, Ch // 4)
             cj = P["c"][j][:M]
             self._gemm([{"A": ao, "W": w[f"{nm}.proj"], "bias": w[f"{nm}.proj.b"], "rowmask": mask, "out_f32": cj,
                          "out_op": View(CAT, C + j * Ch, Ch)}], M, Ch, Ch)

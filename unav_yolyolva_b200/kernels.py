@@ -242,6 +242,26 @@ def attention(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs: in
         A.check(lib.unav_attention(arr, n, nb, Tq, Tk, nh, hs, scale, op_dtype, _stream()), "unav_attention")
 
 
+def attention_tc(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs: int, scale: float, op_dtype: int) -> None:
+    """tcgen05 attention (Tk <= 256): groups carry q, k (operand rows), vt (operand, transposed values), kmask, out and
+    optionally q32 / xk / xv (FP32 rows) + x_first for the per-query extra key."""
+    n = len(groups)
+    arr = (A.AttnTcGroup * n)()
+    for i, g in enumerate(groups):
+        s = arr[i]
+        s.q, s.ldq = _vp(g["q"]), _vld(g["q"])
+        s.k, s.ldk = _vp(g["k"]), _vld(g["k"])
+        s.vt, s.ldvt = _vp(g["vt"]), _vld(g["vt"])
+        s.kmask = _p(g.get("kmask"))
+        s.q32, s.ldq32 = _vp(g.get("q32")), _vld(g.get("q32"))
+        s.xk, s.xv, s.ldx = _vp(g.get("xk")), _vp(g.get("xv")), _vld(g.get("xk"))
+        s.x_first = g.get("x_first", 0)
+        s.out, s.ldo = _vp(g["out"]), _vld(g["out"])
+    lib = A.load()
+    with _Span("attention_tc", 4.0 * n * nb * nh * Tq * Tk * hs, n * nb * nh * hs * (Tq * 8 + Tk * 8), f"{n}x[{nb},{nh},{Tq},{Tk},{hs}]"):
+        A.check(lib.unav_attention_tc(arr, n, nb, Tq, Tk, nh, hs, scale, op_dtype, _stream()), "unav_attention_tc")
+
+
 def maxsig_gate(x, G, head_bias, gate, nb: int, T: int, nwords: int, H: int, hc: int) -> None:
     lib = A.load()
     with _Span("maxsig_gate", 2.0 * nb * T * nwords * H * hc, nb * (T + nwords) * H * hc * 4, f"[{nb},{T},{nwords},{H}x{hc}]"):

@@ -49,12 +49,14 @@ def gather_detections(local: torch.Tensor, video_index: torch.Tensor, n_videos: 
         dist.all_gather_into_tensor(all_idx, idx)
     else:
         all_buf, all_idx = buf, idx
-    out = torch.zeros(n_videos, K, 4, dtype=torch.float32, device=local.device)
-    valid = torch.zeros(n_videos, dtype=torch.bool, device=local.device)
+    # scatter by video index without boolean indexing (no host sync): padded rows go to a spare slot n_videos
     flat_idx = all_idx.reshape(-1)
-    keep = flat_idx >= 0
-    out[flat_idx[keep]] = all_buf.reshape(-1, K, 4)[keep]
-    valid[flat_idx[keep]] = True
+    safe = torch.where(flat_idx >= 0, flat_idx, torch.full_like(flat_idx, n_videos))
+    out = torch.zeros(n_videos + 1, K, 4, dtype=torch.float32, device=local.device)
+    out.index_copy_(0, safe, all_buf.reshape(-1, K, 4))
+    valid = torch.zeros(n_videos + 1, dtype=torch.bool, device=local.device)
+    valid.index_fill_(0, safe, True)
+    out, valid = out[:n_videos], valid[:n_videos]
     return out, valid
 
 
