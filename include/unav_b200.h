@@ -95,6 +95,11 @@ typedef struct UnavGemmGroup {
   float* out_f32;  long long ld_f32;
   void* out_op;    long long ld_op;
   int gate_groups; int gate_width;
+  /* optional TRANSPOSED operand-dtype output of the column window [t_col0, t_col0 + t_ncols) (t_ncols = 0: all N):
+   *   out_opT[((m / t_seg) * ncols + (n - t_col0)) * ld_opT + (m % t_seg)] = acc + bias[n]
+   * i.e. per item of t_seg rows a [ncols, t_seg] matrix — the V^T layout unav_attention_tc consumes. */
+  void* out_opT;   long long ld_opT;
+  int t_seg; int t_col0; int t_ncols; int pad_;
 } UnavGemmGroup;
 
 /* groups: host array of ngroups (<= UNAV_MAX_GROUPS) problems of identical M, N, K.

@@ -127,3 +127,27 @@ def test_tcgen05_linearity_large(cuda):
     torch.cuda.synchronize()
     assert torch.equal(outs[0] + outs[1], outs[2])
     assert torch.equal(outs[0].cpu(), A1 @ W.t())
+
+
+@pytest.mark.parametrize("backend,op", [(K.GEMM_TCGEN05, K.BF16X2), (K.GEMM_TCGEN05, K.BF16), (K.GEMM_SIMT, K.F32)])
+def test_transposed_operand_output(cuda, backend, op):
+    """out_opT: per item of t_seg rows, the column window [t_col0, t_col0+t_ncols) transposed (V^T for attention_tc)."""
+    g = torch.Generator().manual_seed(5)
+    nb, T, Kd, N = 5, 28, 256, 384
+    M = nb * T
+    A, W, bias = torch.randn(M, Kd, generator=g), torch.randn(N, Kd, generator=g) / 16, torch.randn(N, generator=g)
+    col0, ncols = 128, 256
+    outT = K.new_operand(nb * ncols, T, op, cuda)
+    out = torch.empty(M, N, device=cuda)
+    K.gemm([{"A": K.pack_operand(A.to(cuda), op), "W": K.pack_operand(W.to(cuda), op), "bias": bias.to(cuda), "out_f32": out,
+             "out_opT": outT, "t_seg": T, "t_col0": col0, "t_ncols": ncols}], M, N, Kd, op, K.ACT_NONE, False, backend)
+    torch.cuda.synchronize()
+    ref = out.cpu()[:, col0:col0 + ncols].view(nb, T, ncols).transpose(1, 2).reshape(nb * ncols, T)
+    if op == K.F32:
+        got = outT[:, :T].cpu()
+    else:
+        got = outT[:, :T].float().cpu()
+        if op == K.BF16X2:
+            got = got + outT[:, outT.shape[1] // 2: outT.shape[1] // 2 + T].float().cpu()
+    tol = 2e-2 if op == K.BF16 else 1e-5
+    assert (got - ref).abs().max() <= tol * ref.abs().max()

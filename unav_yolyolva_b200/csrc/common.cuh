@@ -119,8 +119,10 @@ struct EpiParams {
   const float* colscale;
   float* out_f32;
   void* out_op;
-  long long ldres, ld_f32, ld_op;
+  void* out_opT;
+  long long ldres, ld_f32, ld_op, ld_opT;
   int gate_groups, gate_width;
+  int t_seg, t_col0, t_ncols;
 };
 
 __device__ __forceinline__ float epilogue_value(const EpiParams& e, int act, int res_masked,
@@ -151,6 +153,8 @@ static inline EpiParams make_epi(const UnavGemmGroup& g) {
   e.ldres = g.ldres; e.ld_f32 = g.ld_f32; e.ld_op = g.ld_op;
   e.gate_groups = g.gate_groups > 0 ? g.gate_groups : 1;
   e.gate_width = g.gate_width > 0 ? g.gate_width : 1;
+  e.out_opT = g.out_opT; e.ld_opT = g.ld_opT; e.t_seg = g.t_seg > 0 ? g.t_seg : 1;
+  e.t_col0 = g.t_col0; e.t_ncols = g.t_ncols;
   return e;
 }
 

@@ -85,6 +85,15 @@ gemm_simt_kernel(const __grid_constant__ SimtParams p) {
         char* row = reinterpret_cast<char*>(g.epi.out_op) + (size_t)m * g.epi.ld_op * es;
         store_op(row, p.op_dtype, n, op_split, v);
       }
+      if (g.epi.out_opT) {
+        const int ncols = g.epi.t_ncols > 0 ? g.epi.t_ncols : p.N;
+        const int nn = n - g.epi.t_col0;
+        if (nn >= 0 && nn < ncols) {
+          const long long item = m / g.epi.t_seg, t = m % g.epi.t_seg;
+          char* row = reinterpret_cast<char*>(g.epi.out_opT) + (size_t)(item * ncols + nn) * g.epi.ld_opT * es;
+          store_op(row, p.op_dtype, t, g.epi.ld_opT / 2, v);
+        }
+      }
     }
   }
 }
@@ -114,7 +123,7 @@ extern "C" int unav_gemm(const UnavGemmGroup* groups, int ngroups, int M, int N,
   UNAV_REQUIRE(op_dtype >= UNAV_F32 && op_dtype <= UNAV_BF16X2, "unav_gemm: bad op_dtype %d", op_dtype);
   for (int i = 0; i < ngroups; ++i) {
     UNAV_REQUIRE(groups[i].A && groups[i].W, "unav_gemm: null operand in group %d", i);
-    UNAV_REQUIRE(groups[i].out_f32 || groups[i].out_op, "unav_gemm: group %d has no output", i);
+    UNAV_REQUIRE(groups[i].out_f32 || groups[i].out_op || groups[i].out_opT, "unav_gemm: group %d has no output", i);
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (backend == UNAV_GEMM_TCGEN05)

@@ -251,7 +251,27 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
     const bool vec_res = nvalid == 4 && has_res && ((reinterpret_cast<uintptr_t>(e.res + n) & 15) == 0) && (e.ldres % 4 == 0);
     const bool vec_op = nvalid == 4 && e.out_op && (((reinterpret_cast<uintptr_t>(e.out_op) + static_cast<size_t>(n) * 2) & 7) == 0) &&
                         (e.ld_op % 4 == 0) && (op_split % 4 == 0);
-    if (nvalid > 0) {
+    if (e.out_opT) {
+      // transposed operand output (V^T for the tensor-core attention): lanes run along the token axis, so each
+      // store instruction writes 32 consecutive keys of one channel row
+      const long long mt = static_cast<long long>(m0) + q * 32 + lane;
+      if (mt < p.M) {
+        const int ncols = e.t_ncols > 0 ? e.t_ncols : p.N;
+        const long long item = mt / e.t_seg, t = mt % e.t_seg;
+        const long long spl = e.ld_opT / 2;
+        for (int j = 0; j < HALF; ++j) {
+          const int nn = n0 + half * HALF + j;
+          const int nc = nn - e.t_col0;
+          if (nn < p.N && nc >= 0 && nc < ncols) {
+            float x = stg[lane * PITCH + j];
+            if (e.bias) x += __ldg(e.bias + nn);
+            char* row = reinterpret_cast<char*>(e.out_opT) + static_cast<size_t>(item * ncols + nc) * e.ld_opT * 2;
+            store_op(row, p.op_dtype, t, spl, x);
+          }
+        }
+      }
+    }
+    if (nvalid > 0 && (e.out_f32 || e.out_op)) {
 #pragma unroll 2
       for (int r = rsub; r < 32; r += RPP) {
         const long long m = static_cast<long long>(m0) + q * 32 + r;

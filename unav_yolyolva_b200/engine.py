@@ -222,7 +222,7 @@ class HotPathEngine:
         P["QKV"] = f32(M_al, 3 * C)
         if self.tc_attn:
             P["QKVop"] = opb(M_al, 3 * C)
-            P["VTa"] = [opb(B * C, T + 1) for _ in range(2)]
+            P["VTa"] = opb(NB * C, T + 1)          # values of both modalities transposed per item: [2B*C, T+1]
         P["AOa"] = opb(M_al, C)
         P["Ha"] = opb(M_al, 4 * C)
         P["Z"] = opb(NB * T, C); P["Y"] = f32(NB * T, C)
@@ -296,11 +296,13 @@ class HotPathEngine:
     def _gemm(self, groups, M, N, Kd, act=ACT_NONE, res_masked=False):
         K.gemm(groups, M, N, Kd, self.op, act, res_masked, self.backend)
 
-    def _qkv_outs(self, q32, k32, v32, qop, kop, rows=None):
-        """Output routing of the q / k / v projection GEMMs: operand-dtype q, k for the tensor-core attention."""
+    def _qkv_outs(self, q32, k32, v32, qop, kop, vt, T, Cc, rows=None, items=None):
+        """Output routing of the q / k / v projection GEMMs.  Tensor-core attention: q, k as operand rows and the
+        values written TRANSPOSED per item ([item*Cc + channel, key]) straight from the GEMM epilogue."""
         sl = (lambda t: t) if rows is None else (lambda t: t[rows[0]:rows[1]])
         if self.tc_attn:
-            return {"out_op": sl(qop)}, {"out_op": sl(kop)}, {"out_f32": sl(v32)}
+            vtv = vt if items is None else vt[items[0] * Cc:items[1] * Cc]
+            return {"out_op": sl(qop)}, {"out_op": sl(kop)}, {"out_opT": vtv, "t_seg": T}
         return {"out_f32": sl(q32)}, {"out_f32": sl(k32)}, {"out_f32": sl(v32)}
 
     def _attend(self, q32, k32, v32, qop, kop, vt, kmask, out, nb, T, nh, hs):
@@ -308,7 +310,6 @@ class HotPathEngine:
         scale = 1.0 / math.sqrt(hs)
         if self.tc_attn:
             Cc = nh * hs
-            K.transpose_cast(v32, v32.stride(0), vt[:nb * Cc], nb, T, Cc, self.op)
             K.attention_tc([{"q": qop, "k": kop, "vt": vt[:nb * Cc], "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op)
         else:
             K.attention([{"q": q32, "k": k32, "v": v32, "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op)
@@ -346,16 +347,16 @@ class HotPathEngine:
             K.layernorm_rows([{"x": F, "w": w["al.n1.w"], "b": w["al.n1.b"], "out_op": P["Fn"]}], Ma, C, op)
             d = {"A": P["Fn"], "W": w["al.qkv"], "bias": w["al.qkv.b"], "out_f32": P["QKV"]}
             if self.tc_attn:
-                d["out_op"] = P["QKVop"]
+                d.update({"out_op": P["QKVop"], "out_opT": P["VTa"], "t_seg": N1, "t_col0": 2 * C, "t_ncols": C})
             self._gemm([d], Ma, 3 * C, C)
             qkv = P["QKV"]
             groups = []
             for g in range(2):
                 own, oth = qkv[g * hm:(g + 1) * hm], qkv[(1 - g) * hm:(2 - g) * hm]
                 if self.tc_attn:
-                    K.transpose_cast(View(own, 2 * C, C), 3 * C, P["VTa"][g], B, N1, C, op)
                     oop = P["QKVop"][g * hm:(g + 1) * hm]
-                    groups.append({"q": View(oop, 0, C), "k": View(oop, C, C), "vt": P["VTa"][g], "kmask": P["m_cls"],
+                    groups.append({"q": View(oop, 0, C), "k": View(oop, C, C), "vt": P["VTa"][g * B * C:(g + 1) * B * C],
+                                   "kmask": P["m_cls"],
                                    "q32": View(own, 0, C), "xk": View(oth, C, C), "xv": View(oth, 2 * C, C), "x_first": 1,
                                    "out": P["AOa"][g * hm:(g + 1) * hm]})
                 else:
@@ -413,7 +414,8 @@ class HotPathEngine:
                          for g, nm in enumerate(names)], B, T, 1, C, op)
             grp = []
             for g, nm in enumerate(names):
-                outs = self._qkv_outs(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"), rows=(g * half, (g + 1) * half))
+                outs = self._qkv_outs(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"), P.get("VT"), T, C,
+                                      rows=(g * half, (g + 1) * half), items=(g * B, (g + 1) * B))
                 for xin, o, key in ((P["Qin"], outs[0], "query"), (P["Kin"], outs[1], "key"), (P["Vin"], outs[2], "value")):
                     grp.append(dict({"A": xin[g * half:(g + 1) * half], "W": w[f"{nm}.attn.{key}"], "bias": w[f"{nm}.attn.{key}.b"]}, **o))
             self._gemm(grp, half, C, C)
@@ -467,7 +469,7 @@ class HotPathEngine:
                      {"x": X[:half], "mask_out": m0[half:], "outs": [kv_out("key", P["Kin"][half:]), kv_out("value", P["Vin"][half:])]}],
                     B, T, 1, C, op)
         K.dwconv_ln([{"x": P["qm"], "mask_out": m0, "outs": [kv_out("query", P["Qin"])]}], NB, T, 1, C, op)
-        outs = self._qkv_outs(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"))
+        outs = self._qkv_outs(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"), P.get("VT"), T, C)
         self._gemm([dict({"A": xin, "W": w[f"{te}.{key}"], "bias": w[f"{te}.{key}.b"]}, **o)
                     for xin, o, key in ((P["Qin"], outs[0], "query"), (P["Kin"], outs[1], "key"), (P["Vin"], outs[2], "value"))],
                    M0, C, C)
@@ -548,7 +550,7 @@ class HotPathEngine:
             K.dwconv_ln([{"x": x, "mask_out": mask,
                           "outs": [{"dw": w[f"{nm}.{key}.dw"], "ln_w": w[f"{nm}.{key}.nw"], "ln_b": w[f"{nm}.{key}.nb"], "out_op": buf}
                                    for key, buf in (("query", q2), ("key", k2), ("value", v2))]}], NB, Tl, 1, Ch, op)
-            outs = self._qkv_outs(qp, kp, vp, q2op, k2op)
+            outs = self._qkv_outs(qp, kp, vp, q2op, k2op, P.get("VT2"), Tl, Ch)
             self._gemm([dict({"A": a, "W": w[f"{nm}.{key}"], "bias": w[f"{nm}.{key}.b"]}, **o)
                         for a, o, key in ((q2, outs[0], "query"), (k2, outs[1], "key"), (v2, outs[2], "value"))], M, Ch, Ch)
             self._attend(qp, kp, vp, q2op, k2op, P.get("VT2"), mask, ao, NB, Tl, 4, Ch // 4)

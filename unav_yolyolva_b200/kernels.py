@@ -160,6 +160,8 @@ def gemm(groups: Sequence[dict], M: int, N: int, K: int, op_dtype: int, act: int
         s.colscale = _vp(g.get("colscale"))
         s.out_f32, s.ld_f32 = _vp(g.get("out_f32")), _vld(g.get("out_f32"))
         s.out_op, s.ld_op = _vp(g.get("out_op")), _vld(g.get("out_op"))
+        s.out_opT, s.ld_opT = _vp(g.get("out_opT")), _vld(g.get("out_opT"))
+        s.t_seg, s.t_col0, s.t_ncols = g.get("t_seg", 0), g.get("t_col0", 0), g.get("t_ncols", 0)
     lib = A.load()
     es = 4 if op_dtype == F32 else (4 if op_dtype == BF16X2 else 2)
     out_b = sum((4 if g.get("out_f32") is not None else 0) + (es if g.get("out_op") is not None else 0) for g in groups)
