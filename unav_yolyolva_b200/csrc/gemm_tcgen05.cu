@@ -20,6 +20,7 @@
 // gives ~FP32 products on the BF16 tensor pipe (measured 5e-6 of range on the logits vs 3e-3 for
 // plain BF16 operands; SURVEY.md §7 "hard parts").
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -27,7 +28,8 @@ namespace unav {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B span
-constexpr int TC_STAGES = 3;          // 3 x 32 KB (BN = 128): two CTAs per SM, one's epilogue overlaps the other's mainloop
+constexpr int TC_STAGES = 3;          // default ring depth: 3 x 32 KB (BN = 128) -> two CTAs per SM, one's epilogue overlaps the other's k-loop
+constexpr int TC_MAX_STAGES = 8;      // deep ring for sub-wave grids: bytes in flight per SM = stages x stage size (latency bound)
 constexpr int TC_THREADS = 320;       // TMA warp + MMA warp + 8 epilogue warps
 constexpr long long TC_SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks, then trap instead of hanging
 
@@ -38,7 +40,7 @@ struct TcGroup {
 };
 struct TcParams {
   TcGroup g[UNAV_MAX_GROUPS];
-  int M, N, K, op_dtype, act, res_masked, nseg;
+  int M, N, K, op_dtype, act, res_masked, nseg, stages, once;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -127,8 +129,7 @@ struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TILE_BYTES = STAGE_BYTES * TC_STAGES;
-  static constexpr int TOTAL = TILE_BYTES + 256 + 1024;   // barriers + alignment slack
+  static constexpr int total(int stages, int nparts) { return STAGE_BYTES * nparts * stages + 256 + 1024; }   // + barriers + slack
 };
 
 template <int BN>
@@ -138,23 +139,23 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   const TcGroup& g = p.g[blockIdx.z];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
-  const uint32_t bar_base = base + TcSmem<BN>::TILE_BYTES;
+  const int NS = p.stages;
+  const uint32_t bar_base = base + TcSmem<BN>::STAGE_BYTES * ((p.once && p.nseg > 1) ? 2 : 1) * NS;
   // barriers: full[s] at +8s, empty[s] at +8(S+s), accum at +8(2S); tmem slot at +8(2S+1)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-  const uint32_t accum_bar = bar_base + 8u * (2 * TC_STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 1);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * TC_MAX_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 1);
 
   const int m0 = blockIdx.x * TC_BM;
   const int n0 = blockIdx.y * BN;
   const int nkb = (p.K + TC_BK - 1) / TC_BK;
-  const int total = nkb * p.nseg;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&g.tmA[0]);
     tma_prefetch_desc(&g.tmW[0]);
     if (p.nseg > 1) { tma_prefetch_desc(&g.tmA[1]); tma_prefetch_desc(&g.tmW[1]); }
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -168,39 +169,59 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
+  // Two k-loop schedules for the split (3-pass) mode:
+  //   once = 1  stage = [A_hi | A_lo | W_hi | W_lo]; every operand part is loaded ONCE per k-block and consumed by the
+  //             three MMA groups (Ahi.Whi, Alo.Whi, Ahi.Wlo): 2/3 of the L2->SMEM bytes.  Used for grids of at most
+  //             two CTAs per SM-slot, where the ~40 B/clk per-SM L2 read port bounds the k-loop.
+  //   once = 0  stage = [A | W]; the three segments are streamed one after the other (3 * nkb iterations).  Half the
+  //             smem per stage, so two CTAs fit per SM and one's epilogue overlaps the other's k-loop: better for
+  //             multi-wave grids (measured with scripts/gemm_probe.py).
+  const int nparts = (p.once && p.nseg > 1) ? 2 : 1;
+  const uint32_t stage_bytes = nparts * TcSmem<BN>::STAGE_BYTES;
+  const uint32_t w_off = nparts * TcSmem<BN>::A_BYTES;
+  const int iters = p.once ? nkb : nkb * p.nseg;
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int it = 0; it < total; ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (it / TC_STAGES) & 1;
-        const int seg = it / nkb, kb = it - seg * nkb;
-        // segments: 0 = (Ahi,Whi), 1 = (Alo,Whi), 2 = (Ahi,Wlo)
-        const CUtensorMap* ma = &g.tmA[seg == 1 ? 1 : 0];
-        const CUtensorMap* mw = &g.tmW[seg == 2 ? 1 : 0];
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % NS;
+        const uint32_t ph = (it / NS) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), TcSmem<BN>::STAGE_BYTES);
-        const uint32_t sa = base + s * TcSmem<BN>::STAGE_BYTES;
-        tma_load_2d(sa, ma, full_bar(s), kb * TC_BK, m0);
-        tma_load_2d(sa + TcSmem<BN>::A_BYTES, mw, full_bar(s), kb * TC_BK, n0);
+        mbar_expect_tx(full_bar(s), stage_bytes);
+        const uint32_t sa = base + s * stage_bytes;
+        if (p.once) {
+          for (int pt = 0; pt < nparts; ++pt) {
+            tma_load_2d(sa + pt * TcSmem<BN>::A_BYTES, &g.tmA[pt], full_bar(s), it * TC_BK, m0);
+            tma_load_2d(sa + w_off + pt * TcSmem<BN>::B_BYTES, &g.tmW[pt], full_bar(s), it * TC_BK, n0);
+          }
+        } else {
+          // k-block major, segment minor: the SAME accumulation order as the once-schedule, so results are
+          // bit-identical whichever schedule / tile width the grid size selects (batch-size independent outputs)
+          const int kb = it / p.nseg, seg = it - kb * p.nseg;   // 0 = (Ahi,Whi), 1 = (Alo,Whi), 2 = (Ahi,Wlo)
+          tma_load_2d(sa, &g.tmA[seg == 1 ? 1 : 0], full_bar(s), kb * TC_BK, m0);
+          tma_load_2d(sa + w_off, &g.tmW[seg == 2 ? 1 : 0], full_bar(s), kb * TC_BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = make_idesc(TC_BM, BN);
-      for (int it = 0; it < total; ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (it / TC_STAGES) & 1;
+      const int nseg_in = p.once ? p.nseg : 1;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % NS;
+        const uint32_t ph = (it / NS) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t sa = base + s * TcSmem<BN>::STAGE_BYTES;
-        const uint64_t adesc = make_smem_desc(sa);
-        const uint64_t bdesc = make_smem_desc(sa + TcSmem<BN>::A_BYTES);
+        const uint32_t sa = base + s * stage_bytes;
+        for (int seg = 0; seg < nseg_in; ++seg) {
+          const uint64_t adesc = make_smem_desc(sa + (seg == 1 ? TcSmem<BN>::A_BYTES : 0));
+          const uint64_t bdesc = make_smem_desc(sa + w_off + (seg == 2 ? TcSmem<BN>::B_BYTES : 0));
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (addr >> 4) field
-          tc_mma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (addr >> 4) field
+            tc_mma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || seg > 0 || k > 0) ? 1u : 0u);
+          }
         }
         tc_commit(empty_bar(s));        // frees the ring slot once these MMAs have read it
       }
@@ -373,11 +394,11 @@ static int encode_map(CUtensorMap* map, const void* ptr, long long rows, long lo
 }
 
 template <int BN>
-static int launch_tc(const TcParams& p, int ngroups, cudaStream_t stream) {
+static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
   static bool attr_set = false;
+  constexpr int MAX_SMEM = 200 * 1024;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TcSmem<BN>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tcgen05<%d>): %s", BN, cudaGetErrorString(e));
       return static_cast<int>(e);
@@ -385,7 +406,26 @@ static int launch_tc(const TcParams& p, int ngroups, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + BN - 1) / BN, ngroups);
-  gemm_tcgen05_kernel<BN><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, stream>>>(p);
+  // Ring depth: big grids keep <= ~100 KB per CTA so two CTAs share an SM (one's epilogue overlaps the other's
+  // k-loop); sub-wave grids take a deeper ring.  The epilogue staging tile (128 x (BN+4) floats) must also fit.
+  const long long ctas = static_cast<long long>(grid.x) * grid.y * grid.z;
+  p.once = (p.nseg > 1 && ctas <= 296) ? 1 : 0;
+  if (const char* env = getenv("UNAV_TC_ONCE")) p.once = (p.nseg > 1 && atoi(env)) ? 1 : 0;
+  const int nparts = (p.once && p.nseg > 1) ? 2 : 1;
+  const int nkb = ((p.K + TC_BK - 1) / TC_BK) * (p.once ? 1 : p.nseg);
+  const int per_stage = TcSmem<BN>::STAGE_BYTES * nparts;
+  int stages = (ctas <= 148 ? 160 * 1024 : 100 * 1024) / per_stage;
+  if (const char* env = getenv("UNAV_TC_STAGES")) {            // experiment knob (scripts/gemm_probe.py)
+    const int v = atoi(env);
+    if (v >= 2) stages = v;
+  }
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages > nkb) stages = nkb;
+  if (stages < 2) stages = 2;
+  while (stages * per_stage < 128 * (BN + 4) * 4) ++stages;      // room for the staging tile
+  while (TcSmem<BN>::total(stages, nparts) > MAX_SMEM) --stages;
+  p.stages = stages;
+  gemm_tcgen05_kernel<BN><<<grid, TC_THREADS, TcSmem<BN>::total(stages, nparts), stream>>>(p);
   count_launch();
   return finish_launch("gemm_tcgen05");
 }
