@@ -205,6 +205,13 @@ int unav_maxsig_gate(const float* x, long long ldx, const float* G, long long ld
                      const float* head_bias, float* gate, int nb, int T, int nwords, int H,
                      int hc, void* stream);
 
+/* Tensor-core version: x and G as operand-dtype rows (column windows x_col0 / g_col0 of wider buffers with leading
+ * dimensions ldx / ldg); S = X_h . G_h^T runs as tcgen05.mma into all 512 TMEM columns, the row max is taken from
+ * tensor memory.  Needs nwords == 512 and hc in {32, 64}. */
+int unav_maxsig_gate_tc(const void* x, long long ldx, int x_col0, const void* G, long long ldg, int g_col0,
+                        const float* head_bias, float* gate, int nb, int T, int nwords, int H, int hc,
+                        int op_dtype, void* stream);
+
 /* ---- AdaptiveAvgPool1d(P) of 3 levels + Conv1d(3P -> Tq, k=1) along the pooled axis ------- */
 /* q[b*Tq + t, c] = bm[t] + sum_{l<3, p<P} Wm[t, l*P + p] * mean_{s in bin p of level l} u_l[b*T_l + s, c] */
 int unav_pool_match(const float* u0, const float* u1, const float* u2, int T0, int T1, int T2,

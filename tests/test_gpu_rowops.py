@@ -198,3 +198,26 @@ def test_pool_match_and_maxsig(cuda):
         aw = torch.einsum("bthc,bnhc->bhtn", emb, gd).max(-1)[0] / hc ** 0.5 + hb[None, :, None]
         ref = aw.sigmoid().permute(0, 2, 1).reshape(nb * T, H)
         assert (gate.cpu() - ref).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("op,tol", [(K.BF16X2, 3e-5), (K.BF16, 2e-2)])
+def test_maxsig_gate_tensor_core(cuda, op, tol):
+    g = torch.Generator().manual_seed(12)
+    for nb, T, H in ((3, 224, 8), (2, 56, 4), (4, 7, 8), (2, 112, 4)):
+        Ce, nw = 256, 512
+        hc = Ce // H
+        xw = torch.randn(nb * T, 1536, generator=g)              # x is the window [1024, 1280) of a concat buffer
+        Gw = torch.randn(nb * nw, 1280, generator=g)             # G is the window [512, 768) of the 5-layer guide_fc output
+        hb = torch.randn(H, generator=g)
+        xo, Go = K.pack_operand(xw.to(cuda), op), K.pack_operand(Gw.to(cuda), op)
+        gate = torch.zeros(nb * T, H, device=cuda)
+        K.maxsig_gate_tc(xo, 1024, Go, 512, hb.to(cuda), gate, nb, T, nw, H, hc, op)
+        torch.cuda.synchronize()
+        def rt(x):
+            hi = x.to(torch.bfloat16).float()
+            return hi + ((x - hi).to(torch.bfloat16).float() if op == K.BF16X2 else 0)
+        emb = rt(xw[:, 1024:1280]).view(nb, T, H, hc)
+        gd = rt(Gw[:, 512:768]).reshape(nb, nw, H, hc)
+        aw = torch.einsum("bthc,bnhc->bhtn", emb.double(), gd.double()).max(-1)[0] / hc ** 0.5 + hb[None, :, None]
+        ref = aw.sigmoid().permute(0, 2, 1).reshape(nb * T, H).float()
+        assert (gate.cpu() - ref).abs().max() < tol, (nb, T, H)

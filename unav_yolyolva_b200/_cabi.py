@@ -79,6 +79,7 @@ _PROTOS = {
     "unav_attention": (c_i, [C.POINTER(AttnGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp]),
     "unav_attention_tc": (c_i, [C.POINTER(AttnTcGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp]),
     "unav_maxsig_gate": (c_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_vp]),
+    "unav_maxsig_gate_tc": (c_i, [c_vp, c_ll, c_i, c_vp, c_ll, c_i, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "unav_pool_match": (c_i, [c_vp, c_vp, c_vp, c_i, c_i, c_i, c_ll, c_vp, c_vp, c_vp, c_ll, c_i, c_i, c_i, c_i, c_vp]),
     "unav_rowcopy": (c_i, [C.POINTER(CopyJob), c_i, c_i, c_vp]),
     "unav_transpose_cast": (c_i, [c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_vp]),

@@ -344,6 +344,98 @@ static int encode2d(CUtensorMap* map, const void* ptr, long long rows, long long
   return 0;
 }
 
+
+// =================================================================================================================
+// MaxSigmoid gate on the tensor cores: gate[r, h] = sigmoid( max_n <x[r, h*hc:], G[item*nwords + n, h*hc:]> / sqrt(hc) + bias[h] )
+// One CTA = 128 rows of one (item, head): S[128 x 512] = X_h . G_h^T as two N=256 tcgen05.mma chains into the whole
+// TMEM (512 columns), then one row per thread reduces its 512 scores with tcgen05.ld + fmax.  (multimodal_backbones.py:170-191)
+// =================================================================================================================
+struct MaxsigTcParams {
+  CUtensorMap tmX[2], tmG[2];
+  const float* head_bias;
+  float* gate;
+  int nb, T, nwords, H, hc, nseg, x_col0, g_col0;
+};
+
+__global__ void __launch_bounds__(192, 1)
+maxsig_tcgen05_kernel(const __grid_constant__ MaxsigTcParams p) {
+  using namespace atc;
+  extern __shared__ uint8_t smem_raw[];
+  const int b = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * 128;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int nparts = p.nseg > 1 ? 2 : 1;
+  const int nhalf = p.nwords / 256;                         // 256-word boxes (nwords = 512 -> 2)
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t x_smem = base, g_smem = base + nparts * 16384;
+  const uint32_t g_box = 256 * 128;
+  const uint32_t bar_base = g_smem + nparts * nhalf * g_box;
+  const uint32_t bar_ld = bar_base, bar_s = bar_base + 8, tmem_slot = bar_base + 16;
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar_ld, 1); mbar_init(bar_s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_ld, nparts * (16384 + nhalf * g_box));
+      for (int pt = 0; pt < nparts; ++pt) {
+        // 64-column boxes starting at this head's first channel; only the first hc columns are consumed
+        tma_load_2d(x_smem + pt * 16384, &p.tmX[pt], bar_ld, p.x_col0 + h * p.hc, b * p.T + t0);
+        for (int hf = 0; hf < nhalf; ++hf)
+          tma_load_2d(g_smem + (pt * nhalf + hf) * g_box, &p.tmG[pt], bar_ld, p.g_col0 + h * p.hc, b * p.nwords + hf * 256);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(bar_ld, 0);
+      tc_fence_after();
+      const uint32_t id = idesc_bf16(128, 256);
+      for (int hf = 0; hf < nhalf; ++hf) {
+        uint32_t acc = 0;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          const int pa = seg == 1 ? 1 : 0, pb = seg == 2 ? 1 : 0;
+          for (int ks = 0; ks < p.hc / 16; ++ks) {
+            mma_ss(tmem_base + hf * 256, smem_desc(x_smem + pa * 16384) + 2u * ks,
+                   smem_desc(g_smem + (pb * nhalf + hf) * g_box) + 2u * ks, id, acc);
+            acc = 1;
+          }
+        }
+      }
+      tc_commit(bar_s);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int t = t0 + qd * 32 + lane;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float mx = -CUDART_INF_F;
+#pragma unroll 1
+    for (int c = 0; c < p.nwords; c += 16) {
+      uint32_t r[16];
+      ld16(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + c, r);
+      wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
+    if (t < p.T)
+      p.gate[(static_cast<long long>(b) * p.T + t) * p.H + h] = sigmoidf_(mx * (1.0f / sqrtf(static_cast<float>(p.hc))) + p.head_bias[h]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 }  // namespace unav
 
 extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int nb, int Tq, int Tk, int nh, int hs,
@@ -396,4 +488,41 @@ extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int
   attention_tcgen05_kernel<<<grid, 192, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   count_launch();
   return finish_launch("attention_tc");
+}
+
+
+extern "C" int unav_maxsig_gate_tc(const void* x, long long ldx, int x_col0, const void* G, long long ldg, int g_col0,
+                                   const float* head_bias, float* gate, int nb, int T, int nwords, int H, int hc,
+                                   int op_dtype, void* stream) {
+  using namespace unav;
+  UNAV_REQUIRE(x && G && head_bias && gate, "maxsig_gate_tc: null pointer");
+  UNAV_REQUIRE(op_dtype == UNAV_BF16 || op_dtype == UNAV_BF16X2, "maxsig_gate_tc: operands must be BF16");
+  UNAV_REQUIRE((hc == 32 || hc == 64) && nwords == 512, "maxsig_gate_tc: needs hc in {32,64} and 512 guide words (got %d, %d)", hc, nwords);
+  UNAV_REQUIRE(ldx % 8 == 0 && ldg % 8 == 0 && x_col0 % 8 == 0 && g_col0 % 8 == 0, "maxsig_gate_tc: unaligned operand views");
+  MaxsigTcParams p;
+  p.head_bias = head_bias; p.gate = gate; p.nb = nb; p.T = T; p.nwords = nwords; p.H = H; p.hc = hc;
+  p.nseg = op_dtype == UNAV_BF16X2 ? 3 : 1;
+  p.x_col0 = x_col0; p.g_col0 = g_col0;
+  const int nparts = p.nseg > 1 ? 2 : 1;
+  // logical widths of the two operand matrices (columns beyond are read as zero by TMA)
+  const long long xw = (op_dtype == UNAV_BF16X2 ? ldx / 2 : ldx), gw = (op_dtype == UNAV_BF16X2 ? ldg / 2 : ldg);
+  for (int pt = 0; pt < nparts; ++pt) {
+    const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x) + (pt ? ldx / 2 : 0);
+    const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(G) + (pt ? ldg / 2 : 0);
+    int rc;
+    if ((rc = encode2d(&p.tmX[pt], xp, static_cast<long long>(nb) * T, xw, ldx, 128))) return rc;
+    if ((rc = encode2d(&p.tmG[pt], gp, static_cast<long long>(nb) * nwords, gw, ldg, 256))) return rc;
+  }
+  if (nparts == 1) { p.tmX[1] = p.tmX[0]; p.tmG[1] = p.tmG[0]; }
+  const int smem = nparts * 16384 + nparts * (nwords / 256) * 256 * 128 + 64 + 1024;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(maxsig_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("maxsig_gate_tc: smem %d: %s", smem, cudaGetErrorString(e)); return (int)e; }
+    smem_set = smem;
+  }
+  dim3 grid((T + 127) / 128, H, nb);
+  maxsig_tcgen05_kernel<<<grid, 192, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  count_launch();
+  return finish_launch("maxsig_gate_tc");
 }

@@ -256,6 +256,8 @@ class HotPathEngine:
         P["gT"] = opb(NB * C, T)
         nG = (L - 1) * Ch
         P["G_td"] = f32(NB * C, nG); P["G_bu"] = f32(NB * C, nG)
+        if self.tc_attn:
+            P["G_td_op"] = opb(NB * C, nG); P["G_bu_op"] = opb(NB * C, nG)
         P["qm"] = f32(M0, C); P["g2"] = f32(M0, C)
         P["DS"] = opb(NB * Tl[1], 3 * C); P["dconv"] = f32(NB * Tl[1], C)
         # heads
@@ -452,7 +454,8 @@ class HotPathEngine:
         K.transpose_cast(X[half:], C, P["gT"][:B * C], B, T, C, op)      # [B,T,C] -> [B*C, T]
         K.transpose_cast(X[:half], C, P["gT"][B * C:], B, T, C, op)
         nG = (L - 1) * (C // 2)
-        self._gemm([{"A": P["gT"], "W": w["fu.td.gfc"], "bias": w["fu.td.gfc.b"], "out_f32": P["G_td"]}], NB * C, nG, T)
+        self._gemm([dict({"A": P["gT"], "W": w["fu.td.gfc"], "bias": w["fu.td.gfc.b"]},
+                         **({"out_op": P["G_td_op"]} if self.tc_attn else {"out_f32": P["G_td"]}))], NB * C, nG, T)
         u = P["u"][:L - 1] + [feats[L - 1]]                                  # u_5 = p_5
         for idx in range(L - 1, 0, -1):
             l = idx - 1                                                      # output level
@@ -477,7 +480,8 @@ class HotPathEngine:
         self._attend(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"), P.get("VT"), m0, P["AO"], NB, T, 4, hs)
         self._gemm([{"A": P["AO"], "W": w[f"{te}.proj"], "bias": w[f"{te}.proj.b"], "rowmask": m0, "out_f32": P["g2"]}], M0, C, C)
         K.transpose_cast(P["g2"], C, P["gT"], NB, T, C, op)
-        self._gemm([{"A": P["gT"], "W": w["fu.bu.gfc"], "bias": w["fu.bu.gfc.b"], "out_f32": P["G_bu"]}], NB * C, nG, T)
+        self._gemm([dict({"A": P["gT"], "W": w["fu.bu.gfc"], "bias": w["fu.bu.gfc.b"]},
+                         **({"out_op": P["G_bu_op"]} if self.tc_attn else {"out_f32": P["G_bu"]}))], NB * C, nG, T)
         # bottom-up (:602-612)
         o = [u[0]] + P["o"][1:]
         for l in range(L - 1):
@@ -561,7 +565,11 @@ class HotPathEngine:
         c3 = P["c"][2][:M]
         hc = Ch // heads
         gate = P["gate"].view(-1)[:M * heads].view(M, heads)
-        K.maxsig_gate(c3, View(G, g_off, Ch), w[name + ".hb"], gate, NB, Tl, C, heads, hc)
+        if self.tc_attn and C == 512:      # tcgen05 gate: c_3's operand copy is the CAT window written by block 2's projection
+            K.maxsig_gate_tc(CAT, C + 2 * Ch, P["G_td_op"] if G is P["G_td"] else P["G_bu_op"], g_off, w[name + ".hb"], gate,
+                             NB, Tl, C, heads, hc, op)
+        else:
+            K.maxsig_gate(c3, View(G, g_off, Ch), w[name + ".hb"], gate, NB, Tl, C, heads, hc)
         K.rowcopy([{"src": c3, "dst": P["c3i"][:M], "nseg": NB, "seg_len_in": Tl, "seg_len_out": Tl, "ntaps": 3,
                     "tap_stride": Ch, "C": Ch}], op)
         self._gemm([{"A": P["c3i"][:M], "W": w[name + ".proj"], "bias": w[name + ".proj.b"], "rowmask": mask, "gate": gate,

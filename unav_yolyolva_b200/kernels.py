@@ -271,6 +271,15 @@ def maxsig_gate(x, G, head_bias, gate, nb: int, T: int, nwords: int, H: int, hc:
                                      hc, _stream()), "unav_maxsig_gate")
 
 
+def maxsig_gate_tc(x_buf, x_col0: int, G_buf, g_col0: int, head_bias, gate, nb: int, T: int, nwords: int, H: int, hc: int,
+                   op_dtype: int) -> None:
+    """tcgen05 MaxSigmoid gate: x_buf / G_buf are whole operand buffers, x_col0 / g_col0 the first column of the window."""
+    lib = A.load()
+    with _Span("maxsig_gate_tc", 2.0 * nb * T * nwords * H * hc, nb * (T + nwords) * H * hc * 4, f"[{nb},{T},{nwords},{H}x{hc}]"):
+        A.check(lib.unav_maxsig_gate_tc(_p(x_buf), _ld(x_buf), x_col0, _p(G_buf), _ld(G_buf), g_col0, _p(head_bias), _p(gate),
+                                        nb, T, nwords, H, hc, op_dtype, _stream()), "unav_maxsig_gate_tc")
+
+
 def pool_match(u0, u1, u2, T0: int, T1: int, T2: int, Wm, bm, q, nb: int, C_: int, Tq: int, P: int = 4) -> None:
     lib = A.load()
     with _Span("pool_match", 2.0 * nb * Tq * 3 * P * C_, nb * C_ * (T0 + T1 + T2 + Tq) * 4):
