@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_rowops.py tests/test_gpu_model.py -q -m gpu --tb=short -s > gpurun_out/test_quick.log 2>&1; echo "tests exit $?"; grep -E "rel err|passed|failed|Error" gpurun_out/test_quick.log | head
+timeout 600 python -m pytest tests/test_gpu_nms.py tests/test_gpu_model.py -q -m gpu --tb=short > gpurun_out/test_quick.log 2>&1; echo "tests exit $?"; tail -5 gpurun_out/test_quick.log
 python bench.py --steps 30 --warmup 10 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; tail -2 gpurun_out/bench.err
 python - <<'PY'
 import json

@@ -30,7 +30,16 @@ def _gpu_nms(cuda, segs, scores, labels, ncls, min_score, method=2, iou=0.7, sig
     return o_s.cpu().numpy(), o_sc.cpu().numpy(), o_l.cpu().numpy(), o_c.cpu().numpy()
 
 
-def test_softnms_bit_exact_on_golden_cases(cuda, golden_dir):
+@pytest.fixture(params=["lazy_per_video", "per_class"])
+def nms_path(request):
+    """Both device schedules must be bit-exact: the lazy per-video kernel (default) and the per-class + merge pair."""
+    if request.param == "per_class":
+        os.environ["UNAV_NMS_PER_CLASS"] = "1"
+    yield request.param
+    os.environ.pop("UNAV_NMS_PER_CLASS", None)
+
+
+def test_softnms_bit_exact_on_golden_cases(cuda, golden_dir, nms_path):
     g = np.load(os.path.join(golden_dir, "nms_cases.npz"))
     for ci in range(6):
         segs, sc, lb = g[f"in_segs_{ci}"], g[f"in_scores_{ci}"], g[f"in_labels_{ci}"]
@@ -46,7 +55,7 @@ def test_softnms_bit_exact_on_golden_cases(cuda, golden_dir):
     assert np.array_equal(o[2][0, :n], g["hard_out_labels"]) and np.array_equal(_bits(o[1][0, :n]), _bits(g["hard_out_scores"]))
 
 
-def test_softnms_batched_ragged_videos_vs_oracle(cuda):
+def test_softnms_batched_ragged_videos_vs_oracle(cuda, nms_path):
     """Config-5 style stress: several videos, empty slots (-1), a skewed class, all methods."""
     rng = np.random.default_rng(7)
     B, cap, ncls = 4, 3000, 100

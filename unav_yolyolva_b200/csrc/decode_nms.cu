@@ -8,6 +8,8 @@
 //   * IoU / decay arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction),
 //   * the gaussian weight uses glibc's expf algorithm (exp2f_data table, double arithmetic), which
 //     reproduces libm bit-for-bit on [-1/sigma, 0].
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace unav {
@@ -415,6 +417,173 @@ merge_kernel(const __grid_constant__ MergeParams p) {
   if (tid == 0) p.out_counts[b] = produced;
 }
 
+
+// =============================================================================================
+// lazy per-video soft-NMS: exact, but only the rounds the global top-K needs
+// =============================================================================================
+// The reference runs every class to completion (<= max_seg rounds each) and then keeps the global top max_seg.
+// A class's emissions are a deterministic non-increasing sequence that does not depend on other classes, and the
+// global top-K is the K-way merge of those sequences, so it is enough to always advance the class whose NEXT
+// emission is the largest: max_seg decay rounds per video instead of ncls * max_seg.  One block per video; all
+// candidates of the video live in shared memory grouped by class.
+struct LazyNmsParams {
+  const float* cand_segs; const float* cand_scores; const int32_t* cand_labels; const float* vid_meta;
+  float* out_segs; float* out_scores; int64_t* out_labels; int32_t* out_counts;
+  int cap, ncls, method, max_seg;
+  float iou_thr, sigma, min_score;
+};
+
+__global__ void __launch_bounds__(256)
+softnms_lazy_kernel(const __grid_constant__ LazyNmsParams p) {
+  extern __shared__ __align__(16) uint8_t lz_smem[];
+  float* x1 = reinterpret_cast<float*>(lz_smem);
+  float* x2 = x1 + p.cap;
+  float* sc = x2 + p.cap;
+  int* sl = reinterpret_cast<int*>(sc + p.cap);
+  int* cls_off = sl + p.cap;                 // [ncls + 1]
+  int* cursor = cls_off + p.ncls + 1;        // [ncls]
+  float* head_s = reinterpret_cast<float*>(cursor + p.ncls);   // [ncls] score of the class's next emission
+  int* head_i = reinterpret_cast<int*>(head_s + p.ncls);       // [ncls] its index in the smem arrays
+  __shared__ unsigned long long s_tab[32];
+  __shared__ float red_s[8];
+  __shared__ int red_a[8], red_b[8];
+  __shared__ int s_win;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const long long base = static_cast<long long>(b) * p.cap;
+  if (tid < 32) s_tab[tid] = kExp2fTab[tid];
+  for (int c = tid; c < p.ncls; c += blockDim.x) cursor[c] = 0;
+  __syncthreads();
+  // ---- counting sort by class (slot id kept for the "first in input order" tie-break)
+  for (int s0 = tid; s0 < p.cap; s0 += blockDim.x) {
+    const int lb = p.cand_labels[base + s0];
+    if (lb >= 0 && lb < p.ncls && !(p.method == 3 && !(p.cand_scores[base + s0] > p.min_score))) atomicAdd(&cursor[lb], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int c = 0; c < p.ncls; ++c) { cls_off[c] = acc; acc += cursor[c]; cursor[c] = 0; }
+    cls_off[p.ncls] = acc;
+  }
+  __syncthreads();
+  for (int s0 = tid; s0 < p.cap; s0 += blockDim.x) {
+    const int lb = p.cand_labels[base + s0];
+    if (lb >= 0 && lb < p.ncls) {
+      const float sv = p.cand_scores[base + s0];
+      if (p.method == 3 && !(sv > p.min_score)) continue;
+      const int pos = cls_off[lb] + atomicAdd(&cursor[lb], 1);
+      x1[pos] = p.cand_segs[(base + s0) * 2];
+      x2[pos] = p.cand_segs[(base + s0) * 2 + 1];
+      sc[pos] = sv;
+      sl[pos] = s0;
+    }
+  }
+  __syncthreads();
+  // ---- first emission of every class: highest score, ties -> lowest slot
+  for (int c = warp; c < p.ncls; c += nwarps) {
+    float bs = -CUDART_INF_F; int bslot = 0x7fffffff, bi = -1;
+    for (int j = cls_off[c] + lane; j < cls_off[c + 1]; j += 32) {
+      const float v = sc[j];
+      if (v > bs || (v == bs && sl[j] < bslot)) { bs = v; bslot = sl[j]; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int osl = __shfl_xor_sync(0xffffffffu, bslot, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (os > bs || (os == bs && osl < bslot)) { bs = os; bslot = osl; bi = oi; }
+    }
+    if (lane == 0) { head_s[c] = bs; head_i[c] = bi; }
+  }
+  __syncthreads();
+  float stride = 1.f, half = 0.f, fps = 1.f, dur = 0.f;
+  if (p.vid_meta) {
+    stride = p.vid_meta[b * 4 + 0]; half = 0.5f * p.vid_meta[b * 4 + 1];
+    fps = p.vid_meta[b * 4 + 2]; dur = p.vid_meta[b * 4 + 3];
+  }
+  int produced = 0;
+  for (int r = 0; r < p.max_seg; ++r) {
+    // ---- which class emits next: largest head score, ties -> lower class
+    float bs = -CUDART_INF_F; int bc = 0x7fffffff;
+    for (int c = tid; c < p.ncls; c += blockDim.x) {
+      const float v = head_i[c] >= 0 ? head_s[c] : -CUDART_INF_F;
+      if (head_i[c] >= 0 && (v > bs || (v == bs && c < bc))) { bs = v; bc = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (oc != 0x7fffffff && (bc == 0x7fffffff || os > bs || (os == bs && oc < bc))) { bs = os; bc = oc; }
+    }
+    if (lane == 0) { red_s[warp] = bs; red_a[warp] = bc; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < nwarps; ++w)
+        if (red_a[w] != 0x7fffffff && (bc == 0x7fffffff || red_s[w] > bs || (red_s[w] == bs && red_a[w] < bc))) { bs = red_s[w]; bc = red_a[w]; }
+      s_win = bc;
+    }
+    __syncthreads();
+    const int cw = s_win;
+    if (cw == 0x7fffffff) break;
+    const int iw = head_i[cw];
+    const float ix1 = x1[iw], ix2 = x2[iw], is = sc[iw];
+    const float ia = __fadd_rn(__fsub_rn(ix2, ix1), 1e-6f);
+    if (tid == 0) {
+      float s0 = ix1, s1 = ix2;
+      if (p.vid_meta) {
+        s0 = __fdiv_rn(__fadd_rn(__fmul_rn(s0, stride), half), fps);
+        s1 = __fdiv_rn(__fadd_rn(__fmul_rn(s1, stride), half), fps);
+        if (s0 <= 0.f) s0 = __fmul_rn(s0, 0.f);
+        if (s1 <= 0.f) s1 = __fmul_rn(s1, 0.f);
+        if (s0 >= dur) s0 = __fadd_rn(__fmul_rn(s0, 0.f), dur);
+        if (s1 >= dur) s1 = __fadd_rn(__fmul_rn(s1, 0.f), dur);
+      }
+      const long long orow = static_cast<long long>(b) * p.max_seg + r;
+      p.out_segs[orow * 2] = s0; p.out_segs[orow * 2 + 1] = s1;
+      p.out_scores[orow] = is; p.out_labels[orow] = cw;
+    }
+    produced = r + 1;
+    // ---- one decay round of that class + its next emission
+    float ns = -CUDART_INF_F; int nslot = 0x7fffffff, ni = -1;
+    for (int j = cls_off[cw] + tid; j < cls_off[cw + 1]; j += blockDim.x) {
+      if (j == iw) continue;
+      float v = sc[j];
+      if (v == -CUDART_INF_F) continue;
+      const float jx1 = x1[j], jx2 = x2[j];
+      const float inter = fmaxf(0.f, __fsub_rn(fminf(ix2, jx2), fmaxf(ix1, jx1)));
+      const float ja = __fadd_rn(__fsub_rn(jx2, jx1), 1e-6f);
+      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ia, ja), inter));
+      float w = 1.f;
+      if (p.method == 0 || p.method == 3) { if (ovr >= p.iou_thr) w = 0.f; }
+      else if (p.method == 1) { if (ovr >= p.iou_thr) w = __fsub_rn(1.f, ovr); }
+      else if (inter > 0.f) w = expf_glibc(__fdiv_rn(-__fmul_rn(ovr, ovr), p.sigma), s_tab);
+      v = __fmul_rn(v, w);
+      if (p.method == 3) { if (w == 0.f) v = -CUDART_INF_F; }
+      else if (v < p.min_score) v = -CUDART_INF_F;
+      sc[j] = v;
+      if (v != -CUDART_INF_F && (v > ns || (v == ns && sl[j] < nslot))) { ns = v; nslot = sl[j]; ni = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, ns, o);
+      const int osl = __shfl_xor_sync(0xffffffffu, nslot, o), oi = __shfl_xor_sync(0xffffffffu, ni, o);
+      if (oi >= 0 && (ni < 0 || os > ns || (os == ns && osl < nslot))) { ns = os; nslot = osl; ni = oi; }
+    }
+    if (lane == 0) { red_s[warp] = ns; red_a[warp] = nslot; red_b[warp] = ni; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < nwarps; ++w)
+        if (red_b[w] >= 0 && (ni < 0 || red_s[w] > ns || (red_s[w] == ns && red_a[w] < nslot))) { ns = red_s[w]; nslot = red_a[w]; ni = red_b[w]; }
+      sc[iw] = -CUDART_INF_F;
+      head_s[cw] = ns; head_i[cw] = ni;
+    }
+    __syncthreads();
+  }
+  for (int r = produced + tid; r < p.max_seg; r += blockDim.x) {
+    const long long orow = static_cast<long long>(b) * p.max_seg + r;
+    p.out_segs[orow * 2] = 0.f; p.out_segs[orow * 2 + 1] = 0.f; p.out_scores[orow] = 0.f; p.out_labels[orow] = 0;
+  }
+  if (tid == 0) p.out_counts[b] = produced;
+}
+
 }  // namespace unav
 
 using namespace unav;
@@ -473,6 +642,26 @@ extern "C" int unav_softnms_batched(const float* cand_segs, const float* cand_sc
   UNAV_REQUIRE(workspace && workspace_bytes >= unav_softnms_workspace_bytes(B, ncls, max_seg_num),
                "softnms: workspace too small");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  {
+    // lazy per-video kernel when a whole video's candidates fit in shared memory (always true on the model path)
+    const size_t lz = static_cast<size_t>(cap) * 16 + (static_cast<size_t>(ncls) * 4 + 1) * 4 + 64;
+    if (lz <= 200 * 1024 && !getenv("UNAV_NMS_PER_CLASS")) {
+      static size_t lz_set = 0;
+      if (lz > 48 * 1024 && lz > lz_set) {
+        cudaError_t e = cudaFuncSetAttribute(softnms_lazy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz);
+        if (e != cudaSuccess) { set_error("softnms: smem %zu: %s", lz, cudaGetErrorString(e)); return (int)e; }
+        lz_set = lz;
+      }
+      LazyNmsParams q;
+      q.cand_segs = cand_segs; q.cand_scores = cand_scores; q.cand_labels = cand_labels; q.vid_meta = vid_meta;
+      q.out_segs = out_segs; q.out_scores = out_scores; q.out_labels = out_labels; q.out_counts = out_counts;
+      q.cap = cap; q.ncls = ncls; q.method = method; q.max_seg = max_seg_num;
+      q.iou_thr = iou_threshold; q.sigma = sigma; q.min_score = min_score;
+      softnms_lazy_kernel<<<B, 256, lz, s>>>(q);
+      count_launch();
+      return finish_launch("softnms_lazy");
+    }
+  }
   NmsParams p;
   p.cand_segs = cand_segs; p.cand_scores = cand_scores; p.cand_labels = cand_labels;
   p.ws_dets = reinterpret_cast<float*>(workspace);

@@ -100,117 +100,134 @@ struct DwLnParams {
   float eps;
 };
 
-constexpr int DWV = 4;   // C <= 512
+constexpr int DWV = 4;        // float4 chunks per lane: C <= 512
+constexpr int DW_ROWS = 16;   // output rows per block (one tile never crosses a segment)
 
-__global__ void __launch_bounds__(128)
+// One block = DW_ROWS consecutive output rows of one segment.  Phase 1 stages the DW_ROWS*stride + 2 input rows
+// in shared memory once (the one-warp-per-row version re-read every input row from three warps and recomputed its
+// pre-LayerNorm statistics three times; ncu: 154 registers, 19 % occupancy, 31 % issue-active); phase 2 gives each
+// warp two output rows: per output, depthwise taps over the staged rows (pre-LN affine applied on the fly), mask,
+// LayerNorm with warp-shuffle reductions, vectorised FP32 / operand stores.
+__global__ void __launch_bounds__(256)
 dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
+  extern __shared__ __align__(16) float dw_smem[];
   const UnavDwLnGroup& g = p.g[blockIdx.y];
-  const int lane = threadIdx.x & 31;
-  const long long r = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);   // output row
-  const long long M = static_cast<long long>(p.nseg) * p.seg_len_out;
-  if (r >= M) return;
   const int C = p.C;
-  const int seg = static_cast<int>(r / p.seg_len_out), t = static_cast<int>(r % p.seg_len_out);
-  // three input rows (tap 0,1,2) = stride*t - 1 .. stride*t + 1, zero outside the segment
-  float4 x[3][DWV];
-  bool ok[3];
-  float mean[3], rstd[3];
-#pragma unroll
-  for (int tap = 0; tap < 3; ++tap) {
-    const int ti = p.stride * t + tap - 1;
-    ok[tap] = ti >= 0 && ti < p.seg_len_in;
-    const float* xr = g.x + (static_cast<long long>(seg) * p.seg_len_in + (ok[tap] ? ti : 0)) * g.ldx;
+  const int tiles_per_seg = (p.seg_len_out + DW_ROWS - 1) / DW_ROWS;
+  const int seg = blockIdx.x / tiles_per_seg, t0 = (blockIdx.x % tiles_per_seg) * DW_ROWS;
+  const int n_in = DW_ROWS * p.stride + 2;                 // staged input rows: stride*t0 - 1 ...
+  float* xs = dw_smem;                                     // [n_in][C]
+  float* st_mean = dw_smem + n_in * C;                     // [n_in]
+  float* st_rstd = st_mean + n_in;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+  for (int i = warp; i < n_in; i += nwarps) {
+    const int ti = p.stride * t0 - 1 + i;
+    const bool ok = ti >= 0 && ti < p.seg_len_in;
+    const float* xr = g.x + (static_cast<long long>(seg) * p.seg_len_in + (ok ? ti : 0)) * g.ldx;
+    float4 v[DWV];
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < DWV; ++j) {
       const int c = (j * 32 + lane) * 4;
       if (c < C) {
-        x[tap][j] = ok[tap] ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        s += (x[tap][j].x + x[tap][j].y) + (x[tap][j].z + x[tap][j].w);
+        v[j] = ok ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(xs + i * C + c) = v[j];
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
       }
     }
     if (p.n_pre > 0) {
-      mean[tap] = warp_sum(s) / C;
+      const float mean = warp_sum(s) / C;
       float q = 0.f;
 #pragma unroll
       for (int j = 0; j < DWV; ++j) {
         const int c = (j * 32 + lane) * 4;
         if (c < C) {
-          const float a = x[tap][j].x - mean[tap], b = x[tap][j].y - mean[tap];
-          const float cc = x[tap][j].z - mean[tap], d = x[tap][j].w - mean[tap];
+          const float a = v[j].x - mean, b = v[j].y - mean, cc = v[j].z - mean, d = v[j].w - mean;
           q += (a * a + b * b) + (cc * cc + d * d);
         }
       }
-      rstd[tap] = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
+      if (lane == 0) { st_mean[i] = mean; st_rstd[i] = ok ? rstd : 0.f; }   // rstd 0 + skipped affine = zero padding
     }
   }
-  const float mk = g.mask_out ? (g.mask_out[r] ? 1.f : 0.f) : 1.f;
+  __syncthreads();
+
   const size_t es = op_elem_size(p.op_dtype);
-  for (int o = 0; o < p.n_out; ++o) {
-    const UnavDwLnOut& od = g.out[o];
-    const float* pw = (od.src >= 0) ? g.pre_w[od.src] : nullptr;
-    const float* pb = (od.src >= 0) ? g.pre_b[od.src] : nullptr;
-    float4 z[DWV];
-    float s = 0.f;
+  for (int ro = warp; ro < DW_ROWS; ro += nwarps) {
+    const int t = t0 + ro;
+    if (t >= p.seg_len_out) break;
+    const long long r = static_cast<long long>(seg) * p.seg_len_out + t;
+    const float mk = g.mask_out ? (g.mask_out[r] ? 1.f : 0.f) : 1.f;
+    const int i0 = ro * p.stride;                          // staged row of tap 0
+    bool okt[3];
 #pragma unroll
-    for (int j = 0; j < DWV; ++j) {
-      const int c = (j * 32 + lane) * 4;
-      if (c < C) {
-        // taps of 4 consecutive channels: 12 contiguous floats of dw[C][3]
-        const float4 d0 = *reinterpret_cast<const float4*>(od.dw + c * 3);
-        const float4 d1 = *reinterpret_cast<const float4*>(od.dw + c * 3 + 4);
-        const float4 d2 = *reinterpret_cast<const float4*>(od.dw + c * 3 + 8);
-        const float wt[4][3] = {{d0.x, d0.y, d0.z}, {d0.w, d1.x, d1.y}, {d1.z, d1.w, d2.x}, {d2.y, d2.z, d2.w}};
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        float4 lw = make_float4(1.f, 1.f, 1.f, 1.f), lb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pw) { lw = *reinterpret_cast<const float4*>(pw + c); lb = *reinterpret_cast<const float4*>(pb + c); }
+    for (int tap = 0; tap < 3; ++tap) {
+      const int ti = p.stride * t + tap - 1;
+      okt[tap] = ti >= 0 && ti < p.seg_len_in;
+    }
+    for (int o = 0; o < p.n_out; ++o) {
+      const UnavDwLnOut& od = g.out[o];
+      const float* pw = (od.src >= 0) ? g.pre_w[od.src] : nullptr;
+      const float* pb = (od.src >= 0) ? g.pre_b[od.src] : nullptr;
+      float4 z[DWV];
+      float s = 0.f;
 #pragma unroll
-        for (int tap = 0; tap < 3; ++tap) {
-          if (!ok[tap]) continue;
-          float4 u = x[tap][j];
-          if (pw) {
-            u.x = (u.x - mean[tap]) * rstd[tap] * lw.x + lb.x;
-            u.y = (u.y - mean[tap]) * rstd[tap] * lw.y + lb.y;
-            u.z = (u.z - mean[tap]) * rstd[tap] * lw.z + lb.z;
-            u.w = (u.w - mean[tap]) * rstd[tap] * lw.w + lb.w;
+      for (int j = 0; j < DWV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        if (c < C) {
+          const float4 d0 = *reinterpret_cast<const float4*>(od.dw + c * 3);       // taps of 4 channels: 12 floats
+          const float4 d1 = *reinterpret_cast<const float4*>(od.dw + c * 3 + 4);
+          const float4 d2 = *reinterpret_cast<const float4*>(od.dw + c * 3 + 8);
+          const float wt[4][3] = {{d0.x, d0.y, d0.z}, {d0.w, d1.x, d1.y}, {d1.z, d1.w, d2.x}, {d2.y, d2.z, d2.w}};
+          float4 lw = make_float4(1.f, 1.f, 1.f, 1.f), lb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pw) { lw = *reinterpret_cast<const float4*>(pw + c); lb = *reinterpret_cast<const float4*>(pb + c); }
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap) {
+            if (!okt[tap]) continue;
+            float4 u = *reinterpret_cast<const float4*>(xs + (i0 + tap) * C + c);
+            if (pw) {
+              const float mean = st_mean[i0 + tap], rstd = st_rstd[i0 + tap];
+              u.x = (u.x - mean) * rstd * lw.x + lb.x; u.y = (u.y - mean) * rstd * lw.y + lb.y;
+              u.z = (u.z - mean) * rstd * lw.z + lb.z; u.w = (u.w - mean) * rstd * lw.w + lb.w;
+            }
+            acc[0] = fmaf(wt[0][tap], u.x, acc[0]); acc[1] = fmaf(wt[1][tap], u.y, acc[1]);
+            acc[2] = fmaf(wt[2][tap], u.z, acc[2]); acc[3] = fmaf(wt[3][tap], u.w, acc[3]);
           }
-          acc[0] = fmaf(wt[0][tap], u.x, acc[0]);
-          acc[1] = fmaf(wt[1][tap], u.y, acc[1]);
-          acc[2] = fmaf(wt[2][tap], u.z, acc[2]);
-          acc[3] = fmaf(wt[3][tap], u.w, acc[3]);
+          z[j] = make_float4(acc[0] * mk, acc[1] * mk, acc[2] * mk, acc[3] * mk);
+          s += (z[j].x + z[j].y) + (z[j].z + z[j].w);
         }
-        z[j] = make_float4(acc[0] * mk, acc[1] * mk, acc[2] * mk, acc[3] * mk);
-        s += (z[j].x + z[j].y) + (z[j].z + z[j].w);
       }
-    }
-    const float mu = warp_sum(s) / C;
-    float q = 0.f;
+      const float mu = warp_sum(s) / C;
+      float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < DWV; ++j) {
-      const int c = (j * 32 + lane) * 4;
-      if (c < C) {
-        z[j].x -= mu; z[j].y -= mu; z[j].z -= mu; z[j].w -= mu;
-        q += (z[j].x * z[j].x + z[j].y * z[j].y) + (z[j].z * z[j].z + z[j].w * z[j].w);
-      }
-    }
-    const float rs = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
-    const bool has_ln = od.ln_w != nullptr;   // NULL: plain masked depthwise conv (MaskedConv1D with groups = C)
-    char* op_row = od.out_op ? reinterpret_cast<char*>(od.out_op) + static_cast<size_t>(r) * od.ld_op * es : nullptr;
-#pragma unroll
-    for (int j = 0; j < DWV; ++j) {
-      const int c = (j * 32 + lane) * 4;
-      if (c < C) {
-        float4 y;
-        if (has_ln) {
-          const float4 w = *reinterpret_cast<const float4*>(od.ln_w + c);
-          const float4 b = *reinterpret_cast<const float4*>(od.ln_b + c);
-          y.x = z[j].x * rs * w.x + b.x; y.y = z[j].y * rs * w.y + b.y;
-          y.z = z[j].z * rs * w.z + b.z; y.w = z[j].w * rs * w.w + b.w;
-        } else {
-          y = make_float4(z[j].x + mu, z[j].y + mu, z[j].z + mu, z[j].w + mu);
+      for (int j = 0; j < DWV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        if (c < C) {
+          z[j].x -= mu; z[j].y -= mu; z[j].z -= mu; z[j].w -= mu;
+          q += (z[j].x * z[j].x + z[j].y * z[j].y) + (z[j].z * z[j].z + z[j].w * z[j].w);
         }
-        if (od.out_f32) *reinterpret_cast<float4*>(od.out_f32 + r * od.ld_f32 + c) = y;
-        if (op_row) store_op4(op_row, p.op_dtype, c, od.ld_op / 2, y);
+      }
+      const float rs = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
+      const bool has_ln = od.ln_w != nullptr;   // NULL: plain masked depthwise conv (MaskedConv1D with groups = C)
+      char* op_row = od.out_op ? reinterpret_cast<char*>(od.out_op) + static_cast<size_t>(r) * od.ld_op * es : nullptr;
+#pragma unroll
+      for (int j = 0; j < DWV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        if (c < C) {
+          float4 y;
+          if (has_ln) {
+            const float4 w = *reinterpret_cast<const float4*>(od.ln_w + c);
+            const float4 b = *reinterpret_cast<const float4*>(od.ln_b + c);
+            y.x = z[j].x * rs * w.x + b.x; y.y = z[j].y * rs * w.y + b.y;
+            y.z = z[j].z * rs * w.z + b.z; y.w = z[j].w * rs * w.w + b.w;
+          } else {
+            y = make_float4(z[j].x + mu, z[j].y + mu, z[j].z + mu, z[j].w + mu);
+          }
+          if (od.out_f32) *reinterpret_cast<float4*>(od.out_f32 + r * od.ld_f32 + c) = y;
+          if (op_row) store_op4(op_row, p.op_dtype, c, od.ld_op / 2, y);
+        }
       }
     }
   }
@@ -471,9 +488,17 @@ extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg
   for (int i = 0; i < ngroups; ++i) p.g[i] = groups[i];
   p.nseg = nseg; p.seg_len_in = seg_len_in; p.seg_len_out = seg_len_in / stride; p.stride = stride; p.C = C;
   p.n_pre = n_pre; p.n_out = n_out; p.op_dtype = op_dtype; p.eps = eps;
-  const long long M = static_cast<long long>(nseg) * p.seg_len_out;
-  dim3 grid(static_cast<unsigned>((M + 3) / 4), ngroups);
-  dwconv_ln_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  const int tiles_per_seg = (p.seg_len_out + DW_ROWS - 1) / DW_ROWS;
+  const int n_in = DW_ROWS * stride + 2;
+  const size_t smem = (static_cast<size_t>(n_in) * C + 2 * n_in) * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("dwconv_ln: smem %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
+    smem_set = smem;
+  }
+  dim3 grid(static_cast<unsigned>(nseg * tiles_per_seg), ngroups);
+  dwconv_ln_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   count_launch();
   return finish_launch("dwconv_ln");
 }
