@@ -24,7 +24,7 @@ struct DecodeParams {
   float* cand_segs; float* cand_scores; int32_t* cand_labels;
   int level_off[9];     // rows
   int cap_off[9];       // candidate slots
-  int B, L, ncls, class_aware, topk, cap, Ttot;
+  int B, L, ncls, class_aware, topk, cap, Ttot, use_smem;
   float thresh, dur_thresh;
 };
 
@@ -56,6 +56,7 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int* warp_tot, int* to
 
 __global__ void __launch_bounds__(DEC_THREADS)
 decode_kernel(const __grid_constant__ DecodeParams p) {
+  extern __shared__ __align__(16) float dec_p[];      // [n] probabilities of this (video, level), computed once
   __shared__ int hist[256];
   __shared__ int warp_tot[DEC_THREADS / 32];
   __shared__ unsigned s_prefix;
@@ -70,7 +71,11 @@ decode_kernel(const __grid_constant__ DecodeParams p) {
   if (tid == 0) s_count = 0;
   __syncthreads();
   int cnt = 0;
-  for (int i = tid; i < n; i += DEC_THREADS) cnt += decode_prob(p, b, row0, i) > p.thresh;
+  for (int i = tid; i < n; i += DEC_THREADS) {
+    const float pr = decode_prob(p, b, row0, i);
+    if (p.use_smem) dec_p[i] = pr;
+    cnt += pr > p.thresh;
+  }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
   if ((tid & 31) == 0 && cnt) atomicAdd(&s_count, cnt);
   __syncthreads();
@@ -87,7 +92,7 @@ decode_kernel(const __grid_constant__ DecodeParams p) {
       const unsigned prefix = s_prefix;
       const int shift = 24 - 8 * pass;
       for (int i = tid; i < n; i += DEC_THREADS) {
-        const float pr = decode_prob(p, b, row0, i);
+        const float pr = p.use_smem ? dec_p[i] : decode_prob(p, b, row0, i);
         if (pr > p.thresh) {
           const unsigned key = __float_as_uint(pr);
           if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
@@ -116,7 +121,7 @@ decode_kernel(const __grid_constant__ DecodeParams p) {
     float pr = 0.f;
     bool above = false, eq = false;
     if (i < n) {
-      pr = decode_prob(p, b, row0, i);
+      pr = p.use_smem ? dec_p[i] : decode_prob(p, b, row0, i);
       if (pr > p.thresh) {
         const unsigned key = __float_as_uint(pr);
         above = (count <= p.topk) || key > vstar;
@@ -618,8 +623,22 @@ extern "C" int unav_decode(const float* logits, const float* offsets, const uint
       if (e != cudaSuccess) { set_error("decode: memset: %s", cudaGetErrorString(e)); return (int)e; }
     }
   }
+  int max_n = 0;
+  for (int l = 0; l < L; ++l) {
+    const int n = (level_off[l + 1] - level_off[l]) * ncls;
+    max_n = n > max_n ? n : max_n;
+  }
+  size_t smem = static_cast<size_t>(max_n) * sizeof(float);
+  p.use_smem = smem <= 200 * 1024;        // long sequences (T = 2304: 921 KB at level 0) recompute the sigmoid per pass
+  if (!p.use_smem) smem = 0;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("decode: smem %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
+    smem_set = smem;
+  }
   dim3 grid(L, B);
-  decode_kernel<<<grid, DEC_THREADS, 0, s>>>(p);
+  decode_kernel<<<grid, DEC_THREADS, smem, s>>>(p);
   count_launch();
   return finish_launch("decode");
 }
