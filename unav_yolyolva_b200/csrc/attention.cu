@@ -32,6 +32,8 @@ struct AttnSmem {
 template <int HS>
 __global__ void __launch_bounds__(128)
 attention_kernel(const __grid_constant__ AttnParams p) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   extern __shared__ __align__(16) uint8_t smem_raw[];
   AttnSmem<HS>& sm = *reinterpret_cast<AttnSmem<HS>*>(smem_raw);
   constexpr int DPT = HS / 16;
@@ -206,7 +208,7 @@ static int launch_attention(const AttnParams& p, int ngroups, cudaStream_t strea
     attr_set = true;
   }
   dim3 grid((p.Tq + AT_Q - 1) / AT_Q, p.nh, p.nb * ngroups);
-  attention_kernel<HS><<<grid, 128, smem, stream>>>(p);
+  launch_pdl(attention_kernel<HS>, dim3(grid), dim3(128), smem, stream, p);
   count_launch();
   return finish_launch("attention");
 }

@@ -148,6 +148,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   for (int j = threadIdx.x; j < Tkp; j += blockDim.x)
     mask_s[j] = (j < p.Tk && (!g.kmask || g.kmask[static_cast<long long>(b) * p.Tk + j])) ? 1 : 0;
   tc_fence_before();
@@ -383,6 +385,8 @@ maxsig_tcgen05_kernel(const __grid_constant__ MaxsigTcParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(bar_ld, nparts * (16384 + nhalf * g_box));
@@ -485,7 +489,7 @@ extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int
     smem_set = smem;
   }
   dim3 grid((Tq + 127) / 128, nh, nb * ngroups);
-  attention_tcgen05_kernel<<<grid, 192, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(attention_tcgen05_kernel, dim3(grid), dim3(192), smem, reinterpret_cast<cudaStream_t>(stream), p);
   count_launch();
   return finish_launch("attention_tc");
 }
@@ -522,7 +526,7 @@ extern "C" int unav_maxsig_gate_tc(const void* x, long long ldx, int x_col0, con
     smem_set = smem;
   }
   dim3 grid((T + 127) / 128, H, nb);
-  maxsig_tcgen05_kernel<<<grid, 192, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(maxsig_tcgen05_kernel, dim3(grid), dim3(192), smem, reinterpret_cast<cudaStream_t>(stream), p);
   count_launch();
   return finish_launch("maxsig_gate_tc");
 }

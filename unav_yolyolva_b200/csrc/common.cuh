@@ -28,6 +28,28 @@ int finish_launch(const char* what);  // cudaGetLastError -> code, records messa
     }                                      \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------
+// Every kernel of the hot path is launched with cudaLaunchAttributeProgrammaticStreamSerialization, so the NEXT
+// kernel's CTAs may be scheduled (launch latency, smem carve-up, barrier init, TMEM allocation, tensor-map prefetch)
+// while this one is still running.  Protocol: no global-memory access before pdl_wait(); pdl_wait() blocks until the
+// preceding grid has completed and flushed; pdl_launch_dependents() right after it lets the successor start its own
+// prologue.  Opt-in with UNAV_PDL=1 (without the launch attribute the device-side calls are no-ops).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- small device helpers ---------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

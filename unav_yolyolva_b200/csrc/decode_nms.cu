@@ -56,6 +56,8 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int* warp_tot, int* to
 
 __global__ void __launch_bounds__(DEC_THREADS)
 decode_kernel(const __grid_constant__ DecodeParams p) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   extern __shared__ __align__(16) float dec_p[];      // [n] probabilities of this (video, level), computed once
   __shared__ int hist[256];
   __shared__ int warp_tot[DEC_THREADS / 32];
@@ -215,6 +217,8 @@ struct NmsParams {
 // One block per (class, video).  Candidates of the class are gathered in slot order into shared memory;
 // each round takes the best live one (ties: lowest slot), emits it and decays the rest.
 __global__ void softnms_kernel(const __grid_constant__ NmsParams p) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   extern __shared__ __align__(16) uint8_t nms_smem[];
   float* x1 = reinterpret_cast<float*>(nms_smem);
   float* x2 = x1 + p.maxn;
@@ -336,6 +340,8 @@ struct MergeParams {
 
 __global__ void __launch_bounds__(256)
 merge_kernel(const __grid_constant__ MergeParams p) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   __shared__ float red_s[8];
   __shared__ int red_c[8];
   __shared__ int s_win;
@@ -440,6 +446,8 @@ struct LazyNmsParams {
 
 __global__ void __launch_bounds__(256)
 softnms_lazy_kernel(const __grid_constant__ LazyNmsParams p) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   extern __shared__ __align__(16) uint8_t lz_smem[];
   float* x1 = reinterpret_cast<float*>(lz_smem);
   float* x2 = x1 + p.cap;
@@ -638,7 +646,7 @@ extern "C" int unav_decode(const float* logits, const float* offsets, const uint
     smem_set = smem;
   }
   dim3 grid(L, B);
-  decode_kernel<<<grid, DEC_THREADS, smem, s>>>(p);
+  launch_pdl(decode_kernel, dim3(grid), dim3(DEC_THREADS), smem, s, p);
   count_launch();
   return finish_launch("decode");
 }
@@ -676,7 +684,7 @@ extern "C" int unav_softnms_batched(const float* cand_segs, const float* cand_sc
       q.out_segs = out_segs; q.out_scores = out_scores; q.out_labels = out_labels; q.out_counts = out_counts;
       q.cap = cap; q.ncls = ncls; q.method = method; q.max_seg = max_seg_num;
       q.iou_thr = iou_threshold; q.sigma = sigma; q.min_score = min_score;
-      softnms_lazy_kernel<<<B, 256, lz, s>>>(q);
+      launch_pdl(softnms_lazy_kernel, dim3(B), dim3(256), lz, s, q);
       count_launch();
       return finish_launch("softnms_lazy");
     }
@@ -701,7 +709,7 @@ extern "C" int unav_softnms_batched(const float* cand_segs, const float* cand_sc
   }
   const int threads = p.maxn <= 1024 ? 32 : 256;
   dim3 grid(ncls, B);
-  softnms_kernel<<<grid, threads, smem, s>>>(p);
+  launch_pdl(softnms_kernel, dim3(grid), dim3(threads), smem, s, p);
   count_launch();
   int rc = finish_launch("softnms");
   if (rc) return rc;
@@ -709,7 +717,7 @@ extern "C" int unav_softnms_batched(const float* cand_segs, const float* cand_sc
   m.ws_dets = p.ws_dets; m.ws_counts = p.ws_counts; m.vid_meta = vid_meta;
   m.out_segs = out_segs; m.out_scores = out_scores; m.out_labels = out_labels; m.out_counts = out_counts;
   m.ncls = ncls; m.max_seg = max_seg_num;
-  merge_kernel<<<B, 256, 0, s>>>(m);
+  launch_pdl(merge_kernel, dim3(B), dim3(256), 0, s, m);
   count_launch();
   return finish_launch("softnms_merge");
 }

@@ -22,6 +22,8 @@ constexpr int SBM = 64, SBN = 64, SBK = 16;
 
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const __grid_constant__ SimtParams p) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   const SimtGroup& g = p.g[blockIdx.z];
   __shared__ float As[SBK][SBM + 4];
   __shared__ float Ws[SBK][SBN + 4];
@@ -108,7 +110,7 @@ static int gemm_simt(const UnavGemmGroup* groups, int ngroups, int M, int N, int
   }
   p.M = M; p.N = N; p.K = K; p.op_dtype = op_dtype; p.act = act; p.res_masked = res_masked;
   dim3 grid((M + SBM - 1) / SBM, (N + SBN - 1) / SBN, ngroups);
-  gemm_simt_kernel<<<grid, 256, 0, stream>>>(p);
+  launch_pdl(gemm_simt_kernel, dim3(grid), dim3(256), 0, stream, p);
   count_launch();
   return finish_launch("gemm_simt");
 }

@@ -168,6 +168,9 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
 
   // Two k-loop schedules for the split (3-pass) mode:
   //   once = 1  stage = [A_hi | A_lo | W_hi | W_lo]; every operand part is loaded ONCE per k-block and consumed by the
@@ -425,7 +428,7 @@ static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
   while (stages * per_stage < 128 * (BN + 4) * 4) ++stages;      // room for the staging tile
   while (TcSmem<BN>::total(stages, nparts) > MAX_SMEM) --stages;
   p.stages = stages;
-  gemm_tcgen05_kernel<BN><<<grid, TC_THREADS, TcSmem<BN>::total(stages, nparts), stream>>>(p);
+  launch_pdl(gemm_tcgen05_kernel<BN>, dim3(grid), dim3(TC_THREADS), TcSmem<BN>::total(stages, nparts), stream, p);
   count_launch();
   return finish_launch("gemm_tcgen05");
 }

@@ -1,6 +1,7 @@
 // lib.cu — library-level entry points: version, per-thread error string, device check, launch counter.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -15,6 +16,17 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // measured on B200 (scripts/gemm_probe.py): -0.8 us per back-to-back tiny GEMM, no change on the whole forward,
+    // so the attribute is opt-in (UNAV_PDL=1)
+    const char* e = getenv("UNAV_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

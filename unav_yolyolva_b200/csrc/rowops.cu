@@ -19,6 +19,8 @@ struct LnParams {
 
 __global__ void __launch_bounds__(128)
 ln_rows_kernel(const __grid_constant__ LnParams p) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   const UnavLnGroup& g = p.g[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const long long r = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
@@ -110,6 +112,8 @@ constexpr int DW_ROWS = 16;   // output rows per block (one tile never crosses a
 // LayerNorm with warp-shuffle reductions, vectorised FP32 / operand stores.
 __global__ void __launch_bounds__(256)
 dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   extern __shared__ __align__(16) float dw_smem[];
   const UnavDwLnGroup& g = p.g[blockIdx.y];
   const int C = p.C;
@@ -243,6 +247,8 @@ struct CopyParams {
 
 __global__ void __launch_bounds__(256)
 rowcopy_kernel(const __grid_constant__ CopyParams p) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   const UnavCopyJob& jb = p.j[blockIdx.y];
   const int cv = jb.C / 4;
   const long long per_row = static_cast<long long>(jb.ntaps) * cv;
@@ -270,6 +276,8 @@ rowcopy_kernel(const __grid_constant__ CopyParams p) {
 __global__ void __launch_bounds__(256)
 transpose_cast_kernel(const float* __restrict__ in, long long ld_in, void* out, long long ld_out, int R, int Cc,
                       int op_dtype) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -299,6 +307,8 @@ __global__ void __launch_bounds__(128)
 align_embed_kernel(const float* __restrict__ x0, const float* cls_v, const float* cls_a, const float* pos_v,
                    const float* pos_a, const float* type_v, const float* type_a, float* tokens, int nb, int T,
                    int C) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   // grid: (T+1, nb, 2)
   const int n = blockIdx.x, b = blockIdx.y, m = blockIdx.z;
   const float* cls = m ? cls_a : cls_v;
@@ -321,6 +331,8 @@ align_embed_kernel(const float* __restrict__ x0, const float* cls_v, const float
 // =============================================================================================
 __global__ void build_masks_kernel(const uint8_t* __restrict__ mask, uint8_t* out_true, uint8_t* out_up,
                                    uint8_t* out_cls, uint8_t* out_heads, int nb, int nb_src, int T, int L) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   long long off = 0, off_up = 0;
   int lvl_off = 0;
   const int Ttot = 2 * T - (T >> (L - 1));
@@ -358,6 +370,8 @@ __global__ void __launch_bounds__(128)
 pool_match_kernel(const float* __restrict__ u0, const float* __restrict__ u1, const float* __restrict__ u2, int T0,
                   int T1, int T2, long long ldu, const float* __restrict__ Wm, const float* __restrict__ bm,
                   float* q, long long ldq, int C, int Tq, int P) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   extern __shared__ float sm[];          // pooled[3P][128] then Wm[Tq][3P], bm[Tq]
   float* pooled = sm;
   float* ws = sm + 3 * P * 128;
@@ -398,6 +412,8 @@ constexpr int MS_TR = 32, MS_TN = 64;
 __global__ void __launch_bounds__(128)
 maxsig_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ G, long long ldg,
               const float* __restrict__ head_bias, float* gate, int T, int nwords, int H, int hc) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   __shared__ float Xs[64][MS_TR + 4];   // [k][row]
   __shared__ float Gs[64][MS_TN + 4];   // [k][n]
   const int b = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * MS_TR;
@@ -473,7 +489,7 @@ extern "C" int unav_layernorm_rows(const UnavLnGroup* groups, int ngroups, int M
   }
   p.M = M; p.C = C; p.act = act; p.op_dtype = op_dtype; p.eps = eps;
   dim3 grid((M + 3) / 4, ngroups);
-  ln_rows_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(ln_rows_kernel, dim3(grid), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), p);
   count_launch();
   return finish_launch("layernorm_rows");
 }
@@ -498,7 +514,7 @@ extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg
     smem_set = smem;
   }
   dim3 grid(static_cast<unsigned>(nseg * tiles_per_seg), ngroups);
-  dwconv_ln_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(dwconv_ln_kernel, dim3(grid), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), p);
   count_launch();
   return finish_launch("dwconv_ln");
 }
@@ -518,7 +534,7 @@ extern "C" int unav_rowcopy(const UnavCopyJob* jobs, int njobs, int op_dtype, vo
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   dim3 grid(static_cast<unsigned>(blocks), njobs);
-  rowcopy_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(rowcopy_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p);
   count_launch();
   return finish_launch("rowcopy");
 }
@@ -527,7 +543,7 @@ extern "C" int unav_transpose_cast(const float* in, long long ld_in, void* out, 
                                    int Cc, int op_dtype, void* stream) {
   UNAV_REQUIRE(in && out && nb > 0 && R > 0 && Cc > 0, "transpose_cast: bad arguments");
   dim3 grid((Cc + 31) / 32, (R + 31) / 32, nb);
-  transpose_cast_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, ld_in, out, ld_out, R, Cc, op_dtype);
+  launch_pdl(transpose_cast_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), in, ld_in, out, ld_out, R, Cc, op_dtype);
   count_launch();
   return finish_launch("transpose_cast");
 }
@@ -537,7 +553,7 @@ extern "C" int unav_align_embed(const float* x0, const float* cls_v, const float
                                 int nb, int T, int C, void* stream) {
   UNAV_REQUIRE(x0 && tokens && C % 4 == 0, "align_embed: bad arguments");
   dim3 grid(T + 1, nb, 2);
-  align_embed_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x0, cls_v, cls_a, pos_v, pos_a, type_v,
+  launch_pdl(align_embed_kernel, dim3(grid), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), x0, cls_v, cls_a, pos_v, pos_a, type_v,
                                                                              type_a, tokens, nb, T, C);
   count_launch();
   return finish_launch("align_embed");
@@ -548,7 +564,7 @@ extern "C" int unav_build_masks(const uint8_t* mask, uint8_t* out_true, uint8_t*
   UNAV_REQUIRE(mask && out_true && (out_up || L == 1) && L >= 1 && (T % (1 << (L - 1))) == 0 && nb_src >= 1 &&
                    nb % nb_src == 0, "build_masks: bad arguments");
   int blocks = (nb * T + 255) / 256;
-  build_masks_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(mask, out_true, out_up, out_cls,
+  launch_pdl(build_masks_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), mask, out_true, out_up, out_cls,
                                                                                out_heads, nb, nb_src, T, L);
   count_launch();
   return finish_launch("build_masks");
@@ -566,7 +582,7 @@ extern "C" int unav_pool_match(const float* u0, const float* u1, const float* u2
     smem_set = smem;
   }
   dim3 grid((C + 127) / 128, nb);
-  pool_match_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(u0, u1, u2, T0, T1, T2, ldu, Wm, bm, q,
+  launch_pdl(pool_match_kernel, dim3(grid), dim3(128), smem, reinterpret_cast<cudaStream_t>(stream), u0, u1, u2, T0, T1, T2, ldu, Wm, bm, q,
                                                                               ldq, C, Tq, P);
   count_launch();
   return finish_launch("pool_match");
@@ -577,7 +593,7 @@ extern "C" int unav_maxsig_gate(const float* x, long long ldx, const float* G, l
   UNAV_REQUIRE(x && G && head_bias && gate, "maxsig_gate: null pointer");
   UNAV_REQUIRE(hc >= 1 && hc <= 64, "maxsig_gate: head channels %d > 64", hc);
   dim3 grid((T + MS_TR - 1) / MS_TR, H, nb);
-  maxsig_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ldx, G, ldg, head_bias, gate, T, nwords, H, hc);
+  launch_pdl(maxsig_kernel, dim3(grid), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), x, ldx, G, ldg, head_bias, gate, T, nwords, H, hc);
   count_launch();
   return finish_launch("maxsig_gate");
 }
