@@ -1,0 +1,97 @@
+"""BASELINE.json configs 4 and 5 as parity cases: long-sequence stress (max_seq_len = 2304, all FPN levels) and
+soft-NMS stress (100 classes, 10 100 overlapping candidates per video, low score threshold)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref as R
+from oracle import nms_ref
+from unav_yolyolva_b200 import kernels as K
+from unav_yolyolva_b200 import synth
+from unav_yolyolva_b200.config import TEST_CFG, default_model_cfg
+from unav_yolyolva_b200.modeling import make_multimodal_meta_arch
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_config4_long_sequence_T2304(cuda):
+    """The reference hard-codes T = 224 in its fusion module; here the guide length is the
+    max_seq_len argument, and the oracle restatement takes it from the weight shapes.  Attention is O(T^2) and runs
+    on the chunked CUDA-core kernel (key length > 256)."""
+    T = 2304
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    model = make_multimodal_meta_arch("LocPointTransformer", **default_model_cfg(max_seq_len=T))
+    manifest = {k: list(v.shape) for k, v in model.state_dict().items()}
+    sd = synth.trained_like_state_dict(manifest)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda).eval()
+    batch = synth.make_batch(1, T, first_index=3, len_lo=1200, len_hi=2304)
+    with torch.no_grad():
+        logits, offsets, masks = R.forward_logits(sd, batch["visual"], batch["audio"], batch["mask"])
+    ref_l, ref_o = torch.cat(logits, 1), torch.cat(offsets, 1)
+    Ttot = ref_l.shape[1]
+    assert Ttot == 4536
+    for mode, tol in (("fp32", 2e-5), ("bf16x3", 1e-4)):
+        model.precision, model.use_cuda_graph = mode, False
+        plan = model.run_hot_path(batch)
+        torch.cuda.synchronize()
+        lg = plan["logits"].cpu().view(1, Ttot, 100)
+        of = plan["offsets"].cpu().view(1, Ttot, 100, 2)
+        e1 = float((lg - ref_l).abs().max() / ref_l.abs().max())
+        e2 = float((of - ref_o).abs().max() / ref_o.abs().max())
+        print(f"[T=2304 {mode}] logits rel err {e1:.3e}, offsets rel err {e2:.3e}")
+        assert e1 <= tol and e2 <= 4 * tol
+        # decode + NMS stage vs the oracle on the device-produced candidates: bit-exact
+        cl = plan["cand_labels"][0].cpu().numpy()
+        keep = cl >= 0
+        r = nms_ref.batched_nms(plan["cand_segs"][0].cpu().numpy()[keep], plan["cand_scores"][0].cpu().numpy()[keep],
+                                cl[keep].astype(np.int64), TEST_CFG["iou_threshold"], TEST_CFG["min_score"],
+                                TEST_CFG["max_seg_num"], True, TEST_CFG["nms_sigma"])
+        assert np.array_equal(plan["out_labels"][0].cpu().numpy(), r[2])
+        assert np.array_equal(_bits(plan["out_scores"][0].cpu().numpy()), _bits(r[1]))
+
+
+def _stress_video(rng, n, ncls, skew):
+    if skew:   # 441 candidates in class 0, the rest spread
+        labels = np.concatenate([np.zeros(441, np.int64), rng.integers(1, ncls, n - 441)])
+        rng.shuffle(labels)
+    else:
+        labels = rng.integers(0, ncls, n)
+    ev = rng.uniform(0, 224, (ncls, 5))
+    centre = ev[labels, rng.integers(0, 5, n)] + rng.normal(0, 2.0, n)
+    half = rng.uniform(0.5, 20, n)
+    segs = np.stack([centre - half, centre + half], 1).astype(np.float32)
+    scores = rng.uniform(0.001, 1.0, n).astype(np.float32)
+    return segs, scores, labels
+
+
+@pytest.mark.parametrize("path", ["lazy_per_video", "per_class"])
+def test_config5_softnms_stress(cuda, path):
+    if path == "per_class":
+        os.environ["UNAV_NMS_PER_CLASS"] = "1"
+    try:
+        rng = np.random.default_rng(55)
+        B, cap, ncls = 4, 10100, 100
+        vids = [_stress_video(rng, cap, ncls, skew=(b % 2 == 1)) for b in range(B)]
+        segs = torch.from_numpy(np.stack([v[0] for v in vids])).to(cuda)
+        scores = torch.from_numpy(np.stack([v[1] for v in vids])).to(cuda)
+        labels = torch.from_numpy(np.stack([v[2] for v in vids]).astype(np.int32)).to(cuda)
+        o_s = torch.zeros(B, 100, 2, device=cuda); o_sc = torch.zeros(B, 100, device=cuda)
+        o_l = torch.zeros(B, 100, dtype=torch.int64, device=cuda); o_c = torch.zeros(B, dtype=torch.int32, device=cuda)
+        ws = torch.zeros(K.softnms_workspace_bytes(B, ncls, 100), dtype=torch.uint8, device=cuda)
+        K.softnms_batched(segs, scores, labels, B, cap, ncls, 0.7, 0.4, 1e-4, 2, 100, 441, None, o_s, o_sc, o_l, o_c, ws)
+        torch.cuda.synchronize()
+        for b in range(B):
+            r = nms_ref.batched_nms(vids[b][0], vids[b][1], vids[b][2], 0.7, 1e-4, 100, True, 0.4)
+            assert int(o_c[b]) == len(r[1]) == 100
+            assert np.array_equal(o_l[b].cpu().numpy(), r[2])
+            assert np.array_equal(_bits(o_sc[b].cpu().numpy()), _bits(r[1]))
+            assert np.array_equal(_bits(o_s[b].cpu().numpy()), _bits(r[0]))
+    finally:
+        os.environ.pop("UNAV_NMS_PER_CLASS", None)
