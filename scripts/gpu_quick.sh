@@ -1,2 +1,7 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_configs.py -q -m gpu --tb=short -s > gpurun_out/test_cfg.log 2>&1; echo "tests exit $?"; grep -E "rel err|passed|failed|Error|error" gpurun_out/test_cfg.log | head -20; tail -5 gpurun_out/test_cfg.log
+python bench.py --steps 30 --warmup 10 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; tail -3 gpurun_out/bench.err
+python - <<'PY'
+import json
+b=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
+print('value',round(b['value'],1),'ms/step',round(b['ms_per_step'],3),'e2e',round(b['e2e']['value'],1),round(b['e2e']['ms_per_step'],3),'launches',b['launches_per_step'], b['step_ms_min_med_max'], b['gather_ms'])
+PY

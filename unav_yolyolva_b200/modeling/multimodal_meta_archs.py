@@ -93,6 +93,29 @@ class PtTransformerRegHead(nn.Module):
         return _fwd.reg_head_forward(self, fpn_feats, fpn_masks)
 
 
+class PendingDetections:
+    """Handle returned by ``PtTransformer.submit``: detections of one step, landing in pinned host memory."""
+
+    def __init__(self, slot, event):
+        self._slot, self._event = slot, event
+
+    def done(self) -> bool:
+        return self._event.query()
+
+    def result(self):
+        """Host tensors {segments [B,K,2], scores [B,K], labels [B,K]} (views of the staging slot: consume or clone
+        them before submitting two more steps).  Same ragged-count error as ``forward``."""
+        self._event.synchronize()
+        counts = self._slot["counts"]
+        K_ = int(counts.max()) if counts.numel() else 0
+        if int(counts.min()) != K_:
+            raise RuntimeError("videos in the batch produced different numbers of detections "
+                               f"({counts.tolist()}); the reference's torch.cat fails the same way "
+                               "(multimodal_meta_archs.py:869-873)")
+        return {"segments": self._slot["segments"][:, :K_], "scores": self._slot["scores"][:, :K_],
+                "labels": self._slot["labels"][:, :K_]}
+
+
 @register_multimodal_meta_arch("LocPointTransformer")
 class PtTransformer(nn.Module):
     """Single-stage audio-visual event localiser; constructor identical to the reference (:267-295)."""
@@ -158,6 +181,7 @@ class PtTransformer(nn.Module):
         self.contrastive_losses = Dual_Contrastive_Loss()
         self._engine = None
         self._engine_key = None
+        self._host_ring = {}
 
     @property
     def device(self):
@@ -199,18 +223,64 @@ class PtTransformer(nn.Module):
         losses = {k: torch.zeros((), device=dev) for k in LOSS_KEYS}
         return results, losses
 
+    def _host_slot(self, B):
+        """Pinned host staging (video metadata in, detections out), two slots per batch size used alternately."""
+        ring = self._host_ring.get(B)
+        if ring is None:
+            K_ = self.test_max_seg_num
+            ring = {"next": 0, "slots": [
+                {"meta": torch.empty(B, 4, dtype=torch.float32).pin_memory(),
+                 "segments": torch.empty(B, K_, 2, dtype=torch.float32).pin_memory(),
+                 "scores": torch.empty(B, K_, dtype=torch.float32).pin_memory(),
+                 "labels": torch.empty(B, K_, dtype=torch.int64).pin_memory(),
+                 "counts": torch.empty(B, dtype=torch.int32).pin_memory(), "event": None} for _ in range(2)]}
+            self._host_ring[B] = ring
+        slot = ring["slots"][ring["next"]]
+        ring["next"] ^= 1
+        if slot["event"] is not None:
+            slot["event"].synchronize()         # its previous user (two submissions ago) must have retired
+        return slot
+
     @torch.no_grad()
-    def run_hot_path(self, video_list):
+    def run_hot_path(self, video_list, _slot=None):
         """Launch the whole device-resident path for one collate dict; returns the engine plan (outputs stay
         on the device, nothing is synchronised)."""
         vis, aud, mask = video_list["visual"], video_list["audio"], video_list["mask"]
         B = vis.shape[0]
-        meta = torch.tensor([[float(video_list["feat_stride"][i]), float(video_list["feat_num_frames"][i]),
-                              float(video_list["fps"][i]), float(video_list["duration"][i])] for i in range(B)],
-                            dtype=torch.float32)
-        if vis.device.type == "cpu" and not meta.is_pinned():
-            meta = meta.pin_memory()
-        return self.engine.run(vis, aud, mask, meta)
+        slot = _slot if _slot is not None else self._host_slot(B)
+        m = slot["meta"]
+        for i in range(B):
+            m[i, 0] = float(video_list["feat_stride"][i]); m[i, 1] = float(video_list["feat_num_frames"][i])
+            m[i, 2] = float(video_list["fps"][i]); m[i, 3] = float(video_list["duration"][i])
+        plan = self.engine.run(vis, aud, mask, m)
+        if _slot is None:                       # the slot's meta is in flight until this point of the stream
+            ev = torch.cuda.Event(); ev.record(); slot["event"] = ev
+        return plan
+
+    @torch.no_grad()
+    def submit(self, video_list):
+        """Asynchronous form of ``forward`` for evaluation loops: enqueue the step and the device->host copy of its
+        detections into pinned memory, return immediately.  ``handle.result()`` waits for that step only, so the host
+        work of step j+1 (collate, upload, launch) overlaps the device work of step j:
+
+            prev = None
+            for batch in CudaPrefetcher(loader, device):
+                cur = model.submit(batch)
+                if prev is not None: consume(prev.result())
+                prev = cur
+
+        At most two handles may be outstanding (the staging buffers are a ring of two)."""
+        if self.training:
+            raise NotImplementedError("training is outside the inference hot path (SURVEY.md §2 C16)")
+        B = video_list["visual"].shape[0]
+        slot = self._host_slot(B)
+        plan = self.run_hot_path(video_list, _slot=slot)
+        slot["segments"].copy_(plan["out_segs"], non_blocking=True)
+        slot["scores"].copy_(plan["out_scores"], non_blocking=True)
+        slot["labels"].copy_(plan["out_labels"], non_blocking=True)
+        slot["counts"].copy_(plan["out_counts"], non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(); slot["event"] = ev
+        return PendingDetections(slot, ev)
 
     def collect_results(self, plan):
         counts = plan["out_counts"].cpu()
