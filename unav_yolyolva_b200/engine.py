@@ -607,3 +607,20 @@ class HotPathEngine:
                     P["graph"] = g
                 P["graph"].replay()
         return P
+
+    def capture_traced(self, B: int):
+        """A second CUDA graph of the same launches with an event-record node on each side of every kernel
+        (bench.py's roofline leg).  Returns (graph, records); after ``graph.replay()`` + synchronize,
+        ``kernels.read_trace(records)`` gives the per-launch durations of that replay."""
+        P = self._plan(B)
+        with torch.cuda.device(self.dev):
+            self._launch_all(P)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            K.start_trace(external=True)
+            try:
+                with torch.cuda.graph(g):
+                    self._launch_all(P)
+            finally:
+                rec = K.stop_trace(read=False)
+        return g, rec

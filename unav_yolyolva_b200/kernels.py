@@ -23,18 +23,29 @@ def _stream() -> int:
 # ---- optional per-launch tracing (bench.py's roofline leg): CUDA events on the launching stream around each
 # C-ABI call, plus the algorithmic FLOPs / bytes of the call.  Off (None) on the product path.
 _TRACE: Optional[list] = None
+_TRACE_EXTERNAL = False
 
 
-def start_trace() -> None:
-    global _TRACE
+def start_trace(external: bool = False) -> None:
+    """external=True: the events become event-record NODES when the calls are being captured into a CUDA graph, so the
+    same spans can be read after every replay (per-kernel times without the CPU launch gaps of an eager pass)."""
+    global _TRACE, _TRACE_EXTERNAL
     _TRACE = []
+    _TRACE_EXTERNAL = external
 
 
-def stop_trace() -> list:
-    """Returns [(kernel, ms, flops, bytes, note)] for the calls issued since start_trace()."""
+def stop_trace(read: bool = True) -> list:
+    """Returns [(kernel, ms, flops, bytes, note)] for the calls issued since start_trace(); with read=False the raw
+    [(kernel, ev_a, ev_b, flops, bytes, note)] records (for spans captured into a graph: read them after a replay)."""
     global _TRACE
     rec, _TRACE = _TRACE or [], None
+    if not read:
+        return rec
     torch.cuda.synchronize()
+    return read_trace(rec)
+
+
+def read_trace(rec: list) -> list:
     return [(name, a.elapsed_time(b), fl, by, note) for name, a, b, fl, by, note in rec]
 
 
@@ -44,8 +55,9 @@ class _Span:
 
     def __enter__(self):
         if _TRACE is not None:
-            self.a = torch.cuda.Event(enable_timing=True)
-            self.b = torch.cuda.Event(enable_timing=True)
+            kw = {"external": True} if _TRACE_EXTERNAL else {}
+            self.a = torch.cuda.Event(enable_timing=True, **kw)
+            self.b = torch.cuda.Event(enable_timing=True, **kw)
             self.a.record()
         return self
 
