@@ -8,7 +8,9 @@ from unav_yolyolva_b200 import kernels as K
 SHAPES = [(2, 3584, 2048, 512, K.ACT_GELU), (1, 448, 256, 256, 0), (6, 3584, 512, 512, 0), (1, 7056, 1024, 3072, 0),
           (3, 3584, 256, 256, 0), (1, 16384, 1280, 224, 0), (2, 3584, 512, 2048, 0), (1, 448, 256, 512, 0),
           (1, 448, 256, 1024, 0), (1, 448, 512, 1536, 0), (1, 3584, 512, 1536, 0), (1, 896, 256, 256, 0), (1, 448, 256, 64, 0),
-          (1, 128, 64, 64, 0)]
+          (1, 128, 64, 64, 0), (1, 7200, 1536, 512, 0), (2, 7056, 512, 1536, 0), (1, 7168, 512, 1536, 0), (3, 7168, 512, 512, 0),
+          (1, 7168, 512, 1024, 0), (2, 3584, 512, 512, 0), (1, 7200, 512, 512, 0), (3, 7168, 256, 256, 0), (3, 1792, 256, 256, 0),
+          (1, 1792, 512, 1536, 0), (1, 896, 512, 1536, 0), (1, 3584, 256, 768, 0), (1, 7056, 200, 1536, 0)]
 dev = torch.device("cuda", 0)
 only = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1] != "all" else None
 op = K.BF16X2 if (len(sys.argv) < 3 or sys.argv[2] == "x3") else K.BF16

@@ -175,6 +175,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
         for (int kb = 0; kb < nkv; ++kb)
           tma_load_2d(kv_smem + (pt * nkv + kb) * v_box, &g.tmV[pt], bar_v, kb * 64, b * p.nh * hs + h * hs);
     }
+    __syncwarp();     // lanes 1..31 wait for the elected lane: the block barrier at the end must see whole warps
   } else if (warp == 1) {
     if (lane == 0) {
       // ---- S = Q.K^T : segments (Qhi,Khi), (Qlo,Khi), (Qhi,Klo)
@@ -209,6 +210,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
       }
       tc_commit(bar_o);
     }
+    __syncwarp();
   } else {
     // ===== softmax / epilogue warps: one query row per thread =====
     const int qd = warp & 3;
@@ -397,6 +399,7 @@ maxsig_tcgen05_kernel(const __grid_constant__ MaxsigTcParams p) {
           tma_load_2d(g_smem + (pt * nhalf + hf) * g_box, &p.tmG[pt], bar_ld, p.g_col0 + h * p.hc, b * p.nwords + hf * 256);
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
       mbar_wait(bar_ld, 0);
@@ -415,6 +418,7 @@ maxsig_tcgen05_kernel(const __grid_constant__ MaxsigTcParams p) {
       }
       tc_commit(bar_s);
     }
+    __syncwarp();
   } else {
     const int qd = warp & 3;
     const int t = t0 + qd * 32 + lane;

@@ -27,7 +27,7 @@
 namespace unav {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B span
+constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B span (BK = 32: 64-byte rows, SWIZZLE_64B)
 constexpr int TC_STAGES = 3;          // default ring depth: 3 x 32 KB (BN = 128) -> two CTAs per SM, one's epilogue overlaps the other's k-loop
 constexpr int TC_MAX_STAGES = 8;      // deep ring for sub-wave grids: bytes in flight per SM = stages x stage size (latency bound)
 constexpr int TC_THREADS = 320;       // TMA warp + MMA warp + 8 epilogue warps
@@ -41,7 +41,12 @@ struct TcGroup {
 struct TcParams {
   TcGroup g[UNAV_MAX_GROUPS];
   int M, N, K, op_dtype, act, res_masked, nseg, stages, once;
+  long long* phase;    // diagnostics (unav_gemm_set_phase_trace): 8 clock64 stamps per CTA, or nullptr
+  int phase_cap;
 };
+
+static long long* g_phase_buf = nullptr;
+static int g_phase_cap = 0;
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -53,13 +58,16 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// The suspend-time hint lets the hardware park the waiting warp until the phase completes (or the hint expires)
+// instead of re-issuing the poll every ~100 clocks: in the first captures the polling of the 8 epilogue warps and the
+// producer was 3/4 of all issued warp-instructions and competed with the co-resident CTA's epilogue for issue slots.
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x10000u) : "memory");
   return ok;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -107,13 +115,16 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) |
 //   [32,46) SBO >> 4 = 1024 B (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+// BK = 32 (64-byte rows): SWIZZLE_64B, SBO = 8 rows x 64 B = 512 B, layout = 4.
+template <int BK = 64>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  static_assert(BK == 64 || BK == 32, "K-major operand rows are 128 or 64 bytes");
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>((8 * BK * 2) >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(BK == 64 ? 2 : 4) << 61;
   return d;
 }
 
@@ -124,23 +135,69 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, int BK = TC_BK>
 struct TcSmem {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
-  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int A_BYTES = TC_BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int total(int stages, int nparts) { return STAGE_BYTES * nparts * stages + 256 + 1024; }   // + barriers + slack
 };
 
-template <int BN>
+// Phase B of the epilogue for full-width, 16-byte aligned tiles: one instantiation per (activation, operand format) so
+// the row loop carries no dtype / activation dispatch (the generic loop below executed ~170 instructions per float4).
+// Each lane owns 4 consecutive columns of RPP-strided rows; four rows are in flight per lane.
+template <int ACT, bool SPLIT, int PITCH, int RPP>
+__device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const float* stg_lane, long long m_base, int rows,
+                                                   int rsub, int n, int res_masked, const float (&bias)[4],
+                                                   const float (&cs)[4]) {
+  const bool has_res = e.res != nullptr, has_gate = e.gate != nullptr, has_mask = e.rowmask != nullptr,
+             has_rs = e.rowscale != nullptr;
+  const long long op_split = e.ld_op / 2;
+  const int ggrp = has_gate ? n / e.gate_width : 0;       // gate_width % 4 == 0 on this path: one group per lane
+#pragma unroll 4
+  for (int r = rsub; r < rows; r += RPP) {
+    const long long m = m_base + r;
+    const float4 a4 = *reinterpret_cast<const float4*>(stg_lane + r * PITCH);
+    float v[4] = {a4.x, a4.y, a4.z, a4.w};
+    float mk = 1.f, mrs = 1.f;
+    if (has_mask) { mk = e.rowmask[m] ? 1.f : 0.f; mrs = mk; }
+    if (has_rs) mrs *= __ldg(e.rowscale + m);
+    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_res) rr = *reinterpret_cast<const float4*>(e.res + m * e.ldres + n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (v[i] + bias[i]) * mrs;
+    if (has_gate) {
+      const float gt = __ldg(e.gate + m * e.gate_groups + ggrp);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] *= gt;
+    }
+    if (ACT != UNAV_ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], ACT);
+    }
+    if (has_res) {
+      const float rm = res_masked ? mk : 1.f;
+      v[0] = rr.x * rm + cs[0] * v[0]; v[1] = rr.y * rm + cs[1] * v[1];
+      v[2] = rr.z * rm + cs[2] * v[2]; v[3] = rr.w * rm + cs[3] * v[3];
+    }
+    if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + m * e.ld_f32 + n) = make_float4(v[0], v[1], v[2], v[3]);
+    if (e.out_op) {
+      char* row = reinterpret_cast<char*>(e.out_op) + static_cast<size_t>(m) * e.ld_op * 2;
+      store_op4(row, SPLIT ? UNAV_BF16X2 : UNAV_BF16, n, op_split, make_float4(v[0], v[1], v[2], v[3]));
+    }
+  }
+}
+
+template <int BN, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+  using Sm = TcSmem<BN, BK>;
   extern __shared__ uint8_t smem_raw[];
   const TcGroup& g = p.g[blockIdx.z];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
   const int NS = p.stages;
-  const uint32_t bar_base = base + TcSmem<BN>::STAGE_BYTES * ((p.once && p.nseg > 1) ? 2 : 1) * NS;
+  const uint32_t bar_base = base + Sm::STAGE_BYTES * ((p.once && p.nseg > 1) ? 2 : 1) * NS;
   // barriers: full[s] at +8s, empty[s] at +8(S+s), accum at +8(2S); tmem slot at +8(2S+1)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
@@ -149,7 +206,15 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
 
   const int m0 = blockIdx.x * TC_BM;
   const int n0 = blockIdx.y * BN;
-  const int nkb = (p.K + TC_BK - 1) / TC_BK;
+  const int nkb = (p.K + BK - 1) / BK;
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  long long* ph_out = (p.phase && cta_lin < p.phase_cap) ? p.phase + 8ll * cta_lin : nullptr;
+  if (ph_out && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    ph_out[0] = smid;
+    ph_out[1] = clock64();
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&g.tmA[0]);
@@ -171,18 +236,16 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail
   pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
   pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
+  if (ph_out && threadIdx.x == 0) ph_out[2] = clock64();          // setup done
 
-  // Two k-loop schedules for the split (3-pass) mode:
-  //   once = 1  stage = [A_hi | A_lo | W_hi | W_lo]; every operand part is loaded ONCE per k-block and consumed by the
-  //             three MMA groups (Ahi.Whi, Alo.Whi, Ahi.Wlo): 2/3 of the L2->SMEM bytes.  Used for grids of at most
-  //             two CTAs per SM-slot, where the ~40 B/clk per-SM L2 read port bounds the k-loop.
-  //   once = 0  stage = [A | W]; the three segments are streamed one after the other (3 * nkb iterations).  Half the
-  //             smem per stage, so two CTAs fit per SM and one's epilogue overlaps the other's k-loop: better for
-  //             multi-wave grids (measured with scripts/gemm_probe.py).
+  // Stage layout: plain BF16 operands [A | W]; split operands [A_hi | A_lo | W_hi | W_lo] — every operand part is loaded
+  // ONCE per k-block and consumed by the three MMA groups (Ahi.Whi, Alo.Whi, Ahi.Wlo).  (An earlier schedule streamed
+  // the three segments through [A | W] stages: 1.5x the L2->SMEM bytes, slower everywhere once BK = 32 stages made the
+  // combined layout fit twice per SM; it also accumulated in a different order.)
   const int nparts = (p.once && p.nseg > 1) ? 2 : 1;
-  const uint32_t stage_bytes = nparts * TcSmem<BN>::STAGE_BYTES;
-  const uint32_t w_off = nparts * TcSmem<BN>::A_BYTES;
-  const int iters = p.once ? nkb : nkb * p.nseg;
+  const uint32_t stage_bytes = nparts * Sm::STAGE_BYTES;
+  const uint32_t w_off = nparts * Sm::A_BYTES;
+  const int iters = nkb;
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
@@ -194,42 +257,59 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
         const uint32_t sa = base + s * stage_bytes;
         if (p.once) {
           for (int pt = 0; pt < nparts; ++pt) {
-            tma_load_2d(sa + pt * TcSmem<BN>::A_BYTES, &g.tmA[pt], full_bar(s), it * TC_BK, m0);
-            tma_load_2d(sa + w_off + pt * TcSmem<BN>::B_BYTES, &g.tmW[pt], full_bar(s), it * TC_BK, n0);
+            tma_load_2d(sa + pt * Sm::A_BYTES, &g.tmA[pt], full_bar(s), it * BK, m0);
+            tma_load_2d(sa + w_off + pt * Sm::B_BYTES, &g.tmW[pt], full_bar(s), it * BK, n0);
           }
         } else {
-          // k-block major, segment minor: the SAME accumulation order as the once-schedule, so results are
-          // bit-identical whichever schedule / tile width the grid size selects (batch-size independent outputs)
-          const int kb = it / p.nseg, seg = it - kb * p.nseg;   // 0 = (Ahi,Whi), 1 = (Alo,Whi), 2 = (Ahi,Wlo)
-          tma_load_2d(sa, &g.tmA[seg == 1 ? 1 : 0], full_bar(s), kb * TC_BK, m0);
-          tma_load_2d(sa + w_off, &g.tmW[seg == 2 ? 1 : 0], full_bar(s), kb * TC_BK, n0);
+          tma_load_2d(sa, &g.tmA[0], full_bar(s), it * BK, m0);
+          tma_load_2d(sa + w_off, &g.tmW[0], full_bar(s), it * BK, n0);
         }
       }
     }
+    __syncwarp();     // lanes 1..31 wait here for the producer lane: the block barrier below must see whole warps
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = make_idesc(TC_BM, BN);
-      const int nseg_in = p.once ? p.nseg : 1;
+      const int nseg_in = p.nseg;
       for (int it = 0; it < iters; ++it) {
         const int s = it % NS;
         const uint32_t ph = (it / NS) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+        if (ph_out && it == 0) ph_out[3] = clock64();             // first operands landed
         const uint32_t sa = base + s * stage_bytes;
-        for (int seg = 0; seg < nseg_in; ++seg) {
-          const uint64_t adesc = make_smem_desc(sa + (seg == 1 ? TcSmem<BN>::A_BYTES : 0));
-          const uint64_t bdesc = make_smem_desc(sa + w_off + (seg == 2 ? TcSmem<BN>::B_BYTES : 0));
+        // Canonical accumulation order of the split mode, the same for every tile shape / schedule so that results
+        // do not depend on the grid (batch-size independent outputs): K in steps of 32 columns; inside a step
+        // hi.hi, lo.hi, hi.lo; inside a segment the two k=16 MMAs in order.
+        if (nseg_in > 1) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (addr >> 4) field
-            tc_mma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || seg > 0 || k > 0) ? 1u : 0u);
+          for (int h32 = 0; h32 < BK / 32; ++h32) {
+#pragma unroll
+            for (int seg = 0; seg < 3; ++seg) {
+              const uint64_t adesc = make_smem_desc<BK>(sa + (seg == 1 ? Sm::A_BYTES : 0));
+              const uint64_t bdesc = make_smem_desc<BK>(sa + w_off + (seg == 2 ? Sm::B_BYTES : 0));
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                // advance 16 bf16 = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
+                const uint32_t ko = 2u * (h32 * 2 + k);
+                tc_mma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, (it > 0 || h32 > 0 || seg > 0 || k > 0) ? 1u : 0u);
+              }
+            }
           }
+        } else {
+          const uint64_t adesc = make_smem_desc<BK>(sa);
+          const uint64_t bdesc = make_smem_desc<BK>(sa + w_off);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
         tc_commit(empty_bar(s));        // frees the ring slot once these MMAs have read it
       }
       tc_commit(accum_bar);             // accumulator complete
+      if (ph_out) ph_out[4] = clock64();                          // last MMA issued
     }
+    __syncwarp();     // same for the MMA issuer's warp
   } else {
     // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     // Phase A: tcgen05.ld (one accumulator row per thread) -> padded FP32 staging tile in the (now idle)
@@ -243,6 +323,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
     const int q = warp & 3, half = (warp - 2) >> 2;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (ph_out && threadIdx.x == 64) ph_out[5] = clock64();       // accumulator ready
     float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * 32 * PITCH + half * HALF;
 #pragma unroll 1
     for (int c = 0; c < HALF / 32; ++c) {
@@ -295,7 +376,31 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
         }
       }
     }
-    if (nvalid > 0 && (e.out_f32 || e.out_op)) {
+    // CTA-uniform test for the specialised row loop: full-width tile and every vector access 16-byte aligned
+    const bool fast = (n0 + BN <= p.N) && (!e.out_f32 || (((reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0) && e.ld_f32 % 4 == 0)) &&
+                      (!has_res || (((reinterpret_cast<uintptr_t>(e.res) & 15) == 0) && e.ldres % 4 == 0)) &&
+                      (!e.out_op || (((reinterpret_cast<uintptr_t>(e.out_op) & 7) == 0) && e.ld_op % 4 == 0 && op_split % 4 == 0)) &&
+                      (!has_gate || e.gate_width % 4 == 0);
+    if (fast && (e.out_f32 || e.out_op)) {
+      const long long m_base = static_cast<long long>(m0) + q * 32;
+      const int rows = static_cast<int>(min(32ll, static_cast<long long>(p.M) - m_base));
+      const float* sl = stg + cl * 4;
+      const bool split = p.op_dtype == UNAV_BF16X2;
+#define UNAV_EPI_CASE(A)                                                                                          \
+      case A:                                                                                                       \
+        if (split) epilogue_rows_fast<A, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, bias, cs);   \
+        else epilogue_rows_fast<A, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, bias, cs);        \
+        break;
+      switch (act) {
+        UNAV_EPI_CASE(UNAV_ACT_RELU)
+        UNAV_EPI_CASE(UNAV_ACT_GELU)
+        UNAV_EPI_CASE(UNAV_ACT_SILU)
+        default:
+          if (split) epilogue_rows_fast<UNAV_ACT_NONE, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, bias, cs);
+          else epilogue_rows_fast<UNAV_ACT_NONE, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, bias, cs);
+      }
+#undef UNAV_EPI_CASE
+    } else if (nvalid > 0 && (e.out_f32 || e.out_op)) {
 #pragma unroll 2
       for (int r = rsub; r < 32; r += RPP) {
         const long long m = static_cast<long long>(m0) + q * 32 + r;
@@ -350,8 +455,10 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       }
     }
   }
+  if (ph_out && threadIdx.x == 64) ph_out[6] = clock64();         // this warp's epilogue done
   tc_fence_before();
   __syncthreads();
+  if (ph_out && threadIdx.x == 0) ph_out[7] = clock64();          // all warps done
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
@@ -377,18 +484,18 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D K-major BF16 tensor map: dims {K, rows}, row stride ld elements, box {64, box_rows}, SWIZZLE_128B,
-// out-of-bounds elements read as zero (ragged M / N / K tails need no special casing in the kernel).
-static int encode_map(CUtensorMap* map, const void* ptr, long long rows, long long K, long long ld, int box_rows) {
+// 2-D K-major BF16 tensor map: dims {K, rows}, row stride ld elements, box {bk, box_rows}, SWIZZLE_128B (bk = 64) or
+// SWIZZLE_64B (bk = 32); out-of-bounds elements read as zero (ragged M / N / K tails need no special casing in the kernel).
+static int encode_map(CUtensorMap* map, const void* ptr, long long rows, long long K, long long ld, int box_rows, int bk) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return UNAV_ERR_DRIVER;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(TC_BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld K=%lld ld=%lld", (int)r, ptr, rows, K, ld);
     return UNAV_ERR_DRIVER;
@@ -396,28 +503,66 @@ static int encode_map(CUtensorMap* map, const void* ptr, long long rows, long lo
   return 0;
 }
 
-template <int BN>
+constexpr int TC_SLOTS = 296;      // 2 resident CTAs x 148 SMs
+
+// Tile / schedule choice.  All choices accumulate every output element in the same order (k ascending; hi.hi, lo.hi,
+// hi.lo inside a k-step of 16), so the result does not depend on it — only the time does (scripts/gemm_probe.py):
+//   bn     128 unless the 128-wide grid leaves most SMs idle
+//   sched  0 = plain BF16 operands, [A|W] stages of BK=64
+//          1 = split operands, BK=64: [A_hi|A_lo|W_hi|W_lo] per stage, 64 KB stages (BN=128): the ring only fits one
+//              CTA per SM, so it is for grids of at most one CTA per SM
+//          2 = split operands, BK=32 (SWIZZLE_64B): 32 KB stages, two CTAs stay resident per SM
+struct TcChoice { int bn, sched; };
+static TcChoice choose_tile(int M, int N, int K, int ngroups, int nseg) {
+  const long long mt = (M + TC_BM - 1) / TC_BM;
+  const long long tiles128 = mt * ((N + 127) / 128) * ngroups;
+  const long long tiles64 = mt * ((N + 63) / 64) * ngroups;
+  // measured with scripts/gemm_probe.py over the 27 shapes of the batch-16 path
+  TcChoice c;
+  if (nseg == 1) {
+    c.bn = (N <= 64 || tiles128 < 240) ? 64 : 128;
+    c.sched = 0;
+  } else if (N > 64 && tiles128 > 148) {
+    c.bn = 128; c.sched = 2;        // multi-CTA-per-SM grids: 32 KB stages keep two CTAs resident
+  } else if (N > 64 && tiles128 >= 100) {
+    c.bn = 128; c.sched = 1;        // about one CTA per SM: long 64 KB stages, fewer barrier round trips
+  } else {
+    c.bn = 64; c.sched = 1;         // small grids: more CTAs, 48 KB stages
+  }
+  (void)tiles64;
+  if (const char* env = getenv("UNAV_TC_BN")) {            // experiment knobs (scripts/gemm_probe.py)
+    const int v = atoi(env);
+    if (v == 64 || v == 128) c.bn = v;
+  }
+  if (const char* env = getenv("UNAV_TC_ONCE")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= 2) c.sched = nseg == 1 ? 0 : v;
+  }
+  return c;
+}
+
+template <int BN, int BK>
 static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
   static bool attr_set = false;
   constexpr int MAX_SMEM = 200 * 1024;
+  using Sm = TcSmem<BN, BK>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm_tcgen05<%d>): %s", BN, cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(gemm_tcgen05<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
       return static_cast<int>(e);
     }
     attr_set = true;
   }
   dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + BN - 1) / BN, ngroups);
-  // Ring depth: big grids keep <= ~100 KB per CTA so two CTAs share an SM (one's epilogue overlaps the other's
-  // k-loop); sub-wave grids take a deeper ring.  The epilogue staging tile (128 x (BN+4) floats) must also fit.
+  // Ring depth: multi-CTA-per-SM grids keep <= ~100 KB per CTA so two CTAs share an SM (one's epilogue overlaps the
+  // other's k-loop); grids of at most one CTA per SM take a deeper ring.  The epilogue staging tile (128 x (BN+4)
+  // floats) must also fit in the ring's bytes.
   const long long ctas = static_cast<long long>(grid.x) * grid.y * grid.z;
-  p.once = (p.nseg > 1 && ctas <= 296) ? 1 : 0;
-  if (const char* env = getenv("UNAV_TC_ONCE")) p.once = (p.nseg > 1 && atoi(env)) ? 1 : 0;
   const int nparts = (p.once && p.nseg > 1) ? 2 : 1;
-  const int nkb = ((p.K + TC_BK - 1) / TC_BK) * (p.once ? 1 : p.nseg);
-  const int per_stage = TcSmem<BN>::STAGE_BYTES * nparts;
-  int stages = (ctas <= 148 ? 160 * 1024 : 100 * 1024) / per_stage;
+  const int nkb = (p.K + BK - 1) / BK;
+  const int per_stage = Sm::STAGE_BYTES * nparts;
+  int stages = (ctas <= 148 ? 192 * 1024 : 100 * 1024) / per_stage;
   if (const char* env = getenv("UNAV_TC_STAGES")) {            // experiment knob (scripts/gemm_probe.py)
     const int v = atoi(env);
     if (v >= 2) stages = v;
@@ -426,9 +571,9 @@ static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
   if (stages > nkb) stages = nkb;
   if (stages < 2) stages = 2;
   while (stages * per_stage < 128 * (BN + 4) * 4) ++stages;      // room for the staging tile
-  while (TcSmem<BN>::total(stages, nparts) > MAX_SMEM) --stages;
+  while (Sm::total(stages, nparts) > MAX_SMEM) --stages;
   p.stages = stages;
-  launch_pdl(gemm_tcgen05_kernel<BN>, dim3(grid), dim3(TC_THREADS), TcSmem<BN>::total(stages, nparts), stream, p);
+  launch_pdl(gemm_tcgen05_kernel<BN, BK>, dim3(grid), dim3(TC_THREADS), Sm::total(stages, nparts), stream, p);
   count_launch();
   return finish_launch("gemm_tcgen05");
 }
@@ -439,9 +584,10 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.op_dtype = op_dtype; p.act = act; p.res_masked = res_masked;
   p.nseg = (op_dtype == UNAV_BF16X2) ? 3 : 1;
-  // tile width: prefer more CTAs when the problem cannot fill the 148 SMs
-  const long long tiles128 = static_cast<long long>((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128) * ngroups;
-  const int bn = (N <= 64 || tiles128 < 240) ? 64 : 128;   // 2 CTAs/SM x 148 SMs = 296 slots
+  p.phase = g_phase_buf; p.phase_cap = g_phase_cap;
+  const TcChoice ch = choose_tile(M, N, K, ngroups, p.nseg);
+  const int bn = ch.bn, bk = ch.sched == 2 ? 32 : 64;
+  p.once = ch.sched ? 1 : 0;
   for (int i = 0; i < ngroups; ++i) {
     const UnavGemmGroup& g = groups[i];
     UNAV_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.W) & 15) == 0,
@@ -451,20 +597,27 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
       UNAV_REQUIRE(g.lda % 16 == 0 && g.ldw % 16 == 0 && g.lda / 2 >= K && g.ldw / 2 >= K,
                    "gemm_tcgen05: split operands need ld %% 16 == 0 and ld/2 >= K");
     int rc;
-    if ((rc = encode_map(&p.g[i].tmA[0], g.A, M, K, g.lda, TC_BM))) return rc;
-    if ((rc = encode_map(&p.g[i].tmW[0], g.W, N, K, g.ldw, bn))) return rc;
+    if ((rc = encode_map(&p.g[i].tmA[0], g.A, M, K, g.lda, TC_BM, bk))) return rc;
+    if ((rc = encode_map(&p.g[i].tmW[0], g.W, N, K, g.ldw, bn, bk))) return rc;
     if (op_dtype == UNAV_BF16X2) {
       const __nv_bfloat16* alo = reinterpret_cast<const __nv_bfloat16*>(g.A) + g.lda / 2;
       const __nv_bfloat16* wlo = reinterpret_cast<const __nv_bfloat16*>(g.W) + g.ldw / 2;
-      if ((rc = encode_map(&p.g[i].tmA[1], alo, M, K, g.lda, TC_BM))) return rc;
-      if ((rc = encode_map(&p.g[i].tmW[1], wlo, N, K, g.ldw, bn))) return rc;
+      if ((rc = encode_map(&p.g[i].tmA[1], alo, M, K, g.lda, TC_BM, bk))) return rc;
+      if ((rc = encode_map(&p.g[i].tmW[1], wlo, N, K, g.ldw, bn, bk))) return rc;
     } else {
       p.g[i].tmA[1] = p.g[i].tmA[0];
       p.g[i].tmW[1] = p.g[i].tmW[0];
     }
     p.g[i].epi = make_epi(g);
   }
-  return bn == 64 ? launch_tc<64>(p, ngroups, stream) : launch_tc<128>(p, ngroups, stream);
+  if (bk == 32) return bn == 64 ? launch_tc<64, 32>(p, ngroups, stream) : launch_tc<128, 32>(p, ngroups, stream);
+  return bn == 64 ? launch_tc<64, 64>(p, ngroups, stream) : launch_tc<128, 64>(p, ngroups, stream);
 }
 
 }  // namespace unav
+
+extern "C" int unav_gemm_set_phase_trace(long long* device_buf, int capacity_ctas) {
+  unav::g_phase_buf = device_buf;
+  unav::g_phase_cap = device_buf ? capacity_ctas : 0;
+  return 0;
+}
