@@ -77,6 +77,12 @@ int unav_check_device(int dev);
 /* number of kernel launches issued by this library in the calling process so far */
 long long unav_launch_count(void);
 
+/* Diagnostics for the tcgen05 kernels (scripts/gemm_phases.py): while a buffer is set, every CTA with linear index
+ * below capacity_ctas writes 8 int64: GEMM {smid, clock64 at: start, setup done, first operands landed, last MMA
+ * issued, accumulator ready, first epilogue warp done, all warps done}; attention {smid, start, setup done (TMEM
+ * allocated), S ready, P written, O ready, epilogue done, all warps done}.  NULL switches it off (the default). */
+int unav_set_phase_trace(long long* device_buf, int capacity_ctas);
+
 /* ---- GEMM: C[M,N] = epilogue(A[M,K] . W[N,K]^T) ---------------------------------------- */
 /* Epilogue, per element (m, n), in this order:
  *   v = acc + bias[n]; v *= rowmask[m]; v *= rowscale[m]; v *= gate[m*gate_groups + n/gate_width];
@@ -107,10 +113,7 @@ typedef struct UnavGemmGroup {
  * lda, ldw multiples of 8 elements. */
 int unav_gemm(const UnavGemmGroup* groups, int ngroups, int M, int N, int K,
               int op_dtype, int act, int res_masked, int backend, void* stream);
-/* Diagnostics for the tcgen05 GEMM (scripts/gemm_phases.py): while a buffer is set, every CTA with linear index below
- * capacity_ctas writes 8 int64 {smid, clock64 at: start, setup done, first operands landed, last MMA issued,
- * accumulator ready, first epilogue warp done, all warps done}.  NULL switches it off (the default). */
-int unav_gemm_set_phase_trace(long long* device_buf, int capacity_ctas);
+
 
 /* ---- row LayerNorm (+pre-add, +activation, +position table, +im2col scatter) ----------- */
 /* For output row r (0 <= r < M):

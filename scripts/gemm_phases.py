@@ -1,4 +1,4 @@
-"""Per-CTA phase timeline of the tcgen05 GEMM (unav_gemm_set_phase_trace): where a tile's life goes.
+"""Per-CTA phase timeline of the tcgen05 GEMM (unav_set_phase_trace): where a tile's life goes.
     python scripts/gemm_phases.py <G> <M> <N> <K> [act]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -21,13 +21,13 @@ torch.cuda.synchronize()
 cap = 4096
 buf = torch.zeros(cap, 8, dtype=torch.int64, device=dev)
 lib = _cabi.load()
-lib.unav_gemm_set_phase_trace(ctypes.c_void_p(buf.data_ptr()), cap)
+lib.unav_set_phase_trace(ctypes.c_void_p(buf.data_ptr()), cap)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 K.gemm(groups, M, N, Kd, op, act, False, K.GEMM_TCGEN05)
 b.record()
 torch.cuda.synchronize()
-lib.unav_gemm_set_phase_trace(None, 0)
+lib.unav_set_phase_trace(None, 0)
 t = buf.cpu()
 t = t[t[:, 1] != 0]
 n = t.shape[0]

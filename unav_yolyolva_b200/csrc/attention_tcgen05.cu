@@ -82,6 +82,23 @@ __device__ __forceinline__ void ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
 __device__ __forceinline__ void st8(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -117,10 +134,36 @@ struct AttnTcParams {
   AttnTcGroup g[4];
   int nb, Tq, Tk, Tkp, nh, hs, op_dtype, nseg, ncols;
   int q_bytes, kv_bytes;      // smem region sizes
+  long long* phase; int phase_cap;   // diagnostics (unav_set_phase_trace)
   float scale;
 };
 
-__global__ void __launch_bounds__(192, 1)
+constexpr int ATC_THREADS = 320;     // TMA warp, MMA warp, 8 softmax / epilogue warps (two per TMEM lane quarter)
+
+// p = exp(s*scale - max) for N (16 | 32) consecutive keys held in r[], packed to BF16 hi (+ lo) words; returns their sum
+template <int N>
+__device__ __forceinline__ float softmax_chunk(const uint32_t* r, uint32_t m, float sc, float mx, bool split, uint32_t* hi,
+                                               uint32_t* lo) {
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    const float p0 = ((m >> j) & 1u) ? __expf(__uint_as_float(r[j]) * sc - mx) : 0.f;
+    const float p1 = ((m >> (j + 1)) & 1u) ? __expf(__uint_as_float(r[j + 1]) * sc - mx) : 0.f;
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+    const float2 hf = __bfloat1622float2(h2);
+    if (split) {
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(p0 - hf.x, p1 - hf.y);
+      lo[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+      l += p0 + p1;                                         // hi + lo carries (almost) the full FP32 value
+    } else {
+      l += hf.x + hf.y;                                     // normalise by what the MMA will actually sum
+    }
+    hi[j / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+  }
+  return l;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
   using namespace atc;
   extern __shared__ uint8_t smem_raw[];
@@ -133,15 +176,24 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
   const uint32_t bar_base = kv_smem + p.kv_bytes;
   const uint32_t bar_qk = bar_base, bar_s = bar_base + 8, bar_v = bar_base + 16, bar_p = bar_base + 24, bar_o = bar_base + 32;
   const uint32_t tmem_slot = bar_base + 40;
-  uint8_t* mask_s = smem_raw + (bar_base - smem_u32(smem_raw)) + 64;     // [Tkp] key validity bytes
+  uint32_t* maskw = reinterpret_cast<uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 64);   // key validity bits, 9 words
+  float* xch = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 128);         // [2 max | 2 sum][128 rows]
   const int hs = p.hs, Tkp = p.Tkp;
   const int nparts = p.nseg > 1 ? 2 : 1;
   const int kq = hs / 64;                       // 64-column boxes along the head dim
   const int nkv = (Tkp + 63) / 64;              // 64-key boxes of V^T
   const int q_box = 128 * 128, k_box = Tkp * 128, v_box = hs * 128;
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  long long* ph_out = (p.phase && cta_lin < p.phase_cap) ? p.phase + 8ll * cta_lin : nullptr;
+  if (ph_out && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    ph_out[0] = smid;
+    ph_out[1] = clock_stamp();
+  }
 
   if (warp == 0 && lane == 0) {
-    mbar_init(bar_qk, 1); mbar_init(bar_s, 1); mbar_init(bar_v, 1); mbar_init(bar_p, 4); mbar_init(bar_o, 1);
+    mbar_init(bar_qk, 1); mbar_init(bar_s, 1); mbar_init(bar_v, 1); mbar_init(bar_p, 8); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -150,14 +202,19 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
   }
   pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
   pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
-  for (int j = threadIdx.x; j < Tkp; j += blockDim.x)
-    mask_s[j] = (j < p.Tk && (!g.kmask || g.kmask[static_cast<long long>(b) * p.Tk + j])) ? 1 : 0;
+  if (warp < 9) {      // key validity as 8 x 32 bits (+ a zero word for the funnel shift of the last chunk)
+    const int j = warp * 32 + lane;
+    const bool valid = j < p.Tk && (!g.kmask || g.kmask[static_cast<long long>(b) * p.Tk + j]);
+    const uint32_t w = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) maskw[warp] = w;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
   const uint32_t tm_s = tmem_base, tm_p = tmem_base + p.ncols / 2, tm_o = tmem_base;
+  if (ph_out && threadIdx.x == 0) ph_out[2] = clock_stamp();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -212,13 +269,17 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
     }
     __syncwarp();
   } else {
-    // ===== softmax / epilogue warps: one query row per thread =====
-    const int qd = warp & 3;
+    // ===== softmax / epilogue warps: two threads per query row (warps w and w+4 share a TMEM lane quarter and split the
+    // key columns; row max and row sum are combined through shared memory under a 64-thread named barrier) =====
+    const int qd = warp & 3, half = (warp - 2) >> 2;
     const int row = qd * 32 + lane;
     const int qi = q0 + row;
     const bool row_ok = qi < p.Tq;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const float sc = p.scale;
+    const bool split = p.nseg > 1;
+    const int csplit = ((Tkp / 16 + 1) / 2) * 16;
+    const int c_lo = half ? csplit : 0, c_hi = half ? Tkp : csplit;
     // optional extra key: s_x = scale * <q_i, xk_i>
     const bool has_x = g.xk != nullptr && row_ok && qi >= g.x_first;
     float s_x = -CUDART_INF_F;
@@ -235,59 +296,71 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
     }
     mbar_wait(bar_s, 0);
     tc_fence_after();
-    // ---- pass 1: row max over valid keys
-    float mx = s_x;
+    if (ph_out && threadIdx.x == 64) ph_out[3] = clock_stamp();
+    // ---- pass 1: raw row max over this thread's valid keys (scale > 0, so max(s*scale) = max(s)*scale exactly)
+    float mraw = -CUDART_INF_F;
 #pragma unroll 1
-    for (int c = 0; c < Tkp; c += 16) {
-      uint32_t r[16];
-      ld16(tm_s + lane_addr + c, r);
-      wait_ld();
+    for (int c = c_lo; c < c_hi; c += 32) {
+      const uint32_t m = __funnelshift_r(maskw[c >> 5], maskw[(c >> 5) + 1], c & 31);
+      uint32_t r[32];
+      if (c + 32 <= c_hi) {
+        ld32(tm_s + lane_addr + c, r);
+        wait_ld();
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (mask_s[c + j]) mx = fmaxf(mx, __uint_as_float(r[j]) * sc);
+        for (int j = 0; j < 32; ++j)
+          if ((m >> j) & 1u) mraw = fmaxf(mraw, __uint_as_float(r[j]));
+      } else {
+        ld16(tm_s + lane_addr + c, r);
+        wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if ((m >> j) & 1u) mraw = fmaxf(mraw, __uint_as_float(r[j]));
+      }
     }
+    xch[half * 128 + row] = mraw;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+    float mx = fmaxf(s_x, fmaxf(xch[row], xch[128 + row]) * sc);
     if (mx == -CUDART_INF_F) mx = 0.f;         // fully masked row: all probabilities are 0 (0/0 = NaN as in the reference)
     // ---- pass 2: p = exp(s*scale - max), row sum, P -> TMEM as packed BF16 (hi, lo)
     float l = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < Tkp; c += 16) {
-      uint32_t r[16];
-      ld16(tm_s + lane_addr + c, r);
-      wait_ld();
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        float p0 = mask_s[c + j] ? __expf(__uint_as_float(r[j]) * sc - mx) : 0.f;
-        float p1 = mask_s[c + j + 1] ? __expf(__uint_as_float(r[j + 1]) * sc - mx) : 0.f;
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-        const float2 hf = __bfloat1622float2(h2);
-        if (p.nseg > 1) {
-          const __nv_bfloat162 l2 = __floats2bfloat162_rn(p0 - hf.x, p1 - hf.y);
-          lo[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
-          l += p0 + p1;                                         // hi + lo carries (almost) the full FP32 value
-        } else {
-          l += hf.x + hf.y;                                     // normalise by what the MMA will actually sum
-        }
-        hi[j / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+    for (int c = c_lo; c < c_hi; c += 32) {
+      const uint32_t m = __funnelshift_r(maskw[c >> 5], maskw[(c >> 5) + 1], c & 31);
+      uint32_t r[32], hi[16], lo[16];
+      if (c + 32 <= c_hi) {
+        ld32(tm_s + lane_addr + c, r);
+        wait_ld();
+        l += softmax_chunk<32>(r, m, sc, mx, split, hi, lo);
+        st16(tm_p + lane_addr + c / 2, hi);
+        if (split) st16(tm_p + lane_addr + Tkp / 2 + c / 2, lo);
+      } else {
+        ld16(tm_s + lane_addr + c, r);
+        wait_ld();
+        l += softmax_chunk<16>(r, m, sc, mx, split, hi, lo);
+        st8(tm_p + lane_addr + c / 2, hi);
+        if (split) st8(tm_p + lane_addr + Tkp / 2 + c / 2, lo);
       }
-      st8(tm_p + lane_addr + c / 2, hi);
-      if (p.nseg > 1) st8(tm_p + lane_addr + Tkp / 2 + c / 2, lo);
     }
-    float p_x = 0.f;
-    if (has_x) { p_x = __expf(s_x - mx); l += p_x; }
     wait_st();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p);
-    // ---- epilogue: O / l (+ extra key's value), operand-dtype store
+    if (ph_out && threadIdx.x == 64) ph_out[4] = clock_stamp();
+    xch[256 + half * 128 + row] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+    l = xch[256 + row] + xch[384 + row];
+    float p_x = 0.f;
+    if (has_x) { p_x = __expf(s_x - mx); l += p_x; }
+    // ---- epilogue: O / l (+ extra key's value), operand-dtype store; the two threads of a row split the head columns
     mbar_wait(bar_o, 0);
     tc_fence_after();
+    if (ph_out && threadIdx.x == 64) ph_out[5] = clock_stamp();
     const float inv = 1.0f / l;
     const size_t es = op_elem_size(p.op_dtype);
     char* orow = reinterpret_cast<char*>(g.out) + (static_cast<size_t>(b) * p.Tq + (row_ok ? qi : 0)) * g.ldo * es;
     const float* xvr = has_x ? g.xv + (static_cast<long long>(b) * p.Tq + qi) * g.ldx + h * hs : nullptr;
 #pragma unroll 1
-    for (int c = 0; c < hs; c += 16) {
+    for (int c = half * (hs / 2); c < (half + 1) * (hs / 2); c += 16) {
       uint32_t r[16];
       ld16(tm_o + lane_addr + c, r);
       wait_ld();
@@ -303,9 +376,11 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
         store_op4(orow, p.op_dtype, h * hs + c + j, g.ldo / 2, o);
       }
     }
+    if (ph_out && threadIdx.x == 64) ph_out[6] = clock_stamp();
   }
   tc_fence_before();
   __syncthreads();
+  if (ph_out && threadIdx.x == 0) ph_out[7] = clock_stamp();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.ncols) : "memory");
@@ -459,6 +534,7 @@ extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int
   if (p.Tkp < 64) p.Tkp = 64;          // keys beyond Tk are masked; keeps every MMA / TMA box at least 64 wide
   p.nseg = op_dtype == UNAV_BF16X2 ? 3 : 1;
   p.ncols = p.Tkp > 128 ? 512 : 256;
+  p.phase = g_phase_buf; p.phase_cap = g_phase_cap;
   const int nparts = p.nseg > 1 ? 2 : 1;
   const int kq = hs / 64, nkv = (p.Tkp + 63) / 64;
   p.q_bytes = nparts * kq * 128 * 128;
@@ -485,7 +561,7 @@ extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int
     d.kmask = s.kmask; d.q32 = s.q32; d.xk = s.xk; d.xv = s.xv; d.ldq32 = s.ldq32; d.ldx = s.ldx;
     d.out = s.out; d.ldo = s.ldo; d.x_first = s.x_first;
   }
-  const int smem = p.q_bytes + p.kv_bytes + 64 + ((p.Tkp + 63) / 64 * 64) + 1024;
+  const int smem = p.q_bytes + p.kv_bytes + 128 + 4 * 128 * 4 + 1024;     // + barriers, mask words, max/sum exchange, slack
   static int smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -493,7 +569,7 @@ extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int
     smem_set = smem;
   }
   dim3 grid((Tq + 127) / 128, nh, nb * ngroups);
-  launch_pdl(attention_tcgen05_kernel, dim3(grid), dim3(192), smem, reinterpret_cast<cudaStream_t>(stream), p);
+  launch_pdl(attention_tcgen05_kernel, dim3(grid), dim3(ATC_THREADS), smem, reinterpret_cast<cudaStream_t>(stream), p);
   count_launch();
   return finish_launch("attention_tc");
 }

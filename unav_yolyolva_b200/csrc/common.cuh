@@ -36,6 +36,8 @@ int finish_launch(const char* what);  // cudaGetLastError -> code, records messa
 // prologue.  Opt-in with UNAV_PDL=1 (without the launch attribute the device-side calls are no-ops).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+extern long long* g_phase_buf;
+extern int g_phase_cap;
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>
@@ -48,6 +50,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+__device__ __forceinline__ long long clock_stamp() {   // "memory": keep the read where it is written
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory");
+  return t;
 }
 
 // ---- small device helpers ---------------------------------------------------------------

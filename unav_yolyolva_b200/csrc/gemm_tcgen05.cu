@@ -45,8 +45,7 @@ struct TcParams {
   int phase_cap;
 };
 
-static long long* g_phase_buf = nullptr;
-static int g_phase_cap = 0;
+
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -213,7 +212,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     ph_out[0] = smid;
-    ph_out[1] = clock64();
+    ph_out[1] = clock_stamp();
   }
 
   if (warp == 0 && lane == 0) {
@@ -236,7 +235,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail
   pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
   pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
-  if (ph_out && threadIdx.x == 0) ph_out[2] = clock64();          // setup done
+  if (ph_out && threadIdx.x == 0) ph_out[2] = clock_stamp();     // setup done
 
   // Stage layout: plain BF16 operands [A | W]; split operands [A_hi | A_lo | W_hi | W_lo] — every operand part is loaded
   // ONCE per k-block and consumed by the three MMA groups (Ahi.Whi, Alo.Whi, Ahi.Wlo).  (An earlier schedule streamed
@@ -277,7 +276,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
         const uint32_t ph = (it / NS) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        if (ph_out && it == 0) ph_out[3] = clock64();             // first operands landed
+        if (ph_out && it == 0) ph_out[3] = clock_stamp();             // first operands landed
         const uint32_t sa = base + s * stage_bytes;
         // Canonical accumulation order of the split mode, the same for every tile shape / schedule so that results
         // do not depend on the grid (batch-size independent outputs): K in steps of 32 columns; inside a step
@@ -307,7 +306,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
         tc_commit(empty_bar(s));        // frees the ring slot once these MMAs have read it
       }
       tc_commit(accum_bar);             // accumulator complete
-      if (ph_out) ph_out[4] = clock64();                          // last MMA issued
+      if (ph_out) ph_out[4] = clock_stamp();                          // last MMA issued
     }
     __syncwarp();     // same for the MMA issuer's warp
   } else {
@@ -323,7 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
     const int q = warp & 3, half = (warp - 2) >> 2;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    if (ph_out && threadIdx.x == 64) ph_out[5] = clock64();       // accumulator ready
+    if (ph_out && threadIdx.x == 64) ph_out[5] = clock_stamp();       // accumulator ready
     float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * 32 * PITCH + half * HALF;
 #pragma unroll 1
     for (int c = 0; c < HALF / 32; ++c) {
@@ -455,10 +454,10 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       }
     }
   }
-  if (ph_out && threadIdx.x == 64) ph_out[6] = clock64();         // this warp's epilogue done
+  if (ph_out && threadIdx.x == 64) ph_out[6] = clock_stamp();         // this warp's epilogue done
   tc_fence_before();
   __syncthreads();
-  if (ph_out && threadIdx.x == 0) ph_out[7] = clock64();          // all warps done
+  if (ph_out && threadIdx.x == 0) ph_out[7] = clock_stamp();          // all warps done
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
@@ -616,8 +615,3 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
 
 }  // namespace unav
 
-extern "C" int unav_gemm_set_phase_trace(long long* device_buf, int capacity_ctas) {
-  unav::g_phase_buf = device_buf;
-  unav::g_phase_cap = device_buf ? capacity_ctas : 0;
-  return 0;
-}

@@ -29,6 +29,9 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+long long* g_phase_buf = nullptr;    // unav_set_phase_trace: per-CTA clock stamps of the tcgen05 kernels (diagnostics)
+int g_phase_cap = 0;
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int finish_launch(const char* what) {
@@ -45,6 +48,11 @@ int finish_launch(const char* what) {
 extern "C" const char* unav_version(void) { return "unav_b200 0.1 (sm_100a)"; }
 extern "C" const char* unav_last_error(void) { return unav::g_err; }
 extern "C" long long unav_launch_count(void) { return unav::g_launches.load(); }
+extern "C" int unav_set_phase_trace(long long* device_buf, int capacity_ctas) {
+  unav::g_phase_buf = device_buf;
+  unav::g_phase_cap = device_buf ? capacity_ctas : 0;
+  return 0;
+}
 
 extern "C" int unav_check_device(int dev) {
   int n = 0;

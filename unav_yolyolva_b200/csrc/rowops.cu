@@ -103,40 +103,79 @@ struct DwLnParams {
 };
 
 constexpr int DWV = 4;        // float4 chunks per lane: C <= 512
-constexpr int DW_ROWS = 16;   // output rows per block (one tile never crosses a segment)
 
-// One block = DW_ROWS consecutive output rows of one segment.  Phase 1 stages the DW_ROWS*stride + 2 input rows
-// in shared memory once (the one-warp-per-row version re-read every input row from three warps and recomputed its
-// pre-LayerNorm statistics three times; ncu: 154 registers, 19 % occupancy, 31 % issue-active); phase 2 gives each
-// warp two output rows: per output, depthwise taps over the staged rows (pre-LN affine applied on the fly), mask,
-// LayerNorm with warp-shuffle reductions, vectorised FP32 / operand stores.
-__global__ void __launch_bounds__(256)
+// One block = R consecutive output rows of one segment (R = 8 for C <= 256, 4 for C <= 512), one WARP per unit of
+// work so that no warp runs a second dependent pass: warp w stages input row w (phase 1: global load, pre-LayerNorm
+// statistics, row -> smem) and then produces ONE (output row, output) pair (phase 2: depthwise taps over the staged
+// rows with the pre-LN affine applied on the fly, mask, LayerNorm, vectorised FP32 / operand stores).  The weights of
+// phase 2 (taps, pre-LN and LN affine) are requested before phase 1's reductions, so their L2 latency overlaps it.
+// History: the 16-row / 8-warp version gave every warp ~3 rows of phase 1 and 6 pairs of phase 2 back to back; every
+// launch took ~17 us whatever its grid size (profiles/r01b_launch_summary.md) — a latency chain, not bandwidth.
+template <int NV>
+__global__ void __launch_bounds__(NV == 2 ? 768 : 384)
 dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
   pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
   pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   extern __shared__ __align__(16) float dw_smem[];
+  constexpr int R = NV == 2 ? 8 : 4;
   const UnavDwLnGroup& g = p.g[blockIdx.y];
   const int C = p.C;
-  const int tiles_per_seg = (p.seg_len_out + DW_ROWS - 1) / DW_ROWS;
-  const int seg = blockIdx.x / tiles_per_seg, t0 = (blockIdx.x % tiles_per_seg) * DW_ROWS;
-  const int n_in = DW_ROWS * p.stride + 2;                 // staged input rows: stride*t0 - 1 ...
+  const int tiles_per_seg = (p.seg_len_out + R - 1) / R;
+  const int seg = blockIdx.x / tiles_per_seg, t0 = (blockIdx.x % tiles_per_seg) * R;
+  const int n_in = R * p.stride + 2;                       // staged input rows: stride*t0 - 1 ...
   float* xs = dw_smem;                                     // [n_in][C]
   float* st_mean = dw_smem + n_in * C;                     // [n_in]
   float* st_rstd = st_mean + n_in;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = warp; i < n_in; i += nwarps) {
-    const int ti = p.stride * t0 - 1 + i;
-    const bool ok = ti >= 0 && ti < p.seg_len_in;
+  // ---- phase 1 loads (input row `warp`)
+  float4 v[NV];
+  bool ok = false;
+  if (warp < n_in) {
+    const int ti = p.stride * t0 - 1 + warp;
+    ok = ti >= 0 && ti < p.seg_len_in;
     const float* xr = g.x + (static_cast<long long>(seg) * p.seg_len_in + (ok ? ti : 0)) * g.ldx;
-    float4 v[DWV];
-    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < DWV; ++j) {
+    for (int j = 0; j < NV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      v[j] = (ok && c < C) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  // ---- phase 2 weights (pair `warp` = (row ro, output o)), requested now, consumed after the barrier
+  const int ro = warp / p.n_out, o = warp - ro * p.n_out;
+  const int t = t0 + ro;
+  const bool task = ro < R && t < p.seg_len_out;
+  const UnavDwLnOut& od = g.out[task ? o : 0];
+  const bool has_pre = task && od.src >= 0;
+  const bool has_ln = od.ln_w != nullptr;   // NULL: plain masked depthwise conv (MaskedConv1D with groups = C)
+  float4 d0[NV], d1[NV], d2[NV], lw[NV], lb[NV], nw[NV], nb[NV];
+  float mk = 1.f;
+  long long r = 0;
+  if (task) {
+    r = static_cast<long long>(seg) * p.seg_len_out + t;
+    mk = g.mask_out ? (g.mask_out[r] ? 1.f : 0.f) : 1.f;
+    const float* pw = has_pre ? g.pre_w[od.src] : nullptr;
+    const float* pb = has_pre ? g.pre_b[od.src] : nullptr;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
       const int c = (j * 32 + lane) * 4;
       if (c < C) {
-        v[j] = ok ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(xs + i * C + c) = v[j];
+        d0[j] = *reinterpret_cast<const float4*>(od.dw + c * 3);       // taps of 4 channels: 12 floats
+        d1[j] = *reinterpret_cast<const float4*>(od.dw + c * 3 + 4);
+        d2[j] = *reinterpret_cast<const float4*>(od.dw + c * 3 + 8);
+        if (has_pre) { lw[j] = *reinterpret_cast<const float4*>(pw + c); lb[j] = *reinterpret_cast<const float4*>(pb + c); }
+        if (has_ln) { nw[j] = *reinterpret_cast<const float4*>(od.ln_w + c); nb[j] = *reinterpret_cast<const float4*>(od.ln_b + c); }
+      }
+    }
+  }
+  // ---- phase 1 finish: row -> smem, statistics
+  if (warp < n_in) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      if (c < C) {
+        *reinterpret_cast<float4*>(xs + warp * C + c) = v[j];
         s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
       }
     }
@@ -144,7 +183,7 @@ dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
       const float mean = warp_sum(s) / C;
       float q = 0.f;
 #pragma unroll
-      for (int j = 0; j < DWV; ++j) {
+      for (int j = 0; j < NV; ++j) {
         const int c = (j * 32 + lane) * 4;
         if (c < C) {
           const float a = v[j].x - mean, b = v[j].y - mean, cc = v[j].z - mean, d = v[j].w - mean;
@@ -152,87 +191,74 @@ dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
         }
       }
       const float rstd = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
-      if (lane == 0) { st_mean[i] = mean; st_rstd[i] = ok ? rstd : 0.f; }   // rstd 0 + skipped affine = zero padding
+      if (lane == 0) { st_mean[warp] = mean; st_rstd[warp] = ok ? rstd : 0.f; }   // rstd 0 + skipped affine = zero padding
     }
   }
   __syncthreads();
+  if (!task) return;
 
+  // ---- phase 2
   const size_t es = op_elem_size(p.op_dtype);
-  for (int ro = warp; ro < DW_ROWS; ro += nwarps) {
-    const int t = t0 + ro;
-    if (t >= p.seg_len_out) break;
-    const long long r = static_cast<long long>(seg) * p.seg_len_out + t;
-    const float mk = g.mask_out ? (g.mask_out[r] ? 1.f : 0.f) : 1.f;
-    const int i0 = ro * p.stride;                          // staged row of tap 0
-    bool okt[3];
+  const int i0 = ro * p.stride;                          // staged row of tap 0
+  bool okt[3];
+  float tm[3], tr[3];
 #pragma unroll
-    for (int tap = 0; tap < 3; ++tap) {
-      const int ti = p.stride * t + tap - 1;
-      okt[tap] = ti >= 0 && ti < p.seg_len_in;
+  for (int tap = 0; tap < 3; ++tap) {
+    const int ti = p.stride * t + tap - 1;
+    okt[tap] = ti >= 0 && ti < p.seg_len_in;
+    tm[tap] = has_pre ? st_mean[i0 + tap] : 0.f;
+    tr[tap] = has_pre ? st_rstd[i0 + tap] : 1.f;
+  }
+  float4 z[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+      const float wt[4][3] = {{d0[j].x, d0[j].y, d0[j].z}, {d0[j].w, d1[j].x, d1[j].y}, {d1[j].z, d1[j].w, d2[j].x},
+                              {d2[j].y, d2[j].z, d2[j].w}};
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int tap = 0; tap < 3; ++tap) {
+        if (!okt[tap]) continue;
+        float4 u = *reinterpret_cast<const float4*>(xs + (i0 + tap) * C + c);
+        if (has_pre) {
+          u.x = (u.x - tm[tap]) * tr[tap] * lw[j].x + lb[j].x; u.y = (u.y - tm[tap]) * tr[tap] * lw[j].y + lb[j].y;
+          u.z = (u.z - tm[tap]) * tr[tap] * lw[j].z + lb[j].z; u.w = (u.w - tm[tap]) * tr[tap] * lw[j].w + lb[j].w;
+        }
+        acc[0] = fmaf(wt[0][tap], u.x, acc[0]); acc[1] = fmaf(wt[1][tap], u.y, acc[1]);
+        acc[2] = fmaf(wt[2][tap], u.z, acc[2]); acc[3] = fmaf(wt[3][tap], u.w, acc[3]);
+      }
+      z[j] = make_float4(acc[0] * mk, acc[1] * mk, acc[2] * mk, acc[3] * mk);
+      s += (z[j].x + z[j].y) + (z[j].z + z[j].w);
     }
-    for (int o = 0; o < p.n_out; ++o) {
-      const UnavDwLnOut& od = g.out[o];
-      const float* pw = (od.src >= 0) ? g.pre_w[od.src] : nullptr;
-      const float* pb = (od.src >= 0) ? g.pre_b[od.src] : nullptr;
-      float4 z[DWV];
-      float s = 0.f;
+  }
+  const float mu = warp_sum(s) / C;
+  float q = 0.f;
 #pragma unroll
-      for (int j = 0; j < DWV; ++j) {
-        const int c = (j * 32 + lane) * 4;
-        if (c < C) {
-          const float4 d0 = *reinterpret_cast<const float4*>(od.dw + c * 3);       // taps of 4 channels: 12 floats
-          const float4 d1 = *reinterpret_cast<const float4*>(od.dw + c * 3 + 4);
-          const float4 d2 = *reinterpret_cast<const float4*>(od.dw + c * 3 + 8);
-          const float wt[4][3] = {{d0.x, d0.y, d0.z}, {d0.w, d1.x, d1.y}, {d1.z, d1.w, d2.x}, {d2.y, d2.z, d2.w}};
-          float4 lw = make_float4(1.f, 1.f, 1.f, 1.f), lb = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (pw) { lw = *reinterpret_cast<const float4*>(pw + c); lb = *reinterpret_cast<const float4*>(pb + c); }
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < NV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    if (c < C) {
+      z[j].x -= mu; z[j].y -= mu; z[j].z -= mu; z[j].w -= mu;
+      q += (z[j].x * z[j].x + z[j].y * z[j].y) + (z[j].z * z[j].z + z[j].w * z[j].w);
+    }
+  }
+  const float rs = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
+  char* op_row = od.out_op ? reinterpret_cast<char*>(od.out_op) + static_cast<size_t>(r) * od.ld_op * es : nullptr;
 #pragma unroll
-          for (int tap = 0; tap < 3; ++tap) {
-            if (!okt[tap]) continue;
-            float4 u = *reinterpret_cast<const float4*>(xs + (i0 + tap) * C + c);
-            if (pw) {
-              const float mean = st_mean[i0 + tap], rstd = st_rstd[i0 + tap];
-              u.x = (u.x - mean) * rstd * lw.x + lb.x; u.y = (u.y - mean) * rstd * lw.y + lb.y;
-              u.z = (u.z - mean) * rstd * lw.z + lb.z; u.w = (u.w - mean) * rstd * lw.w + lb.w;
-            }
-            acc[0] = fmaf(wt[0][tap], u.x, acc[0]); acc[1] = fmaf(wt[1][tap], u.y, acc[1]);
-            acc[2] = fmaf(wt[2][tap], u.z, acc[2]); acc[3] = fmaf(wt[3][tap], u.w, acc[3]);
-          }
-          z[j] = make_float4(acc[0] * mk, acc[1] * mk, acc[2] * mk, acc[3] * mk);
-          s += (z[j].x + z[j].y) + (z[j].z + z[j].w);
-        }
+  for (int j = 0; j < NV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    if (c < C) {
+      float4 y;
+      if (has_ln) {
+        y.x = z[j].x * rs * nw[j].x + nb[j].x; y.y = z[j].y * rs * nw[j].y + nb[j].y;
+        y.z = z[j].z * rs * nw[j].z + nb[j].z; y.w = z[j].w * rs * nw[j].w + nb[j].w;
+      } else {
+        y = make_float4(z[j].x + mu, z[j].y + mu, z[j].z + mu, z[j].w + mu);
       }
-      const float mu = warp_sum(s) / C;
-      float q = 0.f;
-#pragma unroll
-      for (int j = 0; j < DWV; ++j) {
-        const int c = (j * 32 + lane) * 4;
-        if (c < C) {
-          z[j].x -= mu; z[j].y -= mu; z[j].z -= mu; z[j].w -= mu;
-          q += (z[j].x * z[j].x + z[j].y * z[j].y) + (z[j].z * z[j].z + z[j].w * z[j].w);
-        }
-      }
-      const float rs = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
-      const bool has_ln = od.ln_w != nullptr;   // NULL: plain masked depthwise conv (MaskedConv1D with groups = C)
-      char* op_row = od.out_op ? reinterpret_cast<char*>(od.out_op) + static_cast<size_t>(r) * od.ld_op * es : nullptr;
-#pragma unroll
-      for (int j = 0; j < DWV; ++j) {
-        const int c = (j * 32 + lane) * 4;
-        if (c < C) {
-          float4 y;
-          if (has_ln) {
-            const float4 w = *reinterpret_cast<const float4*>(od.ln_w + c);
-            const float4 b = *reinterpret_cast<const float4*>(od.ln_b + c);
-            y.x = z[j].x * rs * w.x + b.x; y.y = z[j].y * rs * w.y + b.y;
-            y.z = z[j].z * rs * w.z + b.z; y.w = z[j].w * rs * w.w + b.w;
-          } else {
-            y = make_float4(z[j].x + mu, z[j].y + mu, z[j].z + mu, z[j].w + mu);
-          }
-          if (od.out_f32) *reinterpret_cast<float4*>(od.out_f32 + r * od.ld_f32 + c) = y;
-          if (op_row) store_op4(op_row, p.op_dtype, c, od.ld_op / 2, y);
-        }
-      }
+      if (od.out_f32) *reinterpret_cast<float4*>(od.out_f32 + r * od.ld_f32 + c) = y;
+      if (op_row) store_op4(op_row, p.op_dtype, c, od.ld_op / 2, y);
     }
   }
 }
@@ -504,17 +530,17 @@ extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg
   for (int i = 0; i < ngroups; ++i) p.g[i] = groups[i];
   p.nseg = nseg; p.seg_len_in = seg_len_in; p.seg_len_out = seg_len_in / stride; p.stride = stride; p.C = C;
   p.n_pre = n_pre; p.n_out = n_out; p.op_dtype = op_dtype; p.eps = eps;
-  const int tiles_per_seg = (p.seg_len_out + DW_ROWS - 1) / DW_ROWS;
-  const int n_in = DW_ROWS * stride + 2;
+  const bool narrow = C <= 256;
+  const int R = narrow ? 8 : 4;
+  const int tiles_per_seg = (p.seg_len_out + R - 1) / R;
+  const int n_in = R * stride + 2;
   const size_t smem = (static_cast<size_t>(n_in) * C + 2 * n_in) * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("dwconv_ln: smem %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    smem_set = smem;
-  }
+  const int nwarps = n_in > R * n_out ? n_in : R * n_out;     // one warp per staged row and per (row, output) pair
   dim3 grid(static_cast<unsigned>(nseg * tiles_per_seg), ngroups);
-  launch_pdl(dwconv_ln_kernel, dim3(grid), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), p);
+  if (narrow)
+    launch_pdl(dwconv_ln_kernel<2>, dim3(grid), dim3(32 * nwarps), smem, reinterpret_cast<cudaStream_t>(stream), p);
+  else
+    launch_pdl(dwconv_ln_kernel<4>, dim3(grid), dim3(32 * nwarps), smem, reinterpret_cast<cudaStream_t>(stream), p);
   count_launch();
   return finish_launch("dwconv_ln");
 }
