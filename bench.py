@@ -20,6 +20,7 @@ collective is one all-gather of the detections at the end of the timed region.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -63,9 +64,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_from=0.0):
+        """Summary of the samples taken at or after perf_counter() time t_from."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -73,10 +75,11 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = [r for t, r in self.rows if t >= t_from]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -216,28 +219,39 @@ def main():
     launches_per_step = plan.get("launches_per_step", 0)
 
     def device_step(j):
-        eng.run(*dev_inputs[j % n_rot], meta[j % n_rot])
+        # streaming mode: forward + decode on the current stream, this batch's soft-NMS on the engine's side stream,
+        # where it overlaps the next batch's forward (engine.run docstring)
+        return eng.run(*dev_inputs[j % n_rot], meta[j % n_rot], overlap_nms=True)
 
     # ---------------- value: device-resident inputs
     for j in range(W):
         device_step(j)
     # warm the (torch) packing / gather plumbing once so its first-use module loads are not in the timed region
-    _w = runner.pack_detections(plan["out_segs"], plan["out_scores"], plan["out_labels"])
+    with torch.cuda.stream(eng.nms_stream):
+        _w = runner.pack_detections(plan["out_segs"], plan["out_scores"], plan["out_labels"]).clone()
+    barrier()
     runner.gather_detections(_w, torch.arange(B, device=dev) + rank * B, world * B)
+    launches_per_step = plan.get("launches_per_step", launches_per_step)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kst)]
+        time.sleep(0.35)                                # let nvidia-smi start sampling before the timed region
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     all_dets = []
     barrier()
-    t_wall0 = time.perf_counter()
+    cur = torch.cuda.current_stream()
+    # ONE timed region over the K steps (the steps overlap, so per-step events would not mean anything): every step's
+    # forward, decode, NMS, the copy of its detections out of the plan, and the L2-flushing memset between steps.
+    t_timed = time.perf_counter()
+    t0e.record()
     for j in range(Kst):
-        flush.zero_()                                   # L2 flush, outside the timed events
-        ev[j][0].record()
+        flush.zero_()                                   # L2 flush between steps (inside the timed region)
         device_step(j)
-        ev[j][1].record()
-        all_dets.append(runner.pack_detections(plan["out_segs"], plan["out_scores"], plan["out_labels"]).clone())
+        with torch.cuda.stream(eng.nms_stream):         # ordered after this step's NMS
+            all_dets.append(runner.pack_detections(plan["out_segs"], plan["out_scores"], plan["out_labels"]).clone())
+    cur.wait_event(plan["ev_nms"])
+    t1e.record()
     ga = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     ga[0].record()
     local = torch.cat(all_dets)
@@ -246,9 +260,20 @@ def main():
     gathered, valid = runner.gather_detections(local, vid_index, Kst * world * B)
     ga[1].record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    step_ms = sorted(a.elapsed_time(b) for a, b in ev)
-    dev_ms = sum(step_ms) + ga[0].elapsed_time(ga[1])
+    loop_ms = t0e.elapsed_time(t1e)
+    dev_ms = loop_ms + ga[0].elapsed_time(ga[1])
+    # keep the GPU busy with the same loop (untimed) until nvidia-smi has had time to sample clocks under load
+    if rank == 0:
+        t_end = time.perf_counter() + 0.7
+        j = 0
+        while time.perf_counter() < t_end:
+            device_step(j); j += 1
+            if j % 8 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+    clocks = sampler.stop(t_timed) if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "timed loop + the same loop continued (untimed) for 0.7 s"
     t = torch.tensor([dev_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -375,12 +400,12 @@ def main():
             "ms_per_step": dev_ms / Kst, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.mode != "fp32" else "f32", "data": "synthetic",
             "config": dict(config, parallelism=f"dp{world} (videos sharded by index, one all-gather of detections)",
-                           l2="256 MiB memset between steps (outside the timed events)",
+                           l2="256 MiB memset between steps (inside the timed region)",
+                           schedule="streaming: soft-NMS of batch j on a side stream overlaps the forward of batch j+1",
                            gathered_videos=int(valid.sum().item())),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * Kst, "launches_per_step": launches_per_step,
             "roofline": roof, "cpu_baseline": cpu,
-            "step_ms_min_med_max": [round(step_ms[0], 3), round(step_ms[len(step_ms) // 2], 3), round(step_ms[-1], 3)],
-            "gather_ms": round(ga[0].elapsed_time(ga[1]), 3)}
+            "loop_ms": round(loop_ms, 3), "gather_ms": round(ga[0].elapsed_time(ga[1]), 3)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -3,5 +3,5 @@ python bench.py --steps 30 --warmup 10 --no-cpu-baseline > gpurun_out/bench.json
 python - <<'PY'
 import json
 b=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
-print('value',round(b['value'],1),'ms/step',round(b['ms_per_step'],3),'e2e',round(b['e2e']['value'],1),round(b['e2e']['ms_per_step'],3),'launches',b['launches_per_step'], b['step_ms_min_med_max'], b['gather_ms'])
+print('value',round(b['value'],1),'ms/step',round(b['ms_per_step'],3),'e2e',round(b['e2e']['value'],1),round(b['e2e']['ms_per_step'],3),'launches',b['launches_per_step'], b.get('loop_ms'), b['gather_ms'], b['clocks'])
 PY

@@ -45,6 +45,7 @@ class HotPathEngine:
         self.mode = mode
         self.op, self.backend = MODES[mode]
         self.use_graph = use_graph
+        self.nms_stream = None          # side stream of the streaming mode (run(..., overlap_nms=True))
         self.model = model
         dev = next(model.parameters()).device
         if dev.type != "cuda":
@@ -325,6 +326,11 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------------------ forward
     def _launch_all(self, P):
+        self._launch_forward(P)
+        self._launch_decode(P)
+        self._launch_nms(P, P["vid_meta"])
+
+    def _launch_forward(self, P):
         w, op, B, T, C, L = self.w, self.op, P["B"], self.T, self.C, self.L
         NB, Tl, Ttot = 2 * B, self.Tl, self.Ttot
         N1 = T + 1
@@ -519,16 +525,23 @@ class HotPathEngine:
         self._gemm([{"A": P["HR2"], "W": w["hd.reg.out"], "bias": w["hd.reg.out.b"], "rowmask": mh, "rowscale": P["rowscale"],
                      "out_f32": P["offsets"]}], Mh, 2 * self.ncls, 3 * C, act=ACT_RELU)
 
-        # ================================================================== decode + soft-NMS (meta_archs.py:745-875)
+    def _launch_decode(self, P):
+        """Candidate decode (meta_archs.py:745-817) of the head outputs in P."""
         md = self.model
+        B, mh = P["B"], P["m_heads"]
         K.decode(P["logits"], P["offsets"], mh, P["points"], self.level_off, B, self.ncls, md.class_aware,
                  md.test_pre_nms_thresh, md.test_pre_nms_topk, md.test_duration_thresh, P["cand_segs"], P["cand_scores"],
                  P["cand_labels"], P["cap"])
+
+    def _launch_nms(self, P, vid_meta):
+        """Per-class soft-NMS + merge + seconds (meta_archs.py:819-875, libs/utils/nms.py:103-190) of P's candidates."""
+        md = self.model
+        B, Ttot = P["B"], self.Ttot
         if md.test_nms_method == "none":
             raise NotImplementedError("nms_method='none' is not on the hot path")
         method = 2 if md.test_nms_method == "soft" else 3
         K.softnms_batched(P["cand_segs"], P["cand_scores"], P["cand_labels"], B, P["cap"], self.ncls, md.test_iou_threshold,
-                          md.test_nms_sigma, md.test_min_score, method, md.test_max_seg_num, Ttot, P["vid_meta"],
+                          md.test_nms_sigma, md.test_min_score, method, md.test_max_seg_num, Ttot, vid_meta,
                           P["out_segs"], P["out_scores"], P["out_labels"], P["out_counts"], P["nms_ws"])
 
     def _csp(self, P, name, xin, G, g_off, heads, mask, l, out_f32, out_op):
@@ -581,31 +594,77 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------------------ public
     @torch.no_grad()
-    def run(self, visual: torch.Tensor, audio: torch.Tensor, mask: torch.Tensor, vid_meta: torch.Tensor):
+    def run(self, visual: torch.Tensor, audio: torch.Tensor, mask: torch.Tensor, vid_meta: torch.Tensor,
+            overlap_nms: bool = False):
         """visual [B,2048,T] f32, audio [B,128,T] f32, mask [B,1,T] bool, vid_meta [B,4] f32
         (feat_stride, feat_num_frames, fps, duration) — any device; copied into the plan's static inputs.
-        Returns the plan dict (device-resident outputs: out_segs/out_scores/out_labels/out_counts, logits, offsets)."""
+        Returns the plan dict (device-resident outputs: out_segs/out_scores/out_labels/out_counts, logits, offsets).
+
+        overlap_nms=False: everything is enqueued on the current stream (one CUDA graph).
+        overlap_nms=True : streaming mode for back-to-back batches.  The forward + decode run on the current stream, the
+        soft-NMS kernel (one CTA per video: 16 of 148 SMs, a <=100-round dependency chain) on ``self.nms_stream`` so it
+        overlaps the NEXT batch's forward; the next decode waits for it before overwriting the candidates.  Consumers
+        of out_* must order themselves after ``plan["ev_nms"]`` (or enqueue on ``self.nms_stream``)."""
         B = visual.shape[0]
         assert visual.shape[2] == self.T and audio.shape[2] == self.T, "sequence length must equal max_seq_len"
         P = self._plan(B)
         with torch.cuda.device(self.dev):
+            cur = torch.cuda.current_stream()
+            if P.get("ev_nms") is not None and not overlap_nms:
+                cur.wait_event(P["ev_nms"])                   # a streamed NMS of this plan may still be running
+                P["ev_nms"] = None
             P["visual"].copy_(visual, non_blocking=True)
             P["audio"].copy_(audio, non_blocking=True)
             P["mask_in"].copy_(mask.reshape(B, self.T), non_blocking=True)
-            P["vid_meta"].copy_(vid_meta, non_blocking=True)
+            if not overlap_nms:
+                P["vid_meta"].copy_(vid_meta, non_blocking=True)
+                if not self.use_graph:
+                    self._launch_all(P)
+                else:
+                    if P["graph"] is None:
+                        self._launch_all(P)                     # warm-up (sets function attributes, fills constants)
+                        cur.synchronize()
+                        n0 = K.launch_count()
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._launch_all(P)
+                        P["launches_per_step"] = K.launch_count() - n0
+                        P["graph"] = g
+                    P["graph"].replay()
+                return P
+            # ---- streaming mode
+            if "meta2" not in P:
+                P["meta2"] = torch.zeros(2, B, 4, dtype=torch.float32, device=self.dev)
+                P["ev_dec"] = torch.cuda.Event()
+                P["step"] = 0
+                if self.nms_stream is None:
+                    self.nms_stream = torch.cuda.Stream(self.dev)
+            meta = P["meta2"][P["step"] & 1]
+            P["step"] += 1
+            meta.copy_(vid_meta, non_blocking=True)
             if not self.use_graph:
-                self._launch_all(P)
+                self._launch_forward(P)
             else:
-                if P["graph"] is None:
-                    self._launch_all(P)                     # warm-up (sets function attributes, fills constants)
-                    torch.cuda.current_stream().synchronize()
+                if P.get("graph_fwd") is None:
+                    self._launch_all(P)
+                    torch.cuda.synchronize(self.dev)
                     n0 = K.launch_count()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        self._launch_all(P)
-                    P["launches_per_step"] = K.launch_count() - n0
-                    P["graph"] = g
-                P["graph"].replay()
+                        self._launch_forward(P)
+                    P["launches_per_step"] = K.launch_count() - n0 + 2
+                    P["graph_fwd"] = g
+                P["graph_fwd"].replay()
+            if P.get("ev_nms") is not None:
+                cur.wait_event(P["ev_nms"])                   # the previous batch's NMS has consumed the candidates
+            self._launch_decode(P)
+            P["ev_dec"].record(cur)
+            with torch.cuda.stream(self.nms_stream):
+                self.nms_stream.wait_event(P["ev_dec"])
+                self._launch_nms(P, meta)
+                ev = torch.cuda.Event()
+                ev.record(self.nms_stream)
+                P["ev_nms"] = ev
         return P
 
     def capture_traced(self, B: int):

@@ -242,7 +242,7 @@ class PtTransformer(nn.Module):
         return slot
 
     @torch.no_grad()
-    def run_hot_path(self, video_list, _slot=None):
+    def run_hot_path(self, video_list, _slot=None, _overlap_nms=False):
         """Launch the whole device-resident path for one collate dict; returns the engine plan (outputs stay
         on the device, nothing is synchronised)."""
         vis, aud, mask = video_list["visual"], video_list["audio"], video_list["mask"]
@@ -252,7 +252,7 @@ class PtTransformer(nn.Module):
         for i in range(B):
             m[i, 0] = float(video_list["feat_stride"][i]); m[i, 1] = float(video_list["feat_num_frames"][i])
             m[i, 2] = float(video_list["fps"][i]); m[i, 3] = float(video_list["duration"][i])
-        plan = self.engine.run(vis, aud, mask, m)
+        plan = self.engine.run(vis, aud, mask, m, overlap_nms=_overlap_nms)
         if _slot is None:                       # the slot's meta is in flight until this point of the stream
             ev = torch.cuda.Event(); ev.record(); slot["event"] = ev
         return plan
@@ -274,12 +274,16 @@ class PtTransformer(nn.Module):
             raise NotImplementedError("training is outside the inference hot path (SURVEY.md §2 C16)")
         B = video_list["visual"].shape[0]
         slot = self._host_slot(B)
-        plan = self.run_hot_path(video_list, _slot=slot)
-        slot["segments"].copy_(plan["out_segs"], non_blocking=True)
-        slot["scores"].copy_(plan["out_scores"], non_blocking=True)
-        slot["labels"].copy_(plan["out_labels"], non_blocking=True)
-        slot["counts"].copy_(plan["out_counts"], non_blocking=True)
-        ev = torch.cuda.Event(); ev.record(); slot["event"] = ev
+        plan = self.run_hot_path(video_list, _slot=slot, _overlap_nms=True)
+        # the soft-NMS of this step runs on the engine's side stream (it overlaps the next step's forward); the copies
+        # of its outputs to the host follow it there
+        ns = self.engine.nms_stream
+        with torch.cuda.stream(ns):
+            slot["segments"].copy_(plan["out_segs"], non_blocking=True)
+            slot["scores"].copy_(plan["out_scores"], non_blocking=True)
+            slot["labels"].copy_(plan["out_labels"], non_blocking=True)
+            slot["counts"].copy_(plan["out_counts"], non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(ns); slot["event"] = ev
         return PendingDetections(slot, ev)
 
     def collect_results(self, plan):
