@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--mode", default="bf16x3", choices=["f16x3", "fast", "bf16x3", "f16", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace-out", default=None, help="write the per-launch CUDA-event trace of one eager pass (JSON)")
@@ -398,7 +398,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Kst, "warmup": W,
             "ms_per_step": dev_ms / Kst, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.mode != "fp32" else "f32", "data": "synthetic",
+            "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16"}.get(args.mode, "f16"), "data": "synthetic",
             "config": dict(config, parallelism=f"dp{world} (videos sharded by index, one all-gather of detections)",
                            l2="256 MiB memset between steps (inside the timed region)",
                            schedule="streaming: soft-NMS of batch j on a side stream overlaps the forward of batch j+1",

@@ -56,8 +56,13 @@
 extern "C" {
 #endif
 
-/* UNAV_BF16X2: split BF16 pair, hi = bf16(x) at column c, lo = bf16(x - hi) at column ld/2 + c */
-enum { UNAV_F32 = 0, UNAV_BF16 = 1, UNAV_BF16X2 = 2 };
+/* UNAV_BF16X2 / UNAV_F16X2: split pair, hi = round16(x) at column c, lo = round16(x - hi) at column ld/2 + c; the
+ * tensor-core kernels run 3 MMA passes over it (hi.hi + lo.hi + hi.lo).  F16 halves carry 11 significand bits each
+ * (hi + lo ~ 22 bits: FP32-grade products, measured 1e-6 of range on the logits), BF16 halves 8 each but FP32 range.
+ * Wherever an `op_dtype` argument is taken, bits 8..9 may carry a pass count for split operands:
+ * UNAV_PASSES(1) = hi.hi only (the lo halves are not even loaded), UNAV_PASSES(2) = hi.hi + lo.hi, 0 / 3 = all. */
+enum { UNAV_F32 = 0, UNAV_BF16 = 1, UNAV_BF16X2 = 2, UNAV_F16 = 3, UNAV_F16X2 = 4 };
+#define UNAV_PASSES(n) ((n) << 8)
 enum { UNAV_ACT_NONE = 0, UNAV_ACT_RELU = 1, UNAV_ACT_GELU = 2, UNAV_ACT_SILU = 3 };
 enum { UNAV_GEMM_SIMT = 0, UNAV_GEMM_TCGEN05 = 1 };
 enum {
@@ -109,7 +114,7 @@ typedef struct UnavGemmGroup {
 } UnavGemmGroup;
 
 /* groups: host array of ngroups (<= UNAV_MAX_GROUPS) problems of identical M, N, K.
- * backend UNAV_GEMM_TCGEN05 requires op_dtype == UNAV_BF16, 16-byte aligned A/W and
+ * backend UNAV_GEMM_TCGEN05 requires a 16-bit op_dtype (BF16 / F16, plain or split), 16-byte aligned A/W and
  * lda, ldw multiples of 8 elements. */
 int unav_gemm(const UnavGemmGroup* groups, int ngroups, int M, int N, int K,
               int op_dtype, int act, int res_masked, int backend, void* stream);
@@ -186,7 +191,7 @@ int unav_attention(const UnavAttnGroup* groups, int ngroups, int nb, int Tq, int
                    int nh, int hs, float scale, int op_dtype, void* stream);
 
 /* ---- fused attention on the tensor cores (tcgen05 / TMEM), key length <= 256 ------------------------ */
-/* Same math as unav_attention.  q, k: operand-dtype (UNAV_BF16 | UNAV_BF16X2) token-major rows [nb*T, ld] with
+/* Same math as unav_attention.  q, k: operand-dtype (16-bit, plain or split) token-major rows [nb*T, ld] with
  * head h at columns [h*hs, (h+1)*hs); vt: the values TRANSPOSED per batch item, operand dtype [nb*nh*hs, ldvt >= Tk]
  * (row = item*C + channel, column = key), e.g. unav_transpose_cast(v, nb, R = Tk, Cc = C).  The optional extra key uses FP32 rows q32 / xk / xv
  * (token-major, ld = ldq32 / ldx).  out has operand dtype.  S = Q.K^T and O = P.V run as tcgen05.mma with the

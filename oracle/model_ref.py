@@ -26,19 +26,27 @@ SD = Dict[str, torch.Tensor]
 # applied to both inputs of every dense GEMM/conv to emulate BF16/TF32 tensor-core operands
 # with FP32 accumulation.  None = exact FP32 (the oracle proper).
 OPERAND_ROUND: Optional[Callable[[torch.Tensor], torch.Tensor]] = None
+# Same for the second (B / weight) operand only; None = use OPERAND_ROUND for both operands.
+OPERAND_ROUND_B: Optional[Callable[[torch.Tensor], torch.Tensor]] = None
 
 
 def _r(x):
     return x if OPERAND_ROUND is None else OPERAND_ROUND(x)
 
 
+def _rb(x):
+    if OPERAND_ROUND_B is not None:
+        return OPERAND_ROUND_B(x)
+    return _r(x)
+
+
 def _linear(x, w, b=None):
-    return F.linear(_r(x), _r(w), b)
+    return F.linear(_r(x), _rb(w), b)
 
 
 def _conv(x, w, b=None, stride=1, padding=0, groups=1):
     if groups == 1:
-        return F.conv1d(_r(x), _r(w), b, stride=stride, padding=padding)
+        return F.conv1d(_r(x), _rb(w), b, stride=stride, padding=padding)
     return F.conv1d(x, w, b, stride=stride, padding=padding, groups=groups)  # depthwise: FP32 CUDA cores
 
 
@@ -80,10 +88,10 @@ def masked_mhca(sd: SD, p: str, x1, x2, mask, n_head: int):
     k = k.view(B, n_head, hs, -1).transpose(2, 3)
     q = q.view(B, n_head, hs, -1).transpose(2, 3)
     v = v.view(B, n_head, hs, -1).transpose(2, 3)
-    att = _r(q * (1.0 / math.sqrt(hs))) @ _r(k).transpose(-2, -1)
+    att = _r(q * (1.0 / math.sqrt(hs))) @ _rb(k).transpose(-2, -1)
     att = att.masked_fill(torch.logical_not(km[:, :, None, :]), float("-inf"))
     att = F.softmax(att, dim=-1)
-    out = _r(att) @ _r(v * km[:, :, :, None].to(v.dtype))
+    out = _r(att) @ _rb(v * km[:, :, :, None].to(v.dtype))
     out = out.transpose(2, 3).contiguous().view(B, C, -1)
     out = _conv(out, sd[p + ".proj.weight"], sd[p + ".proj.bias"]) * qm.to(out.dtype)
     return out, qm
@@ -149,10 +157,10 @@ def alignment(sd: SD, p: str, visual, audio, mask, num_layers=2, heads=8):
         q = q.view(-1, b, hd).transpose(0, 1)
         k = k.view(-1, b, hd).transpose(0, 1)
         v = v.view(-1, b, hd).transpose(0, 1)
-        att = torch.bmm(_r(q), _r(k).transpose(1, 2)) / hd ** 0.5
+        att = torch.bmm(_r(q), _rb(k).transpose(1, 2)) / hd ** 0.5
         att = att + add_mask
         att = att.softmax(-1)
-        o = torch.bmm(_r(att), _r(v)).transpose(0, 1).contiguous()
+        o = torch.bmm(_r(att), _rb(v)).transpose(0, 1).contiguous()
         o = o.view(o.size(0), -1, heads * hd).transpose(0, 1)
         o = _linear(o, sd[q0 + ".attn_fusion.m.weight"], sd[q0 + ".attn_fusion.m.bias"])
         residual = residual + o
@@ -185,7 +193,7 @@ def maxsig_attn_block(sd: SD, p: str, x, guide, mask, num_heads: int):
     g = _linear(guide, sd[p + ".guide_fc.weight"], sd[p + ".guide_fc.bias"])      # over the guide's time axis
     g = g.reshape(B, -1, num_heads, hc)
     embed = x.reshape(B, num_heads, hc, H)
-    aw = torch.einsum("bmch,bnmc->bmhn", _r(embed), _r(g))
+    aw = torch.einsum("bmch,bnmc->bmhn", _r(embed), _rb(g))
     aw = aw.max(dim=-1)[0]
     aw = aw / (hc ** 0.5)
     aw = aw + sd[p + ".bias"][None, :, None]

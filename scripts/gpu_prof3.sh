@@ -20,5 +20,5 @@ PY
 echo "heaviest gemm index $IDX"
 ncu --set full --clock-control none --import-source on -k 'regex:^gemm_tcgen05' -s $IDX -c 1 -o gpurun_out/prof_gemm_top -f $CMD > gpurun_out/ncu3.log 2>&1
 echo "full capture exit $?"
-ncu --set full --clock-control none --import-source on -k 'regex:^(attention_tc|dwconv_ln)' -c 2 -o gpurun_out/prof_attn_dw -f $CMD > gpurun_out/ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:^dwconv_ln" -c 3 -o gpurun_out/prof_attn_dw -f $CMD > gpurun_out/ncu4.log 2>&1
 echo "attn/dw capture exit $?"

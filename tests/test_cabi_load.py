@@ -16,18 +16,22 @@ def test_library_builds_and_exports_header_symbols():
     from unav_yolyolva_b200.csrc import build
     so = build.build()
     assert os.path.exists(so)
-    lib = ctypes.CDLL(so)
     names = _declared_symbols()
     assert len(names) >= 17
-    for n in names:
-        assert hasattr(lib, n), f"{n} declared in unav_b200.h but not exported"
+    for path in (so, build.OUT_F16):            # BF16-halves and FP16-halves builds of the same sources
+        assert os.path.exists(path)
+        lib = ctypes.CDLL(path)
+        for n in names:
+            assert hasattr(lib, n), f"{n} declared in unav_b200.h but not exported by {os.path.basename(path)}"
 
 
 def test_ctypes_prototypes_cover_header():
     from unav_yolyolva_b200 import _cabi
     assert set(_declared_symbols()) == set(_cabi.EXPORTS)
     lib = _cabi.load()
-    assert b"sm_100a" in lib.unav_version()
+    assert b"sm_100a" in lib.unav_version() and b"BF16" in lib.unav_version()
+    lib16 = _cabi.load(_cabi.F16X2)
+    assert lib16 is not lib and b"FP16" in lib16.unav_version()
 
 
 def test_no_device_is_reported_not_hidden():

@@ -16,7 +16,9 @@ from unav_yolyolva_b200.modeling import make_multimodal_meta_arch
 pytestmark = pytest.mark.gpu
 
 # max |err| / max |ref| per tensor (SURVEY.md §8d parity gates): FP32 mode 1e-5; tensor-core modes as measured
-TOL = {"fp32": 1e-5, "bf16x3": 5e-5, "bf16": 2e-2}
+# max |err| / max |ref|: (logits, offsets).  north_star: <= 1e-5 in FP32 mode, <= 1e-3 in the 16-bit mode.
+TOL = {"fp32": (1e-5, 1e-5), "f16x3": (1e-5, 5e-5), "bf16x3": (5e-5, 2e-4), "fast": (1e-3, 1e-3), "f16": (1e-3, 4e-3),
+       "bf16": (2e-2, 8e-2)}
 
 
 @pytest.fixture(scope="module")
@@ -41,7 +43,7 @@ def _rel(a, r):
     return float((a - r).abs().max() / r.abs().max())
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "f16x3", "bf16x3", "fast", "f16", "bf16"])
 def test_logits_offsets_vs_oracle(model, oracle, mode):
     model.precision = mode
     model.use_cuda_graph = False
@@ -52,7 +54,7 @@ def test_logits_offsets_vs_oracle(model, oracle, mode):
     of = plan["offsets"].cpu().view(B, 441, 100, 2)
     e1, e2 = _rel(lg, oracle["logits"]), _rel(of, oracle["offsets"])
     print(f"[{mode}] logits rel err {e1:.3e}, offsets rel err {e2:.3e}")
-    assert e1 <= TOL[mode] and e2 <= TOL[mode] * 4
+    assert e1 <= TOL[mode][0] and e2 <= TOL[mode][1]
     assert torch.equal(plan["m_heads"].cpu().view(B, 441).bool(), oracle["masks"])
 
 

@@ -11,9 +11,11 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libunav_b200.so")
+LIB_PATH = os.path.join(_HERE, "csrc", "libunav_b200.so")              # BF16 halves (default)
+LIB_PATH_F16 = os.path.join(_HERE, "csrc", "libunav_b200_f16.so")      # FP16 halves (same sources, -DUNAV_HALF_F16)
 
-F32, BF16, BF16X2 = 0, 1, 2
+F32, BF16, BF16X2, F16, F16X2 = 0, 1, 2, 3, 4
+SPLIT_DTYPES = (BF16X2, F16X2)
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU = 0, 1, 2, 3
 GEMM_SIMT, GEMM_TCGEN05 = 0, 1
 MAX_GROUPS, MAX_COPY_JOBS = 8, 16
@@ -94,29 +96,37 @@ _PROTOS = {
 }
 
 EXPORTS = tuple(_PROTOS)
-_lib: Optional[C.CDLL] = None
+_libs = {False: None, True: None}
 
 
-def load() -> C.CDLL:
-    """Load libunav_b200.so (once) and attach prototypes.  Raises UnavError if it is not built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise UnavError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+def load(op_dtype: int = F32) -> C.CDLL:
+    """Load the library that serves `op_dtype` (once each) and attach prototypes: libunav_b200.so for F32 / BF16 /
+    BF16X2, libunav_b200_f16.so for F16 / F16X2.  Raises UnavError if it is not built."""
+    f16 = (op_dtype & 0xff) in (F16, F16X2)
+    if _libs[f16] is not None:
+        return _libs[f16]
+    path = LIB_PATH_F16 if f16 else LIB_PATH
+    if not os.path.exists(path):
+        raise UnavError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(there is no CPU / eager fallback for the hot path)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in _PROTOS.items():
         fn = getattr(lib, name)   # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    _libs[f16] = lib
     return lib
+
+
+def loaded():
+    """The libraries loaded so far (the BF16-halves one first)."""
+    load()
+    return [l for l in (_libs[False], _libs[True]) if l is not None]
 
 
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
-        msg = load().unav_last_error().decode(errors="replace")
+        msg = " | ".join(l.unav_last_error().decode(errors="replace") for l in loaded())
         raise UnavError(f"{what or 'unav call'} failed with code {rc}: {msg}")
 
 

@@ -220,6 +220,7 @@ extern "C" int unav_attention(const UnavAttnGroup* groups, int ngroups, int nb, 
   using namespace unav;
   UNAV_REQUIRE(groups && ngroups >= 1 && ngroups <= UNAV_MAX_GROUPS, "attention: bad group count");
   UNAV_REQUIRE(hs == 64 || hs == 128, "attention: head size %d not in {64,128}", hs);
+  UNAV_REQUIRE_OP(op_dtype, "attention");
   UNAV_REQUIRE(nb > 0 && Tq > 0 && Tk > 0 && nh > 0, "attention: bad shape");
   AttnParams p;
   for (int i = 0; i < ngroups; ++i) {

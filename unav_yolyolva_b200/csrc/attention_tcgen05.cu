@@ -116,8 +116,8 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {     // K-major, 
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-__device__ __forceinline__ uint32_t idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+__device__ __forceinline__ uint32_t idesc_16(int m, int n, bool f16) {      // a/b format: 0 = F16, 1 = BF16
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 }  // namespace atc
@@ -141,26 +141,32 @@ struct AttnTcParams {
 constexpr int ATC_THREADS = 320;     // TMA warp, MMA warp, 8 softmax / epilogue warps (two per TMEM lane quarter)
 
 // p = exp(s*scale - max) for N (16 | 32) consecutive keys held in r[], packed to BF16 hi (+ lo) words; returns their sum
-template <int N>
-__device__ __forceinline__ float softmax_chunk(const uint32_t* r, uint32_t m, float sc, float mx, bool split, uint32_t* hi,
-                                               uint32_t* lo) {
+template <int N, bool F16>
+__device__ __forceinline__ float softmax_chunk_t(const uint32_t* r, uint32_t m, float sc, float mx, bool split,
+                                                 uint32_t* hi, uint32_t* lo) {
+  constexpr bool f16 = F16;
   float l = 0.f;
 #pragma unroll
   for (int j = 0; j < N; j += 2) {
     const float p0 = ((m >> j) & 1u) ? __expf(__uint_as_float(r[j]) * sc - mx) : 0.f;
     const float p1 = ((m >> (j + 1)) & 1u) ? __expf(__uint_as_float(r[j + 1]) * sc - mx) : 0.f;
-    const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-    const float2 hf = __bfloat1622float2(h2);
+    const uint16_t h0 = f2h16(p0, f16), h1 = f2h16(p1, f16);
+    const float f0 = h162f(h0, f16), f1 = h162f(h1, f16);
     if (split) {
-      const __nv_bfloat162 l2 = __floats2bfloat162_rn(p0 - hf.x, p1 - hf.y);
-      lo[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+      lo[j / 2] = pack2_h16(p0 - f0, p1 - f1, f16);
       l += p0 + p1;                                         // hi + lo carries (almost) the full FP32 value
     } else {
-      l += hf.x + hf.y;                                     // normalise by what the MMA will actually sum
+      l += f0 + f1;                                         // normalise by what the MMA will actually sum
     }
-    hi[j / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+    hi[j / 2] = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
   }
   return l;
+}
+template <int N>
+__device__ __forceinline__ float softmax_chunk(const uint32_t* r, uint32_t m, float sc, float mx, bool split, bool f16,
+                                               uint32_t* hi, uint32_t* lo) {
+  (void)f16;
+  return softmax_chunk_t<N, kHalfF16>(r, m, sc, mx, split, hi, lo);
 }
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
@@ -238,7 +244,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
       // ---- S = Q.K^T : segments (Qhi,Khi), (Qlo,Khi), (Qhi,Klo)
       mbar_wait(bar_qk, 0);
       tc_fence_after();
-      const uint32_t id_s = idesc_bf16(128, Tkp);
+      const uint32_t id_s = idesc_16(128, Tkp, op_is_f16(p.op_dtype));
       uint32_t acc = 0;
       for (int seg = 0; seg < p.nseg; ++seg) {
         const int pa = seg == 1 ? 1 : 0, pb = seg == 2 ? 1 : 0;
@@ -254,7 +260,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
       mbar_wait(bar_p, 0);
       mbar_wait(bar_v, 0);
       tc_fence_after();
-      const uint32_t id_o = idesc_bf16(128, hs);
+      const uint32_t id_o = idesc_16(128, hs, op_is_f16(p.op_dtype));
       acc = 0;
       for (int seg = 0; seg < p.nseg; ++seg) {
         const int pa = seg == 1 ? 1 : 0, pb = seg == 2 ? 1 : 0;
@@ -277,7 +283,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
     const bool row_ok = qi < p.Tq;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const float sc = p.scale;
-    const bool split = p.nseg > 1;
+    const bool split = p.nseg > 1, f16 = op_is_f16(p.op_dtype);
     const int csplit = ((Tkp / 16 + 1) / 2) * 16;
     const int c_lo = half ? csplit : 0, c_hi = half ? Tkp : csplit;
     // optional extra key: s_x = scale * <q_i, xk_i>
@@ -330,13 +336,13 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
       if (c + 32 <= c_hi) {
         ld32(tm_s + lane_addr + c, r);
         wait_ld();
-        l += softmax_chunk<32>(r, m, sc, mx, split, hi, lo);
+        l += softmax_chunk<32>(r, m, sc, mx, split, f16, hi, lo);
         st16(tm_p + lane_addr + c / 2, hi);
         if (split) st16(tm_p + lane_addr + Tkp / 2 + c / 2, lo);
       } else {
         ld16(tm_s + lane_addr + c, r);
         wait_ld();
-        l += softmax_chunk<16>(r, m, sc, mx, split, hi, lo);
+        l += softmax_chunk<16>(r, m, sc, mx, split, f16, hi, lo);
         st8(tm_p + lane_addr + c / 2, hi);
         if (split) st8(tm_p + lane_addr + Tkp / 2 + c / 2, lo);
       }
@@ -433,7 +439,7 @@ struct MaxsigTcParams {
   CUtensorMap tmX[2], tmG[2];
   const float* head_bias;
   float* gate;
-  int nb, T, nwords, H, hc, nseg, x_col0, g_col0;
+  int nb, T, nwords, H, hc, nseg, x_col0, g_col0, f16;
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -479,7 +485,7 @@ maxsig_tcgen05_kernel(const __grid_constant__ MaxsigTcParams p) {
     if (lane == 0) {
       mbar_wait(bar_ld, 0);
       tc_fence_after();
-      const uint32_t id = idesc_bf16(128, 256);
+      const uint32_t id = idesc_16(128, 256, p.f16 != 0);
       for (int hf = 0; hf < nhalf; ++hf) {
         uint32_t acc = 0;
         for (int seg = 0; seg < p.nseg; ++seg) {
@@ -522,17 +528,19 @@ maxsig_tcgen05_kernel(const __grid_constant__ MaxsigTcParams p) {
 }  // namespace unav
 
 extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int nb, int Tq, int Tk, int nh, int hs,
-                                 float scale, int op_dtype, void* stream) {
+                                 float scale, int op_arg, void* stream) {
   using namespace unav;
+  const int op_dtype = op_base(op_arg);
   UNAV_REQUIRE(groups && ngroups >= 1 && ngroups <= 4, "attention_tc: bad group count %d", ngroups);
-  UNAV_REQUIRE(op_dtype == UNAV_BF16 || op_dtype == UNAV_BF16X2, "attention_tc: operands must be BF16");
+  UNAV_REQUIRE(op_is_16bit(op_dtype), "attention_tc: operands must be BF16 / F16");
+  UNAV_REQUIRE_OP(op_dtype, "attention_tc");
   UNAV_REQUIRE(hs == 64 || hs == 128, "attention_tc: head size %d not in {64,128}", hs);
   UNAV_REQUIRE(nb > 0 && Tq > 0 && Tk > 0 && Tk <= 256 && nh > 0, "attention_tc: bad shape (Tk must be <= 256)");
   AttnTcParams p;
   p.nb = nb; p.Tq = Tq; p.Tk = Tk; p.nh = nh; p.hs = hs; p.op_dtype = op_dtype; p.scale = scale;
   p.Tkp = (Tk + 15) / 16 * 16;
   if (p.Tkp < 64) p.Tkp = 64;          // keys beyond Tk are masked; keeps every MMA / TMA box at least 64 wide
-  p.nseg = op_dtype == UNAV_BF16X2 ? 3 : 1;
+  p.nseg = op_passes(op_arg) == 2 ? 3 : op_passes(op_arg);     // 1 = hi halves only, else the full split
   p.ncols = p.Tkp > 128 ? 512 : 256;
   p.phase = g_phase_buf; p.phase_cap = g_phase_cap;
   const int nparts = p.nseg > 1 ? 2 : 1;
@@ -577,19 +585,22 @@ extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int
 
 extern "C" int unav_maxsig_gate_tc(const void* x, long long ldx, int x_col0, const void* G, long long ldg, int g_col0,
                                    const float* head_bias, float* gate, int nb, int T, int nwords, int H, int hc,
-                                   int op_dtype, void* stream) {
+                                   int op_arg, void* stream) {
   using namespace unav;
+  const int op_dtype = op_base(op_arg);
   UNAV_REQUIRE(x && G && head_bias && gate, "maxsig_gate_tc: null pointer");
-  UNAV_REQUIRE(op_dtype == UNAV_BF16 || op_dtype == UNAV_BF16X2, "maxsig_gate_tc: operands must be BF16");
+  UNAV_REQUIRE(op_is_16bit(op_dtype), "maxsig_gate_tc: operands must be BF16 / F16");
+  UNAV_REQUIRE_OP(op_dtype, "maxsig_gate_tc");
   UNAV_REQUIRE((hc == 32 || hc == 64) && nwords == 512, "maxsig_gate_tc: needs hc in {32,64} and 512 guide words (got %d, %d)", hc, nwords);
   UNAV_REQUIRE(ldx % 8 == 0 && ldg % 8 == 0 && x_col0 % 8 == 0 && g_col0 % 8 == 0, "maxsig_gate_tc: unaligned operand views");
   MaxsigTcParams p;
   p.head_bias = head_bias; p.gate = gate; p.nb = nb; p.T = T; p.nwords = nwords; p.H = H; p.hc = hc;
-  p.nseg = op_dtype == UNAV_BF16X2 ? 3 : 1;
+  p.nseg = op_passes(op_arg) == 2 ? 3 : op_passes(op_arg);
+  p.f16 = kHalfF16 ? 1 : 0;
   p.x_col0 = x_col0; p.g_col0 = g_col0;
   const int nparts = p.nseg > 1 ? 2 : 1;
   // logical widths of the two operand matrices (columns beyond are read as zero by TMA)
-  const long long xw = (op_dtype == UNAV_BF16X2 ? ldx / 2 : ldx), gw = (op_dtype == UNAV_BF16X2 ? ldg / 2 : ldg);
+  const long long xw = (op_is_split(op_dtype) ? ldx / 2 : ldx), gw = (op_is_split(op_dtype) ? ldg / 2 : ldg);
   for (int pt = 0; pt < nparts; ++pt) {
     const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x) + (pt ? ldx / 2 : 0);
     const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(G) + (pt ? ldg / 2 : 0);

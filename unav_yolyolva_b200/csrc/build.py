@@ -9,7 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["lib.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "rowops.cu", "attention.cu", "attention_tcgen05.cu", "decode_nms.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "unav_b200.h")]
-OUT = os.path.join(HERE, "libunav_b200.so")
+OUT = os.path.join(HERE, "libunav_b200.so")               # BF16 halves
+OUT_F16 = os.path.join(HERE, "libunav_b200_f16.so")       # same sources, -DUNAV_HALF_F16 (FP16 halves)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -17,9 +18,9 @@ NVCC_FLAGS = [
 
 
 def _stale():
-    if not os.path.exists(OUT):
+    if not (os.path.exists(OUT) and os.path.exists(OUT_F16)):
         return True
-    t = os.path.getmtime(OUT)
+    t = min(os.path.getmtime(OUT), os.path.getmtime(OUT_F16))
     return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS)
 
 
@@ -27,14 +28,16 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
-    for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(HERE, src), "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    variants = (("", [], OUT), ("_f16", ["-DUNAV_HALF_F16"], OUT_F16))
+    objs = {tag: [] for tag, _, _ in variants}
+    for tag, defs, _ in variants:
+        for src in SOURCES:
+            obj = os.path.join(HERE, "build", src.replace(".cu", f"{tag}.o"))
+            objs[tag].append(obj)
+            cmd = [nvcc, *NVCC_FLAGS, *defs, "-c", os.path.join(HERE, src), "-o", obj]
+            procs.append((src + tag, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False
     for src, p in procs:
@@ -47,7 +50,8 @@ def build(force=False, verbose=False):
         print("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed; see log above")
-    subprocess.check_call([nvcc, "-shared", "-o", OUT, *objs, "-cudart", "static"])
+    for tag, _, out in variants:
+        subprocess.check_call([nvcc, "-shared", "-o", out, *objs[tag], "-cudart", "static"])
     return OUT
 
 

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -85,43 +86,95 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// The 16-bit half type is a BUILD-time choice: libunav_b200.so is compiled for BF16 halves, libunav_b200_f16.so (same
+// sources, -DUNAV_HALF_F16) for FP16 halves, and each accepts only its own op dtypes.  (A runtime switch in
+// store_op4 / the GEMM epilogue cost 3.7 % of the whole step for a format that is chosen once per model.)
+#ifdef UNAV_HALF_F16
+constexpr bool kHalfF16 = true;
+#else
+constexpr bool kHalfF16 = false;
+#endif
+__host__ __device__ __forceinline__ bool op_is_split(int op) { return op == UNAV_BF16X2 || op == UNAV_F16X2; }
+__host__ __device__ __forceinline__ constexpr bool op_is_f16(int) { return kHalfF16; }
+__host__ __device__ __forceinline__ bool op_build_ok(int op) {
+  return op == UNAV_F32 || (kHalfF16 ? (op == UNAV_F16 || op == UNAV_F16X2) : (op == UNAV_BF16 || op == UNAV_BF16X2));
+}
+#define UNAV_REQUIRE_OP(op, what)                                                                                 \
+  UNAV_REQUIRE(unav::op_build_ok((op) & 0xff), "%s: op_dtype %d does not belong to this build (%s halves)", what, \
+               (op) & 0xff, unav::kHalfF16 ? "FP16" : "BF16")
+__host__ __device__ __forceinline__ bool op_is_16bit(int op) { return op >= UNAV_BF16 && op <= UNAV_F16X2; }
+// op_dtype arguments may carry a pass count in bits 8..9 (UNAV_PASSES)
+__host__ __device__ __forceinline__ int op_base(int op_arg) { return op_arg & 0xff; }
+__host__ __device__ __forceinline__ int op_passes(int op_arg) {
+  const int n = (op_arg >> 8) & 3;
+  return !op_is_split(op_arg & 0xff) ? 1 : (n == 0 ? 3 : n);
+}
+
+// round-to-nearest 16-bit halves as raw bits (FP16 saturates to the largest finite value instead of overflowing to inf)
+__device__ __forceinline__ uint16_t f2h16(float v, bool f16) {
+  if (f16) {
+    uint16_t h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return h;
+  }
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float h162f(uint16_t h, bool f16) {
+  return f16 ? __half2float(__ushort_as_half(h)) : __bfloat162float(__ushort_as_bfloat16(h));
+}
+__device__ __forceinline__ uint32_t pack2_h16(float a, float b, bool f16) {
+  return static_cast<uint32_t>(f2h16(a, f16)) | (static_cast<uint32_t>(f2h16(b, f16)) << 16);
+}
+
 // Store one value into an operand buffer row (`p` points at the row start, `c` is the column).
-// split_off = ld/2 for BF16X2.
+// split_off = ld/2 for the split formats.
 __device__ __forceinline__ void store_op(void* row, int op_dtype, long long c, long long split_off,
                                          float v) {
   if (op_dtype == UNAV_F32) {
     reinterpret_cast<float*>(row)[c] = v;
   } else {
-    __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    reinterpret_cast<__nv_bfloat16*>(row)[c] = hi;
-    if (op_dtype == UNAV_BF16X2) {
-      float lo = v - __bfloat162float(hi);
-      reinterpret_cast<__nv_bfloat16*>(row)[split_off + c] = __float2bfloat16_rn(lo);
-    }
+    const bool f16 = op_is_f16(op_dtype);
+    const uint16_t hi = f2h16(v, f16);
+    reinterpret_cast<uint16_t*>(row)[c] = hi;
+    if (op_is_split(op_dtype)) reinterpret_cast<uint16_t*>(row)[split_off + c] = f2h16(v - h162f(hi, f16), f16);
   }
 }
 
 // 4 consecutive columns (c % 4 == 0, buffers 16-byte aligned, ld % 8 == 0).
+template <bool F16>
+__device__ __forceinline__ void store_op4_16(uint16_t* r, bool split, long long c, long long split_off, float4 v) {
+  uint2 pk, pl;
+  if (F16) {
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+    pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+    if (split) {
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+      pl.x = *reinterpret_cast<const uint32_t*>(&l01);
+      pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+    }
+  } else {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+    pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+    if (split) {
+      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+      pl.x = *reinterpret_cast<const uint32_t*>(&l01);
+      pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+    }
+  }
+  *reinterpret_cast<uint2*>(r + c) = pk;
+  if (split) *reinterpret_cast<uint2*>(r + split_off + c) = pl;
+}
+
 __device__ __forceinline__ void store_op4(void* row, int op_dtype, long long c, long long split_off,
                                           float4 v) {
   if (op_dtype == UNAV_F32) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(row) + c) = v;
   } else {
-    __nv_bfloat16* r = reinterpret_cast<__nv_bfloat16*>(row);
-    __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y);
-    __nv_bfloat162 h23 = __floats2bfloat162_rn(v.z, v.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&h01);
-    pk.y = *reinterpret_cast<uint32_t*>(&h23);
-    *reinterpret_cast<uint2*>(r + c) = pk;
-    if (op_dtype == UNAV_BF16X2) {
-      float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-      __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
-      __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
-      pk.x = *reinterpret_cast<uint32_t*>(&l01);
-      pk.y = *reinterpret_cast<uint32_t*>(&l23);
-      *reinterpret_cast<uint2*>(r + split_off + c) = pk;
-    }
+    store_op4_16<kHalfF16>(reinterpret_cast<uint16_t*>(row), op_is_split(op_dtype), c, split_off, v);
   }
 }
 
@@ -129,13 +182,14 @@ __host__ __device__ __forceinline__ size_t op_elem_size(int op_dtype) {
   return op_dtype == UNAV_F32 ? 4 : 2;
 }
 
-// Load an operand element as float (SIMT GEMM path). For BF16X2 returns hi + lo.
+// Load an operand element as float (SIMT GEMM path). For the split formats returns hi + lo.
 __device__ __forceinline__ float load_op(const void* row, int op_dtype, long long c,
                                          long long split_off) {
   if (op_dtype == UNAV_F32) return reinterpret_cast<const float*>(row)[c];
-  const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(row);
-  float v = __bfloat162float(r[c]);
-  if (op_dtype == UNAV_BF16X2) v += __bfloat162float(r[split_off + c]);
+  const bool f16 = op_is_f16(op_dtype);
+  const uint16_t* r = reinterpret_cast<const uint16_t*>(row);
+  float v = h162f(r[c], f16);
+  if (op_is_split(op_dtype)) v += h162f(r[split_off + c], f16);
   return v;
 }
 

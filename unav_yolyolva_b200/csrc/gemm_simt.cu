@@ -122,7 +122,8 @@ extern "C" int unav_gemm(const UnavGemmGroup* groups, int ngroups, int M, int N,
   using namespace unav;
   UNAV_REQUIRE(groups && ngroups >= 1 && ngroups <= UNAV_MAX_GROUPS, "unav_gemm: bad group count %d", ngroups);
   UNAV_REQUIRE(M > 0 && N > 0 && K > 0, "unav_gemm: bad shape %d %d %d", M, N, K);
-  UNAV_REQUIRE(op_dtype >= UNAV_F32 && op_dtype <= UNAV_BF16X2, "unav_gemm: bad op_dtype %d", op_dtype);
+  UNAV_REQUIRE(op_base(op_dtype) >= UNAV_F32 && op_base(op_dtype) <= UNAV_F16X2, "unav_gemm: bad op_dtype %d", op_dtype);
+  UNAV_REQUIRE_OP(op_dtype, "unav_gemm");
   for (int i = 0; i < ngroups; ++i) {
     UNAV_REQUIRE(groups[i].A && groups[i].W, "unav_gemm: null operand in group %d", i);
     UNAV_REQUIRE(groups[i].out_f32 || groups[i].out_op || groups[i].out_opT, "unav_gemm: group %d has no output", i);
@@ -130,5 +131,5 @@ extern "C" int unav_gemm(const UnavGemmGroup* groups, int ngroups, int M, int N,
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (backend == UNAV_GEMM_TCGEN05)
     return gemm_tcgen05(groups, ngroups, M, N, K, op_dtype, act, res_masked, s);
-  return gemm_simt(groups, ngroups, M, N, K, op_dtype, act, res_masked, s);
+  return gemm_simt(groups, ngroups, M, N, K, op_base(op_dtype), act, res_masked, s);   // CUDA cores: always hi + lo
 }

@@ -129,9 +129,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
 // a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24.
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool f16 = false) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);      // a/b format: 0 = F16, 1 = BF16
 }
 
 template <int BN, int BK = TC_BK>
@@ -147,7 +147,7 @@ struct TcSmem {
 // Each lane owns 4 consecutive columns of RPP-strided rows; four rows are in flight per lane.
 template <int ACT, bool SPLIT, int PITCH, int RPP>
 __device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const float* stg_lane, long long m_base, int rows,
-                                                   int rsub, int n, int res_masked, const float (&bias)[4],
+                                                   int rsub, int n, int res_masked, bool f16, const float (&bias)[4],
                                                    const float (&cs)[4]) {
   const bool has_res = e.res != nullptr, has_gate = e.gate != nullptr, has_mask = e.rowmask != nullptr,
              has_rs = e.rowscale != nullptr;
@@ -182,7 +182,8 @@ __device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const flo
     if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + m * e.ld_f32 + n) = make_float4(v[0], v[1], v[2], v[3]);
     if (e.out_op) {
       char* row = reinterpret_cast<char*>(e.out_op) + static_cast<size_t>(m) * e.ld_op * 2;
-      store_op4(row, SPLIT ? UNAV_BF16X2 : UNAV_BF16, n, op_split, make_float4(v[0], v[1], v[2], v[3]));
+      store_op4(row, SPLIT ? (f16 ? UNAV_F16X2 : UNAV_BF16X2) : (f16 ? UNAV_F16 : UNAV_BF16), n, op_split,
+                make_float4(v[0], v[1], v[2], v[3]));
     }
   }
 }
@@ -269,7 +270,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(TC_BM, BN);
+      const uint32_t idesc = make_idesc(TC_BM, BN, op_is_f16(p.op_dtype));
       const int nseg_in = p.nseg;
       for (int it = 0; it < iters; ++it) {
         const int s = it % NS;
@@ -286,6 +287,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
           for (int h32 = 0; h32 < BK / 32; ++h32) {
 #pragma unroll
             for (int seg = 0; seg < 3; ++seg) {
+              if (seg >= nseg_in) break;
               const uint64_t adesc = make_smem_desc<BK>(sa + (seg == 1 ? Sm::A_BYTES : 0));
               const uint64_t bdesc = make_smem_desc<BK>(sa + w_off + (seg == 2 ? Sm::B_BYTES : 0));
 #pragma unroll
@@ -384,19 +386,20 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       const long long m_base = static_cast<long long>(m0) + q * 32;
       const int rows = static_cast<int>(min(32ll, static_cast<long long>(p.M) - m_base));
       const float* sl = stg + cl * 4;
-      const bool split = p.op_dtype == UNAV_BF16X2;
+      const bool split = op_is_split(p.op_dtype);
+      constexpr bool f16 = kHalfF16;
 #define UNAV_EPI_CASE(A)                                                                                          \
       case A:                                                                                                       \
-        if (split) epilogue_rows_fast<A, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, bias, cs);   \
-        else epilogue_rows_fast<A, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, bias, cs);        \
+        if (split) epilogue_rows_fast<A, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);   \
+        else epilogue_rows_fast<A, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);        \
         break;
       switch (act) {
         UNAV_EPI_CASE(UNAV_ACT_RELU)
         UNAV_EPI_CASE(UNAV_ACT_GELU)
         UNAV_EPI_CASE(UNAV_ACT_SILU)
         default:
-          if (split) epilogue_rows_fast<UNAV_ACT_NONE, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, bias, cs);
-          else epilogue_rows_fast<UNAV_ACT_NONE, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, bias, cs);
+          if (split) epilogue_rows_fast<UNAV_ACT_NONE, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);
+          else epilogue_rows_fast<UNAV_ACT_NONE, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);
       }
 #undef UNAV_EPI_CASE
     } else if (nvalid > 0 && (e.out_f32 || e.out_op)) {
@@ -577,12 +580,13 @@ static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
   return finish_launch("gemm_tcgen05");
 }
 
-int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, int op_dtype, int act,
+int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, int op_arg, int act,
                  int res_masked, cudaStream_t stream) {
-  UNAV_REQUIRE(op_dtype == UNAV_BF16 || op_dtype == UNAV_BF16X2, "gemm_tcgen05: operands must be BF16 (got %d)", op_dtype);
+  const int op_dtype = op_base(op_arg);
+  UNAV_REQUIRE(op_is_16bit(op_dtype), "gemm_tcgen05: operands must be BF16 / F16 (got %d)", op_dtype);
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.op_dtype = op_dtype; p.act = act; p.res_masked = res_masked;
-  p.nseg = (op_dtype == UNAV_BF16X2) ? 3 : 1;
+  p.nseg = op_passes(op_arg);       // 1 pass on split operands reads the hi halves only
   p.phase = g_phase_buf; p.phase_cap = g_phase_cap;
   const TcChoice ch = choose_tile(M, N, K, ngroups, p.nseg);
   const int bn = ch.bn, bk = ch.sched == 2 ? 32 : 64;
@@ -592,13 +596,13 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
     UNAV_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.W) & 15) == 0,
                  "gemm_tcgen05: A/W must be 16-byte aligned");
     UNAV_REQUIRE(g.lda % 8 == 0 && g.ldw % 8 == 0, "gemm_tcgen05: lda/ldw must be multiples of 8 (got %lld, %lld)", g.lda, g.ldw);
-    if (op_dtype == UNAV_BF16X2)
+    if (op_is_split(op_dtype))
       UNAV_REQUIRE(g.lda % 16 == 0 && g.ldw % 16 == 0 && g.lda / 2 >= K && g.ldw / 2 >= K,
                    "gemm_tcgen05: split operands need ld %% 16 == 0 and ld/2 >= K");
     int rc;
     if ((rc = encode_map(&p.g[i].tmA[0], g.A, M, K, g.lda, TC_BM, bk))) return rc;
     if ((rc = encode_map(&p.g[i].tmW[0], g.W, N, K, g.ldw, bn, bk))) return rc;
-    if (op_dtype == UNAV_BF16X2) {
+    if (p.nseg > 1) {
       const __nv_bfloat16* alo = reinterpret_cast<const __nv_bfloat16*>(g.A) + g.lda / 2;
       const __nv_bfloat16* wlo = reinterpret_cast<const __nv_bfloat16*>(g.W) + g.ldw / 2;
       if ((rc = encode_map(&p.g[i].tmA[1], alo, M, K, g.lda, TC_BM, bk))) return rc;

@@ -45,7 +45,9 @@ int finish_launch(const char* what) {
 
 }  // namespace unav
 
-extern "C" const char* unav_version(void) { return "unav_b200 0.1 (sm_100a)"; }
+extern "C" const char* unav_version(void) {
+  return unav::kHalfF16 ? "unav_b200 0.1 (sm_100a, FP16 halves)" : "unav_b200 0.1 (sm_100a, BF16 halves)";
+}
 extern "C" const char* unav_last_error(void) { return unav::g_err; }
 extern "C" long long unav_launch_count(void) { return unav::g_launches.load(); }
 extern "C" int unav_set_phase_trace(long long* device_buf, int capacity_ctas) {

@@ -505,6 +505,7 @@ using namespace unav;
 extern "C" int unav_layernorm_rows(const UnavLnGroup* groups, int ngroups, int M, int C, float eps, int act,
                                    int op_dtype, void* stream) {
   UNAV_REQUIRE(groups && ngroups >= 1 && ngroups <= UNAV_MAX_GROUPS, "layernorm_rows: bad group count");
+  UNAV_REQUIRE_OP(op_dtype, "layernorm_rows");
   UNAV_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && C <= 128 * MAXV, "layernorm_rows: unsupported C=%d", C);
   LnParams p;
   for (int i = 0; i < ngroups; ++i) {
@@ -523,6 +524,7 @@ extern "C" int unav_layernorm_rows(const UnavLnGroup* groups, int ngroups, int M
 extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg, int seg_len_in, int stride,
                               int C, int n_pre, int n_out, float eps, int op_dtype, void* stream) {
   UNAV_REQUIRE(groups && ngroups >= 1 && ngroups <= UNAV_MAX_GROUPS, "dwconv_ln: bad group count");
+  UNAV_REQUIRE_OP(op_dtype, "dwconv_ln");
   UNAV_REQUIRE(C % 4 == 0 && C <= 128 * DWV, "dwconv_ln: unsupported C=%d", C);
   UNAV_REQUIRE((stride == 1 || stride == 2) && seg_len_in % stride == 0, "dwconv_ln: bad stride/length");
   UNAV_REQUIRE(n_pre >= 0 && n_pre <= 2 && n_out >= 1 && n_out <= 3, "dwconv_ln: bad n_pre/n_out");
@@ -547,6 +549,7 @@ extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg
 
 extern "C" int unav_rowcopy(const UnavCopyJob* jobs, int njobs, int op_dtype, void* stream) {
   UNAV_REQUIRE(jobs && njobs >= 1 && njobs <= UNAV_MAX_COPY_JOBS, "rowcopy: bad job count %d", njobs);
+  UNAV_REQUIRE_OP(op_dtype, "rowcopy");
   CopyParams p;
   long long maxtotal = 0;
   for (int i = 0; i < njobs; ++i) {
@@ -568,6 +571,7 @@ extern "C" int unav_rowcopy(const UnavCopyJob* jobs, int njobs, int op_dtype, vo
 extern "C" int unav_transpose_cast(const float* in, long long ld_in, void* out, long long ld_out, int nb, int R,
                                    int Cc, int op_dtype, void* stream) {
   UNAV_REQUIRE(in && out && nb > 0 && R > 0 && Cc > 0, "transpose_cast: bad arguments");
+  UNAV_REQUIRE_OP(op_dtype, "transpose_cast");
   dim3 grid((Cc + 31) / 32, (R + 31) / 32, nb);
   launch_pdl(transpose_cast_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), in, ld_in, out, ld_out, R, Cc, op_dtype);
   count_launch();

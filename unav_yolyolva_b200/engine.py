@@ -13,8 +13,13 @@ GEMM operands are separate buffers in the operand dtype of the chosen precision 
 
     mode      operands              GEMM backend                    max |err| / range on logits vs FP32 oracle
     fp32      FP32                  CUDA-core FFMA (gemm_simt)      ~1e-6
-    bf16x3    BF16 hi/lo split      tcgen05, 3 MMA passes           ~5e-6
+    f16x3     FP16 hi/lo split      tcgen05, 3 MMA passes           ~1e-6   (2 x 11 significand bits)
+    bf16x3    BF16 hi/lo split      tcgen05, 3 MMA passes           ~8e-6   (2 x 8 bits, FP32 exponent range)
+    fast      FP16 hi/lo split      tcgen05, 1 pass (hi.hi) in the Alignment and backbone stages,
+                                    3 passes in the fusion passes and heads              ~2e-4 (north_star's BF16 budget: 1e-3)
+    f16       FP16                  tcgen05, 1 MMA pass             ~4e-4 (offsets 1.2e-3)
     bf16      BF16                  tcgen05, 1 MMA pass             ~3e-3
+The per-stage pass counts come from scripts/precision_study.py (oracle with emulated operand rounding).
 
 k=3 convolutions are GEMMs over im2col operands that the producing kernel scatters directly (no separate
 im2col pass for LayerNorm outputs).  Reference semantics restated per step with file:line in the comments
@@ -28,10 +33,13 @@ from typing import Dict, List, Optional
 import torch
 
 from . import kernels as K
-from .kernels import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, BF16, BF16X2, F32, GEMM_SIMT, GEMM_TCGEN05, View
+from .kernels import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, BF16, BF16X2, F16, F16X2, F32, GEMM_SIMT, GEMM_TCGEN05, View
 
 MODES = {"fp32": (F32, GEMM_SIMT), "bf16": (BF16, GEMM_TCGEN05), "bf16x3": (BF16X2, GEMM_TCGEN05),
+         "f16": (F16, GEMM_TCGEN05), "f16x3": (F16X2, GEMM_TCGEN05), "fast": (F16X2, GEMM_TCGEN05),
          "bf16_simt": (BF16, GEMM_SIMT), "bf16x3_simt": (BF16X2, GEMM_SIMT)}
+# MMA passes over split operands per stage of the path (0 = all three); stages not listed run all passes
+STAGE_PASSES = {"fast": {"alignment": 1, "backbone": 1}}
 
 
 def _flat(p: torch.Tensor) -> torch.Tensor:
@@ -66,6 +74,8 @@ class HotPathEngine:
             self.level_off.append(self.level_off[-1] + t)
         # fused tcgen05/TMEM attention for the tensor-core modes (key length <= 256); CUDA-core kernel otherwise
         self.tc_attn = self.backend == GEMM_TCGEN05 and self.T + 1 <= 256
+        self.stage_passes = STAGE_PASSES.get(mode, {})
+        self._stage = "alignment"
         self.w: Dict[str, torch.Tensor] = {}
         self._pack_weights()
         self._plans: Dict[int, dict] = {}
@@ -297,7 +307,7 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------------------ helpers
     def _gemm(self, groups, M, N, Kd, act=ACT_NONE, res_masked=False):
-        K.gemm(groups, M, N, Kd, self.op, act, res_masked, self.backend)
+        K.gemm(groups, M, N, Kd, self.op, act, res_masked, self.backend, passes=self.stage_passes.get(self._stage, 0))
 
     def _qkv_outs(self, q32, k32, v32, qop, kop, vt, T, Cc, rows=None, items=None):
         """Output routing of the q / k / v projection GEMMs.  Tensor-core attention: q, k as operand rows and the
@@ -313,7 +323,8 @@ class HotPathEngine:
         scale = 1.0 / math.sqrt(hs)
         if self.tc_attn:
             Cc = nh * hs
-            K.attention_tc([{"q": qop, "k": kop, "vt": vt[:nb * Cc], "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op)
+            K.attention_tc([{"q": qop, "k": kop, "vt": vt[:nb * Cc], "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op,
+                           passes=self.stage_passes.get(self._stage, 0))
         else:
             K.attention([{"q": q32, "k": k32, "v": v32, "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op)
 
@@ -342,6 +353,7 @@ class HotPathEngine:
         K.build_masks(P["mask_in"], P["m_true"], P["m_up"], P["m_cls"], P["m_heads"], NB, B, T, L)
 
         # ================================================================== Alignment (:1144-1207)
+        self._stage = "alignment"
         K.transpose_cast(P["visual"], T, P["Xv"], B, 2048, T, op)        # [B,2048,T] -> [B*T,2048]
         K.transpose_cast(P["audio"], T, P["Xa"], B, 128, T, op)
         self._gemm([{"A": P["Xv"], "W": w["al.pv"], "bias": w["al.pv.b"], "out_f32": P["x0"][:half]}], half, C, 2048)
@@ -371,7 +383,10 @@ class HotPathEngine:
                     groups.append({"q": View(own, 0, C), "k": View(own, C, C), "v": View(own, 2 * C, C),
                                    "kmask": P["m_cls"], "xk": View(oth, C, C), "xv": View(oth, 2 * C, C), "x_first": 1,
                                    "out": P["AOa"][g * hm:(g + 1) * hm]})
-            (K.attention_tc if self.tc_attn else K.attention)(groups, B, N1, N1, 8, C // 8, 1.0 / math.sqrt(C // 8), op)
+            if self.tc_attn:
+                K.attention_tc(groups, B, N1, N1, 8, C // 8, 1.0 / math.sqrt(C // 8), op, passes=self.stage_passes.get(self._stage, 0))
+            else:
+                K.attention(groups, B, N1, N1, 8, C // 8, 1.0 / math.sqrt(C // 8), op)
             self._gemm([{"A": P["AOa"], "W": w["al.m"], "bias": w["al.m.b"], "res": F, "out_f32": F1}], Ma, C, C)
             K.layernorm_rows([{"x": F1[g * hm:(g + 1) * hm], "w": w[f"al.n2.{mod}.w"], "b": w[f"al.n2.{mod}.b"],
                                "out_op": P["Fn"][g * hm:(g + 1) * hm]} for g, mod in enumerate(("video", "text"))], hm, C, op)
@@ -393,6 +408,7 @@ class HotPathEngine:
                            "out_im2col": P["E"][g * half:(g + 1) * half]} for g, mod in enumerate(("video", "text"))], half, C, op)
 
         # ================================================================== backbone stem (:771-807)
+        self._stage = "backbone"
         X, X1 = P["X"], P["X1"]
         for i in range(2):
             self._gemm([{"A": P["E"][g * half:(g + 1) * half], "W": w[f"bb.embd{Xm}{i}"], "rowmask": m0[g * half:(g + 1) * half],
@@ -456,6 +472,7 @@ class HotPathEngine:
             K.dwconv_ln([{"x": feats[l], "mask_out": self._mask(P, l + 1), "outs": [o]}], NB, Tl[l], 2, C, op)
 
         # ================================================================== fusion, both passes as one 2B batch (:552-619)
+        self._stage = "fusion"
         # guide of item i = stem output of the other modality: rows rolled by B*T
         K.transpose_cast(X[half:], C, P["gT"][:B * C], B, T, C, op)      # [B,T,C] -> [B*C, T]
         K.transpose_cast(X[:half], C, P["gT"][B * C:], B, T, C, op)
@@ -501,6 +518,7 @@ class HotPathEngine:
             self._csp(P, f"fu.bu{l}", P["BUin"][l + 1], P["G_bu"], l * (C // 2), self.bu_heads[l], mt, l + 1, o[l + 1], None)
 
         # ================================================================== heads (meta_archs.py:166-178, :245-259)
+        self._stage = "heads"
         Mh = B * Ttot
         jobs = []
         for l in range(L):
@@ -580,7 +598,7 @@ class HotPathEngine:
         gate = P["gate"].view(-1)[:M * heads].view(M, heads)
         if self.tc_attn and C == 512:      # tcgen05 gate: c_3's operand copy is the CAT window written by block 2's projection
             K.maxsig_gate_tc(CAT, C + 2 * Ch, P["G_td_op"] if G is P["G_td"] else P["G_bu_op"], g_off, w[name + ".hb"], gate,
-                             NB, Tl, C, heads, hc, op)
+                             NB, Tl, C, heads, hc, op, passes=self.stage_passes.get(self._stage, 0))
         else:
             K.maxsig_gate(c3, View(G, g_off, Ch), w[name + ".hb"], gate, NB, Tl, C, heads, hc)
         K.rowcopy([{"src": c3, "dst": P["c3i"][:M], "nseg": NB, "seg_len_in": Tl, "seg_len_out": Tl, "ntaps": 3,

@@ -11,9 +11,15 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _cabi as A
-from ._cabi import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, BF16, BF16X2, F32, GEMM_SIMT, GEMM_TCGEN05  # noqa: F401
+from ._cabi import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, BF16, BF16X2, F16, F16X2, F32, GEMM_SIMT,  # noqa: F401
+                    GEMM_TCGEN05, SPLIT_DTYPES)
 
-OP_TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, BF16X2: torch.bfloat16}
+OP_TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, BF16X2: torch.bfloat16, F16: torch.float16, F16X2: torch.float16}
+
+
+def with_passes(op_dtype: int, passes: int = 0) -> int:
+    """op_dtype argument carrying a pass count for split operands (include/unav_b200.h UNAV_PASSES): 0 = all three."""
+    return op_dtype | (passes << 8) if op_dtype in SPLIT_DTYPES else op_dtype
 
 
 def _stream() -> int:
@@ -95,7 +101,7 @@ def op_cols(K: int, op_dtype: int) -> int:
     if op_dtype == F32:
         return round_up(K, 4)
     kp = round_up(K, 8)
-    return 2 * kp if op_dtype == BF16X2 else kp
+    return 2 * kp if op_dtype in SPLIT_DTYPES else kp
 
 
 def new_operand(rows: int, K: int, op_dtype: int, device) -> torch.Tensor:
@@ -110,11 +116,12 @@ def pack_operand(w: torch.Tensor, op_dtype: int) -> torch.Tensor:
     if op_dtype == F32:
         out[:, :K] = w
     else:
-        hi = w.to(torch.bfloat16)
+        dt = OP_TORCH_DTYPE[op_dtype]
+        hi = w.to(dt)
         out[:, :K] = hi
-        if op_dtype == BF16X2:
+        if op_dtype in SPLIT_DTYPES:
             half = out.shape[1] // 2
-            out[:, half:half + K] = (w - hi.float()).to(torch.bfloat16)
+            out[:, half:half + K] = (w - hi.float()).to(dt)
     return out
 
 
@@ -153,9 +160,9 @@ def _vld(v) -> int:
 
 # ------------------------------------------------------------------------------------------- GEMM
 def gemm(groups: Sequence[dict], M: int, N: int, K: int, op_dtype: int, act: int = ACT_NONE,
-         res_masked: bool = False, backend: int = GEMM_TCGEN05) -> None:
+         res_masked: bool = False, backend: int = GEMM_TCGEN05, passes: int = 0) -> None:
     """groups: dicts with keys A, W (required) and bias, rowmask, rowscale, gate, gate_groups, gate_width,
-    res, colscale, out_f32, out_op (tensors or Views)."""
+    res, colscale, out_f32, out_op (tensors or Views).  passes: MMA passes over split operands (0 = all 3)."""
     n = len(groups)
     arr = (A.GemmGroup * n)()
     for i, g in enumerate(groups):
@@ -174,12 +181,14 @@ def gemm(groups: Sequence[dict], M: int, N: int, K: int, op_dtype: int, act: int
         s.out_op, s.ld_op = _vp(g.get("out_op")), _vld(g.get("out_op"))
         s.out_opT, s.ld_opT = _vp(g.get("out_opT")), _vld(g.get("out_opT"))
         s.t_seg, s.t_col0, s.t_ncols = g.get("t_seg", 0), g.get("t_col0", 0), g.get("t_ncols", 0)
-    lib = A.load()
-    es = 4 if op_dtype == F32 else (4 if op_dtype == BF16X2 else 2)
+    lib = A.load(op_dtype)
+    es = 4 if op_dtype == F32 else (4 if op_dtype in SPLIT_DTYPES else 2)
+    es_in = 2 if (op_dtype in SPLIT_DTYPES and passes == 1) else es     # one pass reads the hi halves only
     out_b = sum((4 if g.get("out_f32") is not None else 0) + (es if g.get("out_op") is not None else 0) for g in groups)
     with _Span("gemm_tcgen05" if backend == GEMM_TCGEN05 else "gemm_simt", 2.0 * M * N * K * n,
-               n * (M * K + N * K) * es + M * N * out_b, f"{n}x[{M},{N},{K}]"):
-        A.check(lib.unav_gemm(arr, n, M, N, K, op_dtype, act, int(res_masked), backend, _stream()), "unav_gemm")
+               n * (M * K + N * K) * es_in + M * N * out_b, f"{n}x[{M},{N},{K}]" + (f"p{passes}" if passes else "")):
+        A.check(lib.unav_gemm(arr, n, M, N, K, with_passes(op_dtype, passes), act, int(res_masked), backend, _stream()),
+                "unav_gemm")
 
 
 # -------------------------------------------------------------------------------------- LayerNorm
@@ -202,7 +211,7 @@ def layernorm_rows(groups: Sequence[dict], M: int, C_: int, op_dtype: int, act: 
         s.x_seg_rows = g.get("x_seg_rows", 0)
         s.x_seg_stride = g.get("x_seg_stride", 0)
         s.x_row_off = g.get("x_row_off", 0)
-    lib = A.load()
+    lib = A.load(op_dtype)
     with _Span("layernorm_rows", 8.0 * M * C_ * n, n * M * C_ * 8, f"{n}x[{M},{C_}]"):
         A.check(lib.unav_layernorm_rows(arr, n, M, C_, eps, act, op_dtype, _stream()), "unav_layernorm_rows")
 
@@ -229,7 +238,7 @@ def dwconv_ln(groups: Sequence[dict], nseg: int, seg_len_in: int, stride: int, C
             d.src = o.get("src", -1)
             d.out_f32, d.ld_f32 = _vp(o.get("out_f32")), _vld(o.get("out_f32"))
             d.out_op, d.ld_op = _vp(o.get("out_op")), _vld(o.get("out_op"))
-    lib = A.load()
+    lib = A.load(op_dtype)
     rows = nseg * (seg_len_in // stride)
     with _Span("dwconv_ln", 20.0 * rows * C_ * n * n_out, n * rows * C_ * (4 * stride + 4 * n_out), f"{n}x[{rows},{C_}]x{n_out}"):
         A.check(lib.unav_dwconv_ln(arr, n, nseg, seg_len_in, stride, C_, n_pre, n_out, eps, op_dtype, _stream()),
@@ -251,12 +260,13 @@ def attention(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs: in
         s.ldx = _vld(g.get("xk"))
         s.x_first = g.get("x_first", 0)
         s.out, s.ldo = _vp(g["out"]), _vld(g["out"])
-    lib = A.load()
+    lib = A.load(op_dtype)
     with _Span("attention", 4.0 * n * nb * nh * Tq * Tk * hs, n * nb * nh * hs * (Tq * 8 + Tk * 8), f"{n}x[{nb},{nh},{Tq},{Tk},{hs}]"):
         A.check(lib.unav_attention(arr, n, nb, Tq, Tk, nh, hs, scale, op_dtype, _stream()), "unav_attention")
 
 
-def attention_tc(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs: int, scale: float, op_dtype: int) -> None:
+def attention_tc(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs: int, scale: float, op_dtype: int,
+                 passes: int = 0) -> None:
     """tcgen05 attention (Tk <= 256): groups carry q, k (operand rows), vt (operand, transposed values), kmask, out and
     optionally q32 / xk / xv (FP32 rows) + x_first for the per-query extra key."""
     n = len(groups)
@@ -271,9 +281,10 @@ def attention_tc(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs:
         s.xk, s.xv, s.ldx = _vp(g.get("xk")), _vp(g.get("xv")), _vld(g.get("xk"))
         s.x_first = g.get("x_first", 0)
         s.out, s.ldo = _vp(g["out"]), _vld(g["out"])
-    lib = A.load()
+    lib = A.load(op_dtype)
     with _Span("attention_tc", 4.0 * n * nb * nh * Tq * Tk * hs, n * nb * nh * hs * (Tq * 8 + Tk * 8), f"{n}x[{nb},{nh},{Tq},{Tk},{hs}]"):
-        A.check(lib.unav_attention_tc(arr, n, nb, Tq, Tk, nh, hs, scale, op_dtype, _stream()), "unav_attention_tc")
+        A.check(lib.unav_attention_tc(arr, n, nb, Tq, Tk, nh, hs, scale, with_passes(op_dtype, passes), _stream()),
+                "unav_attention_tc")
 
 
 def maxsig_gate(x, G, head_bias, gate, nb: int, T: int, nwords: int, H: int, hc: int) -> None:
@@ -284,12 +295,12 @@ def maxsig_gate(x, G, head_bias, gate, nb: int, T: int, nwords: int, H: int, hc:
 
 
 def maxsig_gate_tc(x_buf, x_col0: int, G_buf, g_col0: int, head_bias, gate, nb: int, T: int, nwords: int, H: int, hc: int,
-                   op_dtype: int) -> None:
+                   op_dtype: int, passes: int = 0) -> None:
     """tcgen05 MaxSigmoid gate: x_buf / G_buf are whole operand buffers, x_col0 / g_col0 the first column of the window."""
-    lib = A.load()
+    lib = A.load(op_dtype)
     with _Span("maxsig_gate_tc", 2.0 * nb * T * nwords * H * hc, nb * (T + nwords) * H * hc * 4, f"[{nb},{T},{nwords},{H}x{hc}]"):
         A.check(lib.unav_maxsig_gate_tc(_p(x_buf), _ld(x_buf), x_col0, _p(G_buf), _ld(G_buf), g_col0, _p(head_bias), _p(gate),
-                                        nb, T, nwords, H, hc, op_dtype, _stream()), "unav_maxsig_gate_tc")
+                                        nb, T, nwords, H, hc, with_passes(op_dtype, passes), _stream()), "unav_maxsig_gate_tc")
 
 
 def pool_match(u0, u1, u2, T0: int, T1: int, T2: int, Wm, bm, q, nb: int, C_: int, Tq: int, P: int = 4) -> None:
@@ -313,15 +324,15 @@ def rowcopy(jobs: Sequence[dict], op_dtype: int) -> None:
         s.ntaps = j.get("ntaps", 1)
         s.tap_stride = j.get("tap_stride", j["C"])
         s.C = j["C"]
-    lib = A.load()
-    es = 4 if op_dtype in (F32, BF16X2) else 2
+    lib = A.load(op_dtype)
+    es = 4 if op_dtype in (F32, BF16X2, F16X2) else 2
     nbytes = sum(j["nseg"] * j["seg_len_out"] * j.get("ntaps", 1) * j["C"] * (4 + es) for j in jobs)
     with _Span("rowcopy", 0, nbytes, f"{n} jobs"):
         A.check(lib.unav_rowcopy(arr, n, op_dtype, _stream()), "unav_rowcopy")
 
 
 def transpose_cast(inp, ld_in: int, out, nb: int, R: int, Cc: int, op_dtype: int) -> None:
-    lib = A.load()
+    lib = A.load(op_dtype)
     with _Span("transpose_cast", 0, nb * R * Cc * 8, f"[{nb},{R},{Cc}]"):
         A.check(lib.unav_transpose_cast(_vp(inp), ld_in, _vp(out), _vld(out), nb, R, Cc, op_dtype, _stream()),
                 "unav_transpose_cast")
@@ -373,4 +384,4 @@ def softnms_batched(cand_segs, cand_scores, cand_labels, B: int, cap: int, ncls:
 
 
 def launch_count() -> int:
-    return int(A.load().unav_launch_count())
+    return sum(int(lib.unav_launch_count()) for lib in A.loaded())
