@@ -80,20 +80,21 @@ def _tc_inputs(cuda, q, k, v, op):
 
 
 def _rt(x, op):
-    hi = x.to(torch.bfloat16).float()
-    return hi + ((x - hi).to(torch.bfloat16).float() if op == K.BF16X2 else 0)
+    dt = K.OP_TORCH_DTYPE[op]
+    hi = x.to(dt).float()
+    return hi + ((x - hi).to(dt).float() if op in K.SPLIT_DTYPES else 0)
 
 
 def _read(buf, C, op):
     v = buf[:, :C].float()
-    if op == K.BF16X2:
+    if op in K.SPLIT_DTYPES:
         v = v + buf[:, buf.shape[1] // 2: buf.shape[1] // 2 + C].float()
     return v.cpu()
 
 
 @pytest.mark.parametrize("nb,T,nh,hs", [(3, 224, 4, 128), (2, 224, 4, 64), (2, 112, 4, 64), (3, 56, 4, 64), (2, 28, 4, 64),
                                          (5, 14, 4, 64), (5, 7, 4, 64), (2, 200, 2, 128)])
-@pytest.mark.parametrize("op,tol", [(K.BF16X2, 4e-5), (K.BF16, 2e-2)])
+@pytest.mark.parametrize("op,tol", [(K.BF16X2, 4e-5), (K.BF16, 2e-2), (K.F16X2, 4e-5), (K.F16, 3e-3)])
 def test_tc_attention(cuda, nb, T, nh, hs, op, tol):
     g = torch.Generator().manual_seed(T + hs)
     C = nh * hs

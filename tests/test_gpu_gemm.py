@@ -46,10 +46,11 @@ def _run(cuda, M, N, Kd, op, backend, act=K.ACT_NONE, full_epi=False, groups=1, 
             colscale = torch.rand(N, generator=g) + 0.5
         Aop = K.pack_operand(A.to(cuda), op)
         Wop = K.pack_operand(W.to(cuda), op)
-        if op != K.F32:   # the reference sees what the kernel sees: BF16(-split) rounded operands
+        if op != K.F32:   # the reference sees what the kernel sees: 16-bit(-split) rounded operands
+            dt = K.OP_TORCH_DTYPE[op]
             def rt(x):
-                hi = x.to(torch.bfloat16).float()
-                return hi + ((x - hi).to(torch.bfloat16).float() if op == K.BF16X2 else 0)
+                hi = x.to(dt).float()
+                return hi + ((x - hi).to(dt).float() if op in K.SPLIT_DTYPES else 0)
             A, W = rt(A), rt(W)
         out = torch.full((M, N), float("nan"), device=cuda)
         out_op = K.new_operand(M, N, op, cuda)
@@ -65,7 +66,7 @@ def _run(cuda, M, N, Kd, op, backend, act=K.ACT_NONE, full_epi=False, groups=1, 
     for (out, out_op), ref in zip(outs, refs):
         scale = ref.abs().max().item() + 1e-6
         # BF16X2 on tcgen05 drops the lo.lo term (3 of 4 partial products): ~2^-17 relative per product
-        tol = 6e-5 if (op == K.BF16X2 and backend == K.GEMM_TCGEN05) else 2e-5
+        tol = 6e-5 if (op == K.BF16X2 and backend == K.GEMM_TCGEN05) else 2e-5     # F16X2: lo.lo is ~2^-22, negligible
         err = (out.cpu() - ref).abs().max().item() / scale
         assert err < tol, f"out_f32 err {err}"
         if op == K.F32:
@@ -73,9 +74,9 @@ def _run(cuda, M, N, Kd, op, backend, act=K.ACT_NONE, full_epi=False, groups=1, 
         else:
             half = out_op.shape[1] // 2
             got = out_op[:, :N].float().cpu()
-            if op == K.BF16X2:
+            if op in K.SPLIT_DTYPES:
                 got = got + out_op[:, half:half + N].float().cpu()
-        tol_op = (6e-5 if backend == K.GEMM_TCGEN05 else 1e-5) if op != K.BF16 else 5e-3
+        tol_op = {K.BF16: 5e-3, K.F16: 6e-4}.get(op, 6e-5 if backend == K.GEMM_TCGEN05 else 1e-5)
         assert (got - ref).abs().max().item() / scale < tol_op
 
 
@@ -89,14 +90,49 @@ def test_simt_fp32(cuda, M, N, Kd):
 
 
 @pytest.mark.parametrize("M,N,Kd", SHAPES)
-@pytest.mark.parametrize("op", [K.BF16, K.BF16X2])
+@pytest.mark.parametrize("op", [K.BF16, K.BF16X2, K.F16, K.F16X2])
 def test_tcgen05_matches_reference(cuda, M, N, Kd, op):
+    """F16 / F16X2 run from libunav_b200_f16.so (the FP16-halves build of the same kernels)."""
     _run(cuda, M, N, Kd, op, K.GEMM_TCGEN05)
+
+
+@pytest.mark.parametrize("op", [K.BF16X2, K.F16X2])
+@pytest.mark.parametrize("M,N,Kd", [(300, 256, 512), (3584, 512, 1536), (77, 40, 72)])
+def test_tcgen05_single_pass_on_split_operands(cuda, op, M, N, Kd):
+    """passes=1 on split operands = the product of the hi halves only (what the `fast` mode runs in the Alignment and
+    backbone stages), bit-identical to a plain 16-bit GEMM on the same hi halves; the operand output is still split."""
+    g = torch.Generator().manual_seed(3)
+    A, W = torch.randn(M, Kd, generator=g), torch.randn(N, Kd, generator=g) / Kd ** 0.5
+    plain = K.BF16 if op == K.BF16X2 else K.F16
+    o1, o2 = torch.empty(M, N, device=cuda), torch.empty(M, N, device=cuda)
+    oop = K.new_operand(M, N, op, cuda)
+    K.gemm([{"A": K.pack_operand(A.to(cuda), op), "W": K.pack_operand(W.to(cuda), op), "out_f32": o1, "out_op": oop}],
+           M, N, Kd, op, K.ACT_NONE, False, K.GEMM_TCGEN05, passes=1)
+    K.gemm([{"A": K.pack_operand(A.to(cuda), plain), "W": K.pack_operand(W.to(cuda), plain), "out_f32": o2}],
+           M, N, Kd, plain, K.ACT_NONE, False, K.GEMM_TCGEN05)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2)
+    half = oop.shape[1] // 2
+    back = oop[:, :N].float() + oop[:, half:half + N].float()
+    assert (back - o1).abs().max().item() <= 6e-5 * o1.abs().max().item()
+
+
+def test_library_rejects_the_other_builds_dtypes(cuda):
+    """Each build serves only its own half type: the BF16 library must refuse F16 operands instead of misreading them."""
+    from unav_yolyolva_b200 import _cabi
+    A = K.pack_operand(torch.randn(128, 64).to(cuda), K.BF16)
+    out = torch.empty(128, 128, device=cuda)
+    arr = (_cabi.GemmGroup * 1)()
+    arr[0].A, arr[0].lda, arr[0].W, arr[0].ldw = A.data_ptr(), A.stride(0), A.data_ptr(), A.stride(0)
+    arr[0].out_f32, arr[0].ld_f32 = out.data_ptr(), 128
+    rc = _cabi.load().unav_gemm(arr, 1, 128, 128, 64, K.F16, 0, 0, K.GEMM_TCGEN05, None)
+    assert rc != 0 and b"does not belong to this build" in _cabi.load().unav_last_error()
 
 
 @pytest.mark.parametrize("act", [K.ACT_NONE, K.ACT_RELU, K.ACT_GELU, K.ACT_SILU])
 def test_tcgen05_full_epilogue(cuda, act):
     _run(cuda, 300, 256, 512, K.BF16X2, K.GEMM_TCGEN05, act=act, full_epi=True)
+    _run(cuda, 300, 256, 512, K.F16X2, K.GEMM_TCGEN05, act=act, full_epi=True)
     _run(cuda, 300, 200, 512, K.BF16, K.GEMM_TCGEN05, act=act, full_epi=True)
 
 
