@@ -117,6 +117,27 @@ def test_tcgen05_single_pass_on_split_operands(cuda, op, M, N, Kd):
     assert (back - o1).abs().max().item() <= 6e-5 * o1.abs().max().item()
 
 
+@pytest.mark.parametrize("op", [K.BF16X2, K.BF16, K.F16X2])
+@pytest.mark.parametrize("M,N,Kd,groups", [(256, 512, 512, 1), (3584, 512, 1536, 1), (1000, 256, 768, 2), (7056, 1024, 352, 1)])
+def test_tcgen05_cta_pair_kernel(cuda, monkeypatch, op, M, N, Kd, groups):
+    """cta_group::2 kernel (256 x 256 tile per CTA pair): forced on for shapes the heuristic would not give it, ragged M
+    (the second CTA of the last pair partly / wholly out of range), grouped launches, full epilogue; and the SAME bits
+    as the one-CTA kernel (one canonical accumulation order)."""
+    monkeypatch.setenv("UNAV_TC_PAIR", "1")
+    _run(cuda, M, N, Kd, op, K.GEMM_TCGEN05, full_epi=True, act=K.ACT_SILU, groups=groups)
+    g = torch.Generator().manual_seed(9)
+    A, W = torch.randn(M, Kd, generator=g), torch.randn(N, Kd, generator=g) / Kd ** 0.5
+    Aop, Wop = K.pack_operand(A.to(cuda), op), K.pack_operand(W.to(cuda), op)
+    outs = []
+    for pair in ("1", "0"):
+        monkeypatch.setenv("UNAV_TC_PAIR", pair)
+        o = torch.empty(M, N, device=cuda)
+        K.gemm([{"A": Aop, "W": Wop, "out_f32": o}], M, N, Kd, op, K.ACT_NONE, False, K.GEMM_TCGEN05)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_library_rejects_the_other_builds_dtypes(cuda):
     """Each build serves only its own half type: the BF16 library must refuse F16 operands instead of misreading them."""
     from unav_yolyolva_b200 import _cabi

@@ -188,6 +188,153 @@ __device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const flo
   }
 }
 
+// Epilogue of one 128 x BN accumulator tile (TMEM columns [tmem_cols, tmem_cols + BN) of this CTA), executed by the 8
+// epilogue warps (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
+// Phase A: tcgen05.ld (one accumulator row per thread) -> padded FP32 staging tile in the (now idle) pipeline smem;
+// phase B: each warp walks its 32 rows x BN/2 columns with lanes across columns, so residual loads and all stores are
+// row-contiguous 128-bit accesses.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& g, uint32_t tmem_cols, int m0, int n0,
+                                              int warp, int lane, float* stg_base) {
+  constexpr int PITCH = BN + 4;              // floats; 16-byte groups of consecutive rows fall in distinct banks
+  constexpr int HALF = BN / 2;               // columns per warp
+  constexpr int LPR = HALF / 4;              // lanes per row in phase B (16 | 8)
+  constexpr int RPP = 32 / LPR;              // rows per pass (2 | 4)
+  const int q = warp & 3, half = (warp - 2) >> 2;
+  const uint32_t tmem_base = tmem_cols;
+  float* stg = stg_base + q * 32 * PITCH + half * HALF;
+#pragma unroll 1
+  for (int c = 0; c < HALF / 32; ++c) {
+    uint32_t r[32];
+    tc_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * HALF + c * 32, r);
+    tc_wait_ld();
+    float* dst = stg + lane * PITCH + c * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+  }
+  __syncwarp();
+  const EpiParams& e = g.epi;
+  const int cl = lane % LPR, rsub = lane / LPR;
+  const int n = n0 + half * HALF + cl * 4;
+  const int nvalid = min(4, p.N - n);        // <= 0: this lane's columns are past N
+  const long long op_split = e.ld_op / 2;
+  const bool has_res = e.res != nullptr, has_gate = e.gate != nullptr;
+  const int act = p.act;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < nvalid) {
+      if (e.bias) bias[i] = __ldg(e.bias + n + i);
+      if (e.colscale) cs[i] = __ldg(e.colscale + n + i);
+    }
+  }
+  const bool vec_f32 = nvalid == 4 && e.out_f32 && ((reinterpret_cast<uintptr_t>(e.out_f32 + n) & 15) == 0) && (e.ld_f32 % 4 == 0);
+  const bool vec_res = nvalid == 4 && has_res && ((reinterpret_cast<uintptr_t>(e.res + n) & 15) == 0) && (e.ldres % 4 == 0);
+  const bool vec_op = nvalid == 4 && e.out_op && (((reinterpret_cast<uintptr_t>(e.out_op) + static_cast<size_t>(n) * 2) & 7) == 0) &&
+                      (e.ld_op % 4 == 0) && (op_split % 4 == 0);
+  if (e.out_opT) {
+    // transposed operand output (V^T for the tensor-core attention): lanes run along the token axis, so each
+    // store instruction writes 32 consecutive keys of one channel row
+    const long long mt = static_cast<long long>(m0) + q * 32 + lane;
+    if (mt < p.M) {
+      const int ncols = e.t_ncols > 0 ? e.t_ncols : p.N;
+      const long long item = mt / e.t_seg, t = mt % e.t_seg;
+      const long long spl = e.ld_opT / 2;
+      for (int j = 0; j < HALF; ++j) {
+        const int nn = n0 + half * HALF + j;
+        const int nc = nn - e.t_col0;
+        if (nn < p.N && nc >= 0 && nc < ncols) {
+          float x = stg[lane * PITCH + j];
+          if (e.bias) x += __ldg(e.bias + nn);
+          char* row = reinterpret_cast<char*>(e.out_opT) + static_cast<size_t>(item * ncols + nc) * e.ld_opT * 2;
+          store_op(row, p.op_dtype, t, spl, x);
+        }
+      }
+    }
+  }
+  // CTA-uniform test for the specialised row loop: full-width tile and every vector access 16-byte aligned
+  const bool fast = (n0 + BN <= p.N) && (!e.out_f32 || (((reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0) && e.ld_f32 % 4 == 0)) &&
+                    (!has_res || (((reinterpret_cast<uintptr_t>(e.res) & 15) == 0) && e.ldres % 4 == 0)) &&
+                    (!e.out_op || (((reinterpret_cast<uintptr_t>(e.out_op) & 7) == 0) && e.ld_op % 4 == 0 && op_split % 4 == 0)) &&
+                    (!has_gate || e.gate_width % 4 == 0);
+  if (fast && (e.out_f32 || e.out_op)) {
+    const long long m_base = static_cast<long long>(m0) + q * 32;
+    const int rows = static_cast<int>(min(32ll, static_cast<long long>(p.M) - m_base));
+    const float* sl = stg + cl * 4;
+    const bool split = op_is_split(p.op_dtype);
+    constexpr bool f16 = kHalfF16;
+#define UNAV_EPI_CASE(A)                                                                                          \
+    case A:                                                                                                       \
+      if (split) epilogue_rows_fast<A, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);   \
+      else epilogue_rows_fast<A, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);        \
+      break;
+    switch (act) {
+      UNAV_EPI_CASE(UNAV_ACT_RELU)
+      UNAV_EPI_CASE(UNAV_ACT_GELU)
+      UNAV_EPI_CASE(UNAV_ACT_SILU)
+      default:
+        if (split) epilogue_rows_fast<UNAV_ACT_NONE, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);
+        else epilogue_rows_fast<UNAV_ACT_NONE, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);
+    }
+#undef UNAV_EPI_CASE
+  } else if (nvalid > 0 && (e.out_f32 || e.out_op)) {
+#pragma unroll 2
+    for (int r = rsub; r < 32; r += RPP) {
+      const long long m = static_cast<long long>(m0) + q * 32 + r;
+      if (m >= p.M) break;
+      const float4 a4 = *reinterpret_cast<const float4*>(stg + r * PITCH + cl * 4);
+      float v[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float mk = e.rowmask ? (e.rowmask[m] ? 1.f : 0.f) : 1.f;
+      const float rs = e.rowscale ? __ldg(e.rowscale + m) : 1.f;
+      const float mrs = mk * rs;
+      float rr[4] = {0.f, 0.f, 0.f, 0.f};
+      if (has_res) {
+        const float* rp = e.res + m * e.ldres + n;
+        if (vec_res) {
+          const float4 t = *reinterpret_cast<const float4*>(rp);
+          rr[0] = t.x; rr[1] = t.y; rr[2] = t.z; rr[3] = t.w;
+        } else {
+          for (int i = 0; i < nvalid; ++i) rr[i] = rp[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (v[i] + bias[i]) * mrs;
+      if (has_gate) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nvalid) v[i] *= __ldg(e.gate + m * e.gate_groups + (n + i) / e.gate_width);
+      }
+      if (act != UNAV_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], act);
+      }
+      if (has_res) {
+        const float rm = p.res_masked ? mk : 1.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = rr[i] * rm + cs[i] * v[i];
+      }
+      if (e.out_f32) {
+        float* o = e.out_f32 + m * e.ld_f32 + n;
+        if (vec_f32) {
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          for (int i = 0; i < nvalid; ++i) o[i] = v[i];
+        }
+      }
+      if (e.out_op) {
+        char* row = reinterpret_cast<char*>(e.out_op) + static_cast<size_t>(m) * e.ld_op * 2;
+        if (vec_op) {
+          store_op4(row, p.op_dtype, n, op_split, make_float4(v[0], v[1], v[2], v[3]));
+        } else {
+          for (int i = 0; i < nvalid; ++i) store_op(row, p.op_dtype, n + i, op_split, v[i]);
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
@@ -312,150 +459,11 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
     }
     __syncwarp();     // same for the MMA issuer's warp
   } else {
-    // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
-    // Phase A: tcgen05.ld (one accumulator row per thread) -> padded FP32 staging tile in the (now idle)
-    //          pipeline smem; phase B: each warp walks its 32 rows x BN/2 columns with lanes across columns, so
-    //          residual loads and all stores are row-contiguous 128-bit accesses.  Eight warps (two per
-    //          scheduler) and two rows in flight per lane hide the ALU / memory latency of the epilogue math.
-    constexpr int PITCH = BN + 4;              // floats; 16-byte groups of consecutive rows fall in distinct banks
-    constexpr int HALF = BN / 2;               // columns per warp
-    constexpr int LPR = HALF / 4;              // lanes per row in phase B (16 | 8)
-    constexpr int RPP = 32 / LPR;              // rows per pass (2 | 4)
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    // ===== epilogue: warps 2..9 =====
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (ph_out && threadIdx.x == 64) ph_out[5] = clock_stamp();       // accumulator ready
-    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * 32 * PITCH + half * HALF;
-#pragma unroll 1
-    for (int c = 0; c < HALF / 32; ++c) {
-      uint32_t r[32];
-      tc_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * HALF + c * 32, r);
-      tc_wait_ld();
-      float* dst = stg + lane * PITCH + c * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-    }
-    __syncwarp();
-    const EpiParams& e = g.epi;
-    const int cl = lane % LPR, rsub = lane / LPR;
-    const int n = n0 + half * HALF + cl * 4;
-    const int nvalid = min(4, p.N - n);        // <= 0: this lane's columns are past N
-    const long long op_split = e.ld_op / 2;
-    const bool has_res = e.res != nullptr, has_gate = e.gate != nullptr;
-    const int act = p.act;
-    float bias[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (i < nvalid) {
-        if (e.bias) bias[i] = __ldg(e.bias + n + i);
-        if (e.colscale) cs[i] = __ldg(e.colscale + n + i);
-      }
-    }
-    const bool vec_f32 = nvalid == 4 && e.out_f32 && ((reinterpret_cast<uintptr_t>(e.out_f32 + n) & 15) == 0) && (e.ld_f32 % 4 == 0);
-    const bool vec_res = nvalid == 4 && has_res && ((reinterpret_cast<uintptr_t>(e.res + n) & 15) == 0) && (e.ldres % 4 == 0);
-    const bool vec_op = nvalid == 4 && e.out_op && (((reinterpret_cast<uintptr_t>(e.out_op) + static_cast<size_t>(n) * 2) & 7) == 0) &&
-                        (e.ld_op % 4 == 0) && (op_split % 4 == 0);
-    if (e.out_opT) {
-      // transposed operand output (V^T for the tensor-core attention): lanes run along the token axis, so each
-      // store instruction writes 32 consecutive keys of one channel row
-      const long long mt = static_cast<long long>(m0) + q * 32 + lane;
-      if (mt < p.M) {
-        const int ncols = e.t_ncols > 0 ? e.t_ncols : p.N;
-        const long long item = mt / e.t_seg, t = mt % e.t_seg;
-        const long long spl = e.ld_opT / 2;
-        for (int j = 0; j < HALF; ++j) {
-          const int nn = n0 + half * HALF + j;
-          const int nc = nn - e.t_col0;
-          if (nn < p.N && nc >= 0 && nc < ncols) {
-            float x = stg[lane * PITCH + j];
-            if (e.bias) x += __ldg(e.bias + nn);
-            char* row = reinterpret_cast<char*>(e.out_opT) + static_cast<size_t>(item * ncols + nc) * e.ld_opT * 2;
-            store_op(row, p.op_dtype, t, spl, x);
-          }
-        }
-      }
-    }
-    // CTA-uniform test for the specialised row loop: full-width tile and every vector access 16-byte aligned
-    const bool fast = (n0 + BN <= p.N) && (!e.out_f32 || (((reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0) && e.ld_f32 % 4 == 0)) &&
-                      (!has_res || (((reinterpret_cast<uintptr_t>(e.res) & 15) == 0) && e.ldres % 4 == 0)) &&
-                      (!e.out_op || (((reinterpret_cast<uintptr_t>(e.out_op) & 7) == 0) && e.ld_op % 4 == 0 && op_split % 4 == 0)) &&
-                      (!has_gate || e.gate_width % 4 == 0);
-    if (fast && (e.out_f32 || e.out_op)) {
-      const long long m_base = static_cast<long long>(m0) + q * 32;
-      const int rows = static_cast<int>(min(32ll, static_cast<long long>(p.M) - m_base));
-      const float* sl = stg + cl * 4;
-      const bool split = op_is_split(p.op_dtype);
-      constexpr bool f16 = kHalfF16;
-#define UNAV_EPI_CASE(A)                                                                                          \
-      case A:                                                                                                       \
-        if (split) epilogue_rows_fast<A, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);   \
-        else epilogue_rows_fast<A, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);        \
-        break;
-      switch (act) {
-        UNAV_EPI_CASE(UNAV_ACT_RELU)
-        UNAV_EPI_CASE(UNAV_ACT_GELU)
-        UNAV_EPI_CASE(UNAV_ACT_SILU)
-        default:
-          if (split) epilogue_rows_fast<UNAV_ACT_NONE, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);
-          else epilogue_rows_fast<UNAV_ACT_NONE, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);
-      }
-#undef UNAV_EPI_CASE
-    } else if (nvalid > 0 && (e.out_f32 || e.out_op)) {
-#pragma unroll 2
-      for (int r = rsub; r < 32; r += RPP) {
-        const long long m = static_cast<long long>(m0) + q * 32 + r;
-        if (m >= p.M) break;
-        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * PITCH + cl * 4);
-        float v[4] = {a4.x, a4.y, a4.z, a4.w};
-        const float mk = e.rowmask ? (e.rowmask[m] ? 1.f : 0.f) : 1.f;
-        const float rs = e.rowscale ? __ldg(e.rowscale + m) : 1.f;
-        const float mrs = mk * rs;
-        float rr[4] = {0.f, 0.f, 0.f, 0.f};
-        if (has_res) {
-          const float* rp = e.res + m * e.ldres + n;
-          if (vec_res) {
-            const float4 t = *reinterpret_cast<const float4*>(rp);
-            rr[0] = t.x; rr[1] = t.y; rr[2] = t.z; rr[3] = t.w;
-          } else {
-            for (int i = 0; i < nvalid; ++i) rr[i] = rp[i];
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = (v[i] + bias[i]) * mrs;
-        if (has_gate) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < nvalid) v[i] *= __ldg(e.gate + m * e.gate_groups + (n + i) / e.gate_width);
-        }
-        if (act != UNAV_ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], act);
-        }
-        if (has_res) {
-          const float rm = p.res_masked ? mk : 1.f;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = rr[i] * rm + cs[i] * v[i];
-        }
-        if (e.out_f32) {
-          float* o = e.out_f32 + m * e.ld_f32 + n;
-          if (vec_f32) {
-            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-            for (int i = 0; i < nvalid; ++i) o[i] = v[i];
-          }
-        }
-        if (e.out_op) {
-          char* row = reinterpret_cast<char*>(e.out_op) + static_cast<size_t>(m) * e.ld_op * 2;
-          if (vec_op) {
-            store_op4(row, p.op_dtype, n, op_split, make_float4(v[0], v[1], v[2], v[3]));
-          } else {
-            for (int i = 0; i < nvalid; ++i) store_op(row, p.op_dtype, n + i, op_split, v[i]);
-          }
-        }
-      }
-    }
+    epilogue_tile<BN>(p, g, tmem_base, m0, n0, warp, lane, reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))));
   }
   if (ph_out && threadIdx.x == 64) ph_out[6] = clock_stamp();         // this warp's epilogue done
   tc_fence_before();
@@ -464,6 +472,158 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// =============================================================================================
+// CTA-pair variant (cta_group::2): a cluster of two CTAs computes a 256 x 256 tile.  Rank r owns rows
+// [256*pair + 128*r, +128) of A and rows [n0 + 128*r, +128) of W; `tcgen05.mma.cta_group::2` (M = 256, N = 256), issued by
+// rank 0 only, reads A from each CTA's own shared memory and each half of B once for both tensor cores, so a CTA
+// stages 32 KB per 32-wide k-step for 128 x 256 outputs: half the shared-memory traffic per FLOP of the 128 x 128
+// kernel above, which is what bounds its k-loop.  Each CTA keeps its 128 x 256 FP32 accumulator in
+// its own TMEM (256 columns, two CTAs per SM still fit) and runs the same row epilogue on two 128-column halves.
+// Barrier protocol: both producers signal rank 0's full[s] (rank 0 expects the bytes of both CTAs, rank 1 adds a
+// remote arrival; TMA completions are routed to rank 0's barrier), the MMA commit is multicast to empty[s] / accum
+// of both CTAs.
+// =============================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
+// TMA load whose completion bytes are credited to the barrier at the same offset in cluster rank 0
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+constexpr int P2_BK = 32;
+constexpr int P2_PART = 128 * P2_BK * 2;     // one 128-row operand part of a stage: 8 KB
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 2)
+gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const TcGroup& g = p.g[blockIdx.z];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int NS = p.stages;
+  const int nparts = p.nseg > 1 ? 2 : 1;
+  const uint32_t stage_bytes = 2u * nparts * P2_PART;                 // [A parts | W parts]
+  const uint32_t w_off = nparts * P2_PART;
+  const uint32_t bar_base = base + stage_bytes * NS;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * TC_MAX_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 1);
+
+  const int m0 = (blockIdx.x >> 1) * 256 + static_cast<int>(rank) * 128;      // this CTA's accumulator rows
+  const int n0 = blockIdx.y * 256;                                            // the pair's columns
+  const int wn0 = n0 + static_cast<int>(rank) * 128;                          // this CTA's half of W
+  const int nkb = (p.K + P2_BK - 1) / P2_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&g.tmA[0]);
+    tma_prefetch_desc(&g.tmW[0]);
+    if (p.nseg > 1) { tma_prefetch_desc(&g.tmA[1]); tma_prefetch_desc(&g.tmW[1]); }
+    for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrival / multicast commit
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs) =====
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % NS;
+        const uint32_t ph = (it / NS) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (rank == 0) mbar_expect_tx(full_bar(s), 2u * stage_bytes);       // bytes of both CTAs land on this barrier
+        else mbar_arrive_remote(full_bar(s), 0);
+        const uint32_t sa = base + s * stage_bytes;
+        for (int pt = 0; pt < nparts; ++pt) {
+          tma_load_2d_pair(sa + pt * P2_PART, &g.tmA[pt], full_bar(s), it * P2_BK, m0);
+          tma_load_2d_pair(sa + w_off + pt * P2_PART, &g.tmW[pt], full_bar(s), it * P2_BK, wn0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (rank 0 only) =====
+      const uint32_t idesc = make_idesc(256, 256, kHalfF16);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % NS;
+        const uint32_t ph = (it / NS) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * stage_bytes;
+        // same canonical order as the 1-CTA kernel: per 32-wide k-step hi.hi, lo.hi, hi.lo
+#pragma unroll
+        for (int seg = 0; seg < 3; ++seg) {
+          if (seg >= p.nseg) break;
+          const uint64_t adesc = make_smem_desc<P2_BK>(sa + (seg == 1 ? P2_PART : 0));
+          const uint64_t bdesc = make_smem_desc<P2_BK>(sa + w_off + (seg == 2 ? P2_PART : 0));
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            tc_mma_f16_pair(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || seg > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit_pair(empty_bar(s));
+      }
+      tc_commit_pair(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue (both CTAs): two 128-column halves of this CTA's 128 x 256 accumulator =====
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)));
+    for (int hf = 0; hf < 2; ++hf) {
+      if (n0 + hf * 128 >= p.N) break;
+      epilogue_tile<128>(p, g, tmem_base + hf * 128, m0, n0 + hf * 128, warp, lane, stg);
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();            // the peer may still read this CTA's smem / signal its barriers until both are done
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
   }
 }
 
@@ -580,6 +740,46 @@ static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
   return finish_launch("gemm_tcgen05");
 }
 
+static int launch_pair(TcParams& p, int ngroups, cudaStream_t stream) {
+  static bool attr_set = false;
+  constexpr int MAX_SMEM = 110 * 1024;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm_tcgen05_pair): %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  const int nparts = p.nseg > 1 ? 2 : 1;
+  const int per_stage = 2 * nparts * P2_PART;
+  const int nkb = (p.K + P2_BK - 1) / P2_BK;
+  int stages = (100 * 1024) / per_stage;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages > nkb) stages = nkb;
+  if (stages < 2) stages = 2;
+  while (stages * per_stage < 128 * (128 + 4) * 4) ++stages;      // room for the epilogue staging tile
+  p.stages = stages;
+  p.once = p.nseg > 1 ? 1 : 0;
+  dim3 grid(2 * ((p.M + 255) / 256), (p.N + 255) / 256, ngroups);
+  launch_pdl(gemm_tcgen05_pair_kernel, dim3(grid), dim3(TC_THREADS), stages * per_stage + 256 + 1024, stream, p);
+  count_launch();
+  return finish_launch("gemm_tcgen05_pair");
+}
+
+// CTA pairs where they pay (scripts/gemm_probe.py, UNAV_TC_PAIR=0/1): grids of at least two 128 x 128 CTAs per SM with a
+// long k-loop — [7056,1024,3072] 134 -> 108 us (410 TFLOP/s algorithmic, 1230 executed), 2x[7056,512,1536] 77 -> 65 us.  The
+// K = 512 shapes are epilogue-bound and gain nothing; grids of ~1.5 CTAs per SM lose the second resident CTA's overlap.
+static bool use_pair(int M, int N, int K, int ngroups) {
+  int v = -1;
+  if (const char* env = getenv("UNAV_TC_PAIR")) v = atoi(env);       // experiment knob: 0 never, 1 whenever possible
+  if (N % 256 != 0 || M < 256) return false;
+  if (v == 0) return false;
+  if (v == 1) return true;
+  const long long tiles128 = static_cast<long long>((M + 127) / 128) * (N / 128) * ngroups;
+  return tiles128 >= 296 && K >= 1024;
+}
+
 int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, int op_arg, int act,
                  int res_masked, cudaStream_t stream) {
   const int op_dtype = op_base(op_arg);
@@ -588,8 +788,9 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
   p.M = M; p.N = N; p.K = K; p.op_dtype = op_dtype; p.act = act; p.res_masked = res_masked;
   p.nseg = op_passes(op_arg);       // 1 pass on split operands reads the hi halves only
   p.phase = g_phase_buf; p.phase_cap = g_phase_cap;
+  const bool pair = use_pair(M, N, K, ngroups);
   const TcChoice ch = choose_tile(M, N, K, ngroups, p.nseg);
-  const int bn = ch.bn, bk = ch.sched == 2 ? 32 : 64;
+  const int bn = pair ? 128 : ch.bn, bk = pair ? P2_BK : (ch.sched == 2 ? 32 : 64);
   p.once = ch.sched ? 1 : 0;
   for (int i = 0; i < ngroups; ++i) {
     const UnavGemmGroup& g = groups[i];
@@ -613,6 +814,7 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
     }
     p.g[i].epi = make_epi(g);
   }
+  if (pair) return launch_pair(p, ngroups, stream);
   if (bk == 32) return bn == 64 ? launch_tc<64, 32>(p, ngroups, stream) : launch_tc<128, 32>(p, ngroups, stream);
   return bn == 64 ? launch_tc<64, 64>(p, ngroups, stream) : launch_tc<128, 64>(p, ngroups, stream);
 }
