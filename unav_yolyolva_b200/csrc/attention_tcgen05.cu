@@ -39,9 +39,9 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x10000u) : "memory");      // suspend hint: park instead of polling
   return ok;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -141,26 +141,45 @@ struct AttnTcParams {
 constexpr int ATC_THREADS = 320;     // TMA warp, MMA warp, 8 softmax / epilogue warps (two per TMEM lane quarter)
 
 // p = exp(s*scale - max) for N (16 | 32) consecutive keys held in r[], packed to BF16 hi (+ lo) words; returns their sum
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sc2 = scale * log2(e), mx2 = max * log2(e): p = 2^(s*sc2 - mx2) is one FFMA + one MUFU per key; packed 2-wide
+// conversions (F2FP) — the scalar F2F conversions of an earlier version ran at MUFU rate and dominated the softmax.
 template <int N, bool F16>
-__device__ __forceinline__ float softmax_chunk_t(const uint32_t* r, uint32_t m, float sc, float mx, bool split,
+__device__ __forceinline__ float softmax_chunk_t(const uint32_t* r, uint32_t m, float sc2, float mx2, bool split,
                                                  uint32_t* hi, uint32_t* lo) {
-  constexpr bool f16 = F16;
-  float l = 0.f;
+  float l0 = 0.f, l1 = 0.f;
 #pragma unroll
   for (int j = 0; j < N; j += 2) {
-    const float p0 = ((m >> j) & 1u) ? __expf(__uint_as_float(r[j]) * sc - mx) : 0.f;
-    const float p1 = ((m >> (j + 1)) & 1u) ? __expf(__uint_as_float(r[j + 1]) * sc - mx) : 0.f;
-    const uint16_t h0 = f2h16(p0, f16), h1 = f2h16(p1, f16);
-    const float f0 = h162f(h0, f16), f1 = h162f(h1, f16);
-    if (split) {
-      lo[j / 2] = pack2_h16(p0 - f0, p1 - f1, f16);
-      l += p0 + p1;                                         // hi + lo carries (almost) the full FP32 value
+    const float p0 = ((m >> j) & 1u) ? ex2_ftz(fmaf(__uint_as_float(r[j]), sc2, -mx2)) : 0.f;
+    const float p1 = ((m >> (j + 1)) & 1u) ? ex2_ftz(fmaf(__uint_as_float(r[j + 1]), sc2, -mx2)) : 0.f;
+    float f0, f1;
+    if (F16) {
+      const __half2 h2 = __floats2half2_rn(p0, p1);
+      hi[j / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+      const float2 hf = __half22float2(h2);
+      f0 = hf.x; f1 = hf.y;
+      if (split) {
+        const __half2 l2 = __floats2half2_rn(p0 - f0, p1 - f1);
+        lo[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
     } else {
-      l += f0 + f1;                                         // normalise by what the MMA will actually sum
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+      hi[j / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+      const float2 hf = __bfloat1622float2(h2);
+      f0 = hf.x; f1 = hf.y;
+      if (split) {
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(p0 - f0, p1 - f1);
+        lo[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
     }
-    hi[j / 2] = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
+    if (split) { l0 += p0; l1 += p1; }          // hi + lo carries (almost) the full FP32 value
+    else { l0 += f0; l1 += f1; }                // normalise by what the MMA will actually sum
   }
-  return l;
+  return l0 + l1;
 }
 template <int N>
 __device__ __forceinline__ float softmax_chunk(const uint32_t* r, uint32_t m, float sc, float mx, bool split, bool f16,
@@ -303,48 +322,56 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
     mbar_wait(bar_s, 0);
     tc_fence_after();
     if (ph_out && threadIdx.x == 64) ph_out[3] = clock_stamp();
-    // ---- pass 1: raw row max over this thread's valid keys (scale > 0, so max(s*scale) = max(s)*scale exactly)
+    // ---- this thread's S columns (<= 128 of them) are read from TMEM ONCE into registers: all loads in flight, one
+    //      wait (the two-pass version re-read S for the exponentials and waited per 16-column chunk)
+    uint32_t r[4][32];
+    uint32_t mk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c_lo + 32 * k;
+      mk[k] = 0;
+      if (c < c_hi) {
+        mk[k] = __funnelshift_r(maskw[c >> 5], maskw[(c >> 5) + 1], c & 31);
+        if (c + 32 <= c_hi) {
+          ld32(tm_s + lane_addr + c, r[k]);
+        } else {
+          ld16(tm_s + lane_addr + c, r[k]);
+          mk[k] &= 0xffffu;
+        }
+      }
+    }
+    wait_ld();
+    // ---- raw row max over the valid keys (scale > 0, so max(s*scale) = max(s)*scale exactly)
     float mraw = -CUDART_INF_F;
-#pragma unroll 1
-    for (int c = c_lo; c < c_hi; c += 32) {
-      const uint32_t m = __funnelshift_r(maskw[c >> 5], maskw[(c >> 5) + 1], c & 31);
-      uint32_t r[32];
-      if (c + 32 <= c_hi) {
-        ld32(tm_s + lane_addr + c, r);
-        wait_ld();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c_lo + 32 * k < c_hi) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if ((m >> j) & 1u) mraw = fmaxf(mraw, __uint_as_float(r[j]));
-      } else {
-        ld16(tm_s + lane_addr + c, r);
-        wait_ld();
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if ((m >> j) & 1u) mraw = fmaxf(mraw, __uint_as_float(r[j]));
+          if ((mk[k] >> j) & 1u) mraw = fmaxf(mraw, __uint_as_float(r[k][j]));
       }
     }
     xch[half * 128 + row] = mraw;
     asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
     float mx = fmaxf(s_x, fmaxf(xch[row], xch[128 + row]) * sc);
     if (mx == -CUDART_INF_F) mx = 0.f;         // fully masked row: all probabilities are 0 (0/0 = NaN as in the reference)
-    // ---- pass 2: p = exp(s*scale - max), row sum, P -> TMEM as packed BF16 (hi, lo)
+    // ---- p = exp(s*scale - max), row sum, P -> TMEM as packed 16-bit (hi, lo)
+    const float sc2 = sc * 1.4426950408889634f, mx2 = mx * 1.4426950408889634f;
     float l = 0.f;
-#pragma unroll 1
-    for (int c = c_lo; c < c_hi; c += 32) {
-      const uint32_t m = __funnelshift_r(maskw[c >> 5], maskw[(c >> 5) + 1], c & 31);
-      uint32_t r[32], hi[16], lo[16];
-      if (c + 32 <= c_hi) {
-        ld32(tm_s + lane_addr + c, r);
-        wait_ld();
-        l += softmax_chunk<32>(r, m, sc, mx, split, f16, hi, lo);
-        st16(tm_p + lane_addr + c / 2, hi);
-        if (split) st16(tm_p + lane_addr + Tkp / 2 + c / 2, lo);
-      } else {
-        ld16(tm_s + lane_addr + c, r);
-        wait_ld();
-        l += softmax_chunk<16>(r, m, sc, mx, split, f16, hi, lo);
-        st8(tm_p + lane_addr + c / 2, hi);
-        if (split) st8(tm_p + lane_addr + Tkp / 2 + c / 2, lo);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c_lo + 32 * k;
+      if (c < c_hi) {
+        uint32_t hi[16], lo[16];
+        if (c + 32 <= c_hi) {
+          l += softmax_chunk<32>(r[k], mk[k], sc2, mx2, split, f16, hi, lo);
+          st16(tm_p + lane_addr + c / 2, hi);
+          if (split) st16(tm_p + lane_addr + Tkp / 2 + c / 2, lo);
+        } else {
+          l += softmax_chunk<16>(r[k], mk[k], sc2, mx2, split, f16, hi, lo);
+          st8(tm_p + lane_addr + c / 2, hi);
+          if (split) st8(tm_p + lane_addr + Tkp / 2 + c / 2, lo);
+        }
       }
     }
     wait_st();
@@ -356,7 +383,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
     asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
     l = xch[256 + row] + xch[384 + row];
     float p_x = 0.f;
-    if (has_x) { p_x = __expf(s_x - mx); l += p_x; }
+    if (has_x) { p_x = ex2_ftz(s_x * 1.4426950408889634f - mx2); l += p_x; }
     // ---- epilogue: O / l (+ extra key's value), operand-dtype store; the two threads of a row split the head columns
     mbar_wait(bar_o, 0);
     tc_fence_after();
