@@ -32,6 +32,7 @@
  *   unav_transpose_cast    the [B,C,T] <-> [B,T,C] transposes (multimodal_backbones.py:1145-1146,
  *                          :1200-1201, :170)
  *   unav_align_embed       multimodal_backbones.py:1157-1166 (CLS + pos + type embedding)
+ *   unav_collate_pad       libs/datasets/data_utils.py:178-205 (padding + mask of collate_fcn, on the device)
  *   unav_build_masks       blocks.py:45-51 (mask[::s]) and multimodal_backbones.py:568-570
  *
  * Conventions
@@ -253,6 +254,13 @@ int unav_transpose_cast(const float* in, long long ld_in, void* out, long long l
 int unav_align_embed(const float* x0, const float* cls_v, const float* cls_a,
                      const float* pos_v, const float* pos_a, const float* type_v,
                      const float* type_a, float* tokens, int nb, int T, int C, void* stream);
+
+/* Device-side collate (what libs/datasets/data_utils.py:178-205 does on the host with per-video copy_ loops):
+ * ragged = the B videos' [C, lens[b]] row-major feature blocks back to back, offsets[b] = index of the first float of
+ * video b.  out[b, c, t] = t < min(lens[b], T) ? ragged[offsets[b] + c*lens[b] + t] : pad  ([B, C, T], the model's
+ * input layout); mask (optional) [B, T] = t < lens[b]  (data_utils.py:201: arange(max_len) < feats_lens). */
+int unav_collate_pad(const float* ragged, const long long* offsets, const int* lens, float* out,
+                     uint8_t* mask, int B, int C, int T, float pad, void* stream);
 
 /* Pyramid masks from the level-0 mask [nb_src, T] replicated to nb = k*nb_src batch items (item b uses
  * mask[b % nb_src]):  out_true[l][b][t] = mask[b][t << l]  (blocks.py:45-51),

@@ -77,3 +77,63 @@ def test_submit_result_matches_forward_and_pipelines():
     for j, (g, w) in enumerate(zip(got, want)):
         for k in ("segments", "scores", "labels"):
             assert g[k].device.type == "cpu" and torch.equal(g[k], w[k]), (j, k)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# device-side collate
+def test_device_collate_matches_reference_golden(golden_dir):
+    """unav_collate_pad through DeviceCollator vs what the reference's collate_fcn produced (bit-exact)."""
+    import os
+    import numpy as np
+    from unav_yolyolva_b200.ingest import DeviceCollator
+    d = np.load(os.path.join(golden_dir, "collate_b3.npz"))
+    n = len(d["lens"])
+    items = [{"video_id": f"v{i}", "feats": {"visual": torch.from_numpy(d[f"visual_{i}"]), "audio": torch.from_numpy(d[f"audio_{i}"])},
+              "fps": 25.0, "duration": 1.0, "feat_stride": 8, "feat_num_frames": 24} for i in range(n)]
+    out = DeviceCollator(int(d["max_seq_len"]), "cuda:0")(items)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["visual"].cpu().numpy(), d["visual"])
+    assert np.array_equal(out["audio"].cpu().numpy(), d["audio"])
+    assert out["mask"].dtype == torch.bool and np.array_equal(out["mask"].cpu().numpy(), d["mask"])
+    assert out["video_id"] == ["v0", "v1", "v2"]
+
+
+def test_device_collate_full_size_and_model_parity():
+    """Ragged items of the full-size synthetic videos: padded batch identical to the host collate (synth.make_batch),
+    through the prefetcher with ragged batch sizes, and identical detections from the model."""
+    from oracle import collate_ref
+    from unav_yolyolva_b200.ingest import DeviceCollator
+    dev = torch.device("cuda", 0)
+    model = make_multimodal_meta_arch("LocPointTransformer", **default_model_cfg())
+    model.load_state_dict(synth.trained_like_state_dict(), strict=True)
+    model = model.to(dev).eval()
+    sizes, first = [4, 4, 3, 4], 0
+    lists, batches = [], []
+    for n in sizes:
+        lists.append(synth.make_items(n, first))
+        batches.append(synth.make_batch(n, 224, first_index=first, with_gt=False))
+        first += n
+    want = []
+    for b in batches:
+        res, _ = model(b)
+        want.append({k: res[k].cpu() for k in ("segments", "scores", "labels")})
+    coll = DeviceCollator(224, dev)
+    for j, got in enumerate(CudaPrefetcher(iter(lists), dev, collate=coll)):
+        ref_v, ref_m = collate_ref.collate_pad([x["feats"]["visual"].numpy() for x in lists[j]], 224)
+        assert torch.equal(got["visual"].cpu(), torch.from_numpy(ref_v)) and torch.equal(got["visual"].cpu(), batches[j]["visual"])
+        assert torch.equal(got["audio"].cpu(), batches[j]["audio"])
+        assert torch.equal(got["mask"].cpu(), batches[j]["mask"]) and torch.equal(got["mask"].cpu(), torch.from_numpy(ref_m))
+        assert got["duration"] == batches[j]["duration"] and got["video_id"] == batches[j]["video_id"]
+        res, _ = model(got)
+        for k in ("segments", "scores", "labels"):
+            assert torch.equal(res[k].cpu(), want[j][k]), (j, k)
+
+
+def test_device_collate_rejects_cpu_and_mismatched_lengths():
+    from unav_yolyolva_b200.ingest import DeviceCollator
+    with pytest.raises(RuntimeError):
+        DeviceCollator(224, "cpu")
+    it = synth.make_items(2, 0)
+    it[1]["feats"]["audio"] = it[1]["feats"]["audio"][:, :-1]
+    with pytest.raises(ValueError):
+        DeviceCollator(224, "cuda:0")(it)

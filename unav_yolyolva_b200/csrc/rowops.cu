@@ -390,6 +390,29 @@ __global__ void build_masks_kernel(const uint8_t* __restrict__ mask, uint8_t* ou
 }
 
 // =============================================================================================
+// device-side collate: ragged per-video features -> padded batch + validity mask
+// =============================================================================================
+// ragged = the videos' [C, len_b] row-major feature blocks back to back (offsets[b] = first float of video b).
+__global__ void __launch_bounds__(256)
+collate_pad_kernel(const float* __restrict__ ragged, const long long* __restrict__ offsets, const int* __restrict__ lens,
+                   float* __restrict__ out, uint8_t* __restrict__ mask, int C, int T, float pad) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.y;
+  const int len = min(lens[b], T);
+  const float* src = ragged + offsets[b];
+  float* dst = out + static_cast<long long>(b) * C * T;
+  const long long n = static_cast<long long>(C) * T;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i / T), t = static_cast<int>(i % T);
+    dst[i] = t < len ? src[static_cast<long long>(c) * lens[b] + t] : pad;
+  }
+  if (mask && blockIdx.x == 0)
+    for (int t = threadIdx.x; t < T; t += blockDim.x) mask[static_cast<long long>(b) * T + t] = t < len ? 1 : 0;
+}
+
+// =============================================================================================
 // adaptive avg-pool (P bins) of three levels + match projection
 // =============================================================================================
 __global__ void __launch_bounds__(128)
@@ -626,4 +649,17 @@ extern "C" int unav_maxsig_gate(const float* x, long long ldx, const float* G, l
   launch_pdl(maxsig_kernel, dim3(grid), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), x, ldx, G, ldg, head_bias, gate, T, nwords, H, hc);
   count_launch();
   return finish_launch("maxsig_gate");
+}
+
+extern "C" int unav_collate_pad(const float* ragged, const long long* offsets, const int* lens, float* out,
+                                uint8_t* mask, int B, int C, int T, float pad, void* stream) {
+  UNAV_REQUIRE(ragged && offsets && lens && out && B > 0 && C > 0 && T > 0, "collate_pad: bad arguments");
+  const long long n = static_cast<long long>(C) * T;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dim3 grid(static_cast<unsigned>(blocks), B);
+  launch_pdl(collate_pad_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), ragged, offsets, lens, out,
+             mask, C, T, pad);
+  count_launch();
+  return finish_launch("collate_pad");
 }

@@ -14,9 +14,11 @@ The yielded tensors alias the slots: they stay valid until ``depth - 1`` further
 """
 from __future__ import annotations
 
-from typing import Iterable, Iterator, Optional
+from typing import Iterable, Iterator, List, Optional
 
 import torch
+
+from . import kernels as K
 
 _TENSOR_KEYS = ("visual", "audio", "mask")
 
@@ -30,7 +32,9 @@ class CudaPrefetcher:
     of batch j+depth waits, on the copy stream, for everything the consumer enqueued for batch j.
     """
 
-    def __init__(self, batches: Iterable[dict], device, keys=_TENSOR_KEYS, depth: int = 2):
+    def __init__(self, batches: Iterable, device, keys=_TENSOR_KEYS, depth: int = 2, collate: "Optional[DeviceCollator]" = None):
+        """batches: collate dicts — or, with ``collate=DeviceCollator(...)``, the raw per-batch lists of dataset items
+        (a DataLoader built with ``collate_fn=lambda items: items``), which are then padded on the device."""
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("CudaPrefetcher needs a CUDA device")
@@ -39,6 +43,9 @@ class CudaPrefetcher:
         self.it: Iterator[dict] = iter(batches)
         self.keys = keys
         self.depth = depth
+        self.collate = collate
+        if collate is not None and collate.slots < depth:
+            raise ValueError("the DeviceCollator needs at least as many slots as the prefetcher's depth")
         self.stream = torch.cuda.Stream(self.device)
         self._slots = [dict() for _ in range(depth)]          # slot -> {key: device tensor}
         self._free = [None] * depth                            # slot -> event: consumer done with the slot
@@ -61,6 +68,15 @@ class CudaPrefetcher:
             return
         slot = self._n % self.depth
         self._n += 1
+        if self.collate is not None:
+            with torch.cuda.stream(self.stream):
+                if self._free[slot] is not None:
+                    self.stream.wait_event(self._free[slot])
+                out = self.collate.enqueue(batch, slot)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            self._ready = (out, ev, slot)
+            return
         out = dict(batch)
         # device buffers are created on the consumer's stream (plain allocations, made once per shape)
         dst = {}
@@ -97,3 +113,95 @@ class CudaPrefetcher:
         cur.wait_event(ev)                       # compute stream waits for this batch's upload only
         self._preload()                          # start uploading the next batch while this one computes
         return batch
+
+
+class DeviceCollator:
+    """``collate_fcn`` of the reference (/root/reference/libs/datasets/data_utils.py:123-229) for inference, with the
+    padding and the mask done on the device.
+
+    The reference pads every video to ``max_seq_len`` on the host (a Python loop of ``copy_`` per video, :178-198) and the
+    padded ``[B, 2048+128, T]`` batch then crosses PCIe.  Here only the valid frames do: the videos' ``[C, len]`` feature
+    blocks are packed back to back into one pinned staging buffer, uploaded with one copy, and ``unav_collate_pad`` writes
+    the padded ``visual`` / ``audio`` tensors and the ``mask`` (``arange(T) < len``, :201).  Output keys are the ones the
+    inference path reads (visual, audio, mask, video_id, fps, duration, feat_stride, feat_num_frames); the loss-only keys of
+    the reference's dict (scores, start_end, m_labels, gt_*, points) are not produced.
+
+    ``collator(items)`` enqueues on the current stream and returns device tensors that alias slot 0;
+    ``CudaPrefetcher(loader, device, collate=collator)`` runs it one batch ahead on the copy stream.
+    """
+
+    def __init__(self, max_seq_len: int, device, max_div_factor: int = 1, padding_val: float = 0.0, slots: int = 2):
+        self.T = int(max_seq_len)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DeviceCollator needs a CUDA device (no CPU fallback)")
+        self.max_div_factor = int(max_div_factor)
+        self.pad = float(padding_val)
+        self.slots = slots
+        self._host: List[Optional[torch.Tensor]] = [None] * slots       # pinned staging (floats + header)
+        self._dev: List[dict] = [dict() for _ in range(slots)]
+
+    def _buffers(self, slot: int, B: int, Cv: int, Ca: int, T: int, nfloat: int):
+        hdr = 4 * B                                                    # offsets (2 x i64 per video = 4 floats) per modality ...
+        need = nfloat + 2 * hdr + 2 * B                                # ... + lens (i32)
+        h = self._host[slot]
+        if h is None or h.numel() < need:
+            h = torch.empty(int(need * 1.25) + 1024, dtype=torch.float32).pin_memory()
+            self._host[slot] = h
+        d = self._dev[slot]
+        if d.get("key") != (B, Cv, Ca, T) or d["stage"].numel() < h.numel():
+            d.clear()
+            d["key"] = (B, Cv, Ca, T)
+            d["stage"] = torch.empty(h.numel(), dtype=torch.float32, device=self.device)
+            d["visual"] = torch.empty(B, Cv, T, dtype=torch.float32, device=self.device)
+            d["audio"] = torch.empty(B, Ca, T, dtype=torch.float32, device=self.device)
+            d["mask"] = torch.empty(B, 1, T, dtype=torch.uint8, device=self.device)
+        return h, d
+
+    def enqueue(self, video_list: List[dict], slot: int = 0) -> dict:
+        B = len(video_list)
+        vis = [x["feats"]["visual"] for x in video_list]
+        aud = [x["feats"]["audio"] for x in video_list]
+        lens = [int(v.shape[-1]) for v in vis]
+        Cv, Ca = int(vis[0].shape[0]), int(aud[0].shape[0])
+        max_len = max(lens)
+        if max_len <= self.T:                                          # data_utils.py:170-176 (eval branch)
+            T = self.T
+        else:
+            st = self.max_div_factor
+            T = (max_len + (st - 1)) // st * st
+        nfloat = sum(lens) * (Cv + Ca)
+        h, d = self._buffers(slot, B, Cv, Ca, T, nfloat)
+        # header: [offsets_v i64 x B | offsets_a i64 x B | lens i32 x B], then the feature blocks
+        hb = h.view(torch.uint8)
+        off_v = hb[0:8 * B].view(torch.int64)
+        off_a = hb[8 * B:16 * B].view(torch.int64)
+        ln = hb[16 * B:20 * B].view(torch.int32)
+        base = 5 * B + (-5 * B) % 4                                    # first payload float, 16-byte aligned
+        pos = base
+        for i, (v, L) in enumerate(zip(vis, lens)):
+            n = Cv * L
+            h[pos:pos + n].view(Cv, L).copy_(v)
+            off_v[i] = pos
+            pos += n
+        for i, (a, L) in enumerate(zip(aud, lens)):
+            if int(a.shape[-1]) != L:
+                raise ValueError("visual and audio features of a video must have the same length")
+            n = Ca * L
+            h[pos:pos + n].view(Ca, L).copy_(a)
+            off_a[i] = pos
+            ln[i] = L
+            pos += n
+        st = d["stage"]
+        st[:pos].copy_(h[:pos], non_blocking=True)
+        sb = st.view(torch.uint8)
+        d_off_v, d_off_a, d_ln = sb[0:8 * B].view(torch.int64), sb[8 * B:16 * B].view(torch.int64), sb[16 * B:20 * B].view(torch.int32)
+        mask_u8 = d["mask"].view(B, T)
+        K.collate_pad(st, d_off_v, d_ln, d["visual"], mask_u8, B, Cv, T, self.pad)
+        K.collate_pad(st, d_off_a, d_ln, d["audio"], None, B, Ca, T, self.pad)
+        return {"visual": d["visual"], "audio": d["audio"], "mask": d["mask"].view(torch.bool),
+                "video_id": [x["video_id"] for x in video_list], "fps": [x["fps"] for x in video_list],
+                "duration": [x["duration"] for x in video_list], "feat_stride": [x["feat_stride"] for x in video_list],
+                "feat_num_frames": [x["feat_num_frames"] for x in video_list]}
+
+    __call__ = enqueue

@@ -345,6 +345,14 @@ def align_embed(x0, cls_v, cls_a, pos_v, pos_a, type_v, type_a, tokens, nb: int,
                                      _p(tokens), nb, T, C_, _stream()), "unav_align_embed")
 
 
+def collate_pad(ragged, offsets, lens, out, mask, B: int, C_: int, T: int, pad: float = 0.0) -> None:
+    """ragged f32 (videos' [C, len] blocks back to back), offsets i64 [B], lens i32 [B] -> out [B, C, T] f32, mask [B, T] u8."""
+    lib = A.load()
+    with _Span("collate_pad", 0, B * C_ * T * 8):
+        A.check(lib.unav_collate_pad(_p(ragged), _p(offsets), _p(lens), _p(out), _p(mask), B, C_, T, pad, _stream()),
+                "unav_collate_pad")
+
+
 def build_masks(mask, out_true, out_up, out_cls, out_heads, nb: int, nb_src: int, T: int, L: int) -> None:
     lib = A.load()
     with _Span("build_masks", 0, nb * T * 4):

@@ -164,3 +164,19 @@ def make_batch(B: int, T: int = 224, first_index: int = 0, num_classes: int = 10
             "gt_cls_labels": torch.zeros(B, Ttot, num_classes),
         })
     return batch
+
+
+def make_items(B: int, first_index: int = 0, len_lo: int = 60, len_hi: int = 187) -> list:
+    """The same synthetic videos as ``make_batch`` as a list of un-collated dataset items (ragged features), the
+    input of the reference's ``collate_fcn`` (/root/reference/libs/datasets/data_utils.py:123) and of
+    ``ingest.DeviceCollator``.  Inference keys only."""
+    items = []
+    for i in range(B):
+        vid = first_index + i
+        g = torch.Generator().manual_seed(1234 + vid)
+        L = int(torch.randint(len_lo, len_hi + 1, (1,), generator=g).item())
+        vis = 0.3 * torch.randn(2048, L, generator=g).abs()
+        aud = 0.5 * torch.randn(128, L, generator=g).abs()
+        items.append({"video_id": f"synth_{vid:06d}", "feats": {"visual": vis, "audio": aud}, "fps": 25.0,
+                      "duration": (L * 8 + 24) / 25.0, "feat_stride": 8, "feat_num_frames": 24})
+    return items
