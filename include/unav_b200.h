@@ -32,6 +32,7 @@
  *   unav_transpose_cast    the [B,C,T] <-> [B,T,C] transposes (multimodal_backbones.py:1145-1146,
  *                          :1200-1201, :170)
  *   unav_align_embed       multimodal_backbones.py:1157-1166 (CLS + pos + type embedding)
+ *   unav_map_match         libs/utils/metrics.py:340-398 (greedy tIoU matching of compute_average_precision_detection)
  *   unav_collate_pad       libs/datasets/data_utils.py:178-205 (padding + mask of collate_fcn, on the device)
  *   unav_build_masks       blocks.py:45-51 (mask[::s]) and multimodal_backbones.py:568-570
  *
@@ -308,6 +309,15 @@ int unav_softnms_batched(const float* cand_segs, const float* cand_scores,
                          float* out_segs,
                          float* out_scores, int64_t* out_labels, int32_t* out_counts,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- detection mAP: greedy matching of ranked detections to ground truth ------------------------------------ */
+/* libs/utils/metrics.py:340-398 for every class, video and tIoU threshold at once.  Detections and ground truth are grouped
+ * by (class, video): group g owns detections det_ptr[g] .. det_ptr[g+1] (det_seg rows [start, end] in FP64, in the class's
+ * descending-score order) and ground-truth rows gt_ptr[2g] .. gt_ptr[2g+1] of gt_seg (original order; may be empty).
+ * tp[t*ndet + i] = 1 if detection i is a true positive at tious[t], else 0 (it is then a false positive).
+ * lock: workspace of nt*ngt bytes. */
+int unav_map_match(const double* det_seg, const double* gt_seg, const int* det_ptr, const int* gt_ptr, int ngroups,
+                   const double* tious, int nt, int ndet, int ngt, uint8_t* tp, uint8_t* lock, void* stream);
 
 #ifdef __cplusplus
 }

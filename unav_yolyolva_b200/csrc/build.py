@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["lib.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "rowops.cu", "attention.cu", "attention_tcgen05.cu", "decode_nms.cu"]
+SOURCES = ["lib.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "rowops.cu", "attention.cu", "attention_tcgen05.cu", "decode_nms.cu", "metrics.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "unav_b200.h")]
 OUT = os.path.join(HERE, "libunav_b200.so")               # BF16 halves
 OUT_F16 = os.path.join(HERE, "libunav_b200_f16.so")       # same sources, -DUNAV_HALF_F16 (FP16 halves)
