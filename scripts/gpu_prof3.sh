@@ -1,6 +1,6 @@
 # round-1 final profile set: launch list (durations), DRAM bytes of every GEMM launch, full capture of the heaviest GEMM
 mkdir -p gpurun_out
-REGEX='regex:^(gemm_|attention_|ln_rows|dwconv|rowcopy|maxsig|softnms|merge_|decode_|transpose_cast|align_embed|build_masks|pool_match)'
+REGEX='regex:^(gemm_|attention_|ln_rows|dwconv|rowcopy|maxsig|softnms|merge_|decode_|transpose_cast|align_embed|build_masks|pool_match|collate_pad|map_match)'
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $CMD --trace-out gpurun_out/trace.json > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$REGEX" -c 520 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu.log 2>&1

@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01b"
-CLS = {'gemm_tcgen05_kernel': 'gemm_tcgen05', 'gemm_tcgen05_2cta_kernel': 'gemm_tcgen05', 'gemm_simt_kernel': 'gemm_simt',
+CLS = {'gemm_tcgen05_kernel': 'gemm_tcgen05', 'gemm_tcgen05_pair_kernel': 'gemm_tcgen05', 'collate_pad_kernel': 'collate_pad', 'gemm_simt_kernel': 'gemm_simt',
        'dwconv_ln_kernel': 'dwconv_ln',
        'attention_tcgen05_kernel': 'attention_tc', 'attention_kernel': 'attention', 'softnms_lazy_kernel': 'softnms',
        'softnms_kernel': 'softnms', 'merge_kernel': 'softnms', 'ln_rows_kernel': 'layernorm_rows', 'rowcopy_kernel': 'rowcopy',
