@@ -148,16 +148,43 @@ dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
   const UnavDwLnOut& od = g.out[task ? o : 0];
   const bool has_pre = task && od.src >= 0;
   const bool has_ln = od.ln_w != nullptr;   // NULL: plain masked depthwise conv (MaskedConv1D with groups = C)
-  float4 d0[NV], d1[NV], d2[NV], lw[NV], lb[NV], nw[NV], nb[NV];
+  // NV == 2 (C <= 256) keeps them in registers; NV == 4 (C <= 512) would need 112 registers for them (154 in total, one
+  // CTA per SM, 12 waves on the [7168,512] launches), so there the CTA stages all its weights in shared memory instead.
+  constexpr bool WSM = NV == 4;
+  constexpr int NR = WSM ? 1 : NV;
+  float4 d0[NR], d1[NR], d2[NR], lw[NR], lb[NR], nw[NR], nb[NR];
+  float* wsm = st_rstd + n_in;                             // [n_out][dw 3C | ln_w C | ln_b C] then [2][pre_w C | pre_b C]
   float mk = 1.f;
   long long r = 0;
+  if (WSM) {
+    const int C4 = C / 4;
+    for (int oo = 0; oo < p.n_out; ++oo) {
+      const UnavDwLnOut& q = g.out[oo];
+      float4* dst = reinterpret_cast<float4*>(wsm + oo * 5 * C);
+      for (int i = threadIdx.x; i < 3 * C4; i += blockDim.x) dst[i] = reinterpret_cast<const float4*>(q.dw)[i];
+      if (q.ln_w)
+        for (int i = threadIdx.x; i < C4; i += blockDim.x) {
+          dst[3 * C4 + i] = reinterpret_cast<const float4*>(q.ln_w)[i];
+          dst[4 * C4 + i] = reinterpret_cast<const float4*>(q.ln_b)[i];
+        }
+    }
+    for (int sidx = 0; sidx < p.n_pre; ++sidx) {
+      float4* dst = reinterpret_cast<float4*>(wsm + p.n_out * 5 * C + sidx * 2 * C);
+      for (int i = threadIdx.x; i < C4; i += blockDim.x) {
+        dst[i] = reinterpret_cast<const float4*>(g.pre_w[sidx])[i];
+        dst[C4 + i] = reinterpret_cast<const float4*>(g.pre_b[sidx])[i];
+      }
+    }
+  }
   if (task) {
     r = static_cast<long long>(seg) * p.seg_len_out + t;
     mk = g.mask_out ? (g.mask_out[r] ? 1.f : 0.f) : 1.f;
+  }
+  if (task && !WSM) {
     const float* pw = has_pre ? g.pre_w[od.src] : nullptr;
     const float* pb = has_pre ? g.pre_b[od.src] : nullptr;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
+    for (int j = 0; j < NR; ++j) {
       const int c = (j * 32 + lane) * 4;
       if (c < C) {
         d0[j] = *reinterpret_cast<const float4*>(od.dw + c * 3);       // taps of 4 channels: 12 floats
@@ -216,16 +243,28 @@ dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
     const int c = (j * 32 + lane) * 4;
     z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < C) {
-      const float wt[4][3] = {{d0[j].x, d0[j].y, d0[j].z}, {d0[j].w, d1[j].x, d1[j].y}, {d1[j].z, d1[j].w, d2[j].x},
-                              {d2[j].y, d2[j].z, d2[j].w}};
+      const int jr = WSM ? 0 : j;
+      if (WSM) {
+        const float* wo = wsm + o * 5 * C;
+        d0[0] = *reinterpret_cast<const float4*>(wo + c * 3);
+        d1[0] = *reinterpret_cast<const float4*>(wo + c * 3 + 4);
+        d2[0] = *reinterpret_cast<const float4*>(wo + c * 3 + 8);
+        if (has_pre) {
+          const float* wp = wsm + p.n_out * 5 * C + od.src * 2 * C;
+          lw[0] = *reinterpret_cast<const float4*>(wp + c);
+          lb[0] = *reinterpret_cast<const float4*>(wp + C + c);
+        }
+      }
+      const float wt[4][3] = {{d0[jr].x, d0[jr].y, d0[jr].z}, {d0[jr].w, d1[jr].x, d1[jr].y}, {d1[jr].z, d1[jr].w, d2[jr].x},
+                              {d2[jr].y, d2[jr].z, d2[jr].w}};
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int tap = 0; tap < 3; ++tap) {
         if (!okt[tap]) continue;
         float4 u = *reinterpret_cast<const float4*>(xs + (i0 + tap) * C + c);
         if (has_pre) {
-          u.x = (u.x - tm[tap]) * tr[tap] * lw[j].x + lb[j].x; u.y = (u.y - tm[tap]) * tr[tap] * lw[j].y + lb[j].y;
-          u.z = (u.z - tm[tap]) * tr[tap] * lw[j].z + lb[j].z; u.w = (u.w - tm[tap]) * tr[tap] * lw[j].w + lb[j].w;
+          u.x = (u.x - tm[tap]) * tr[tap] * lw[jr].x + lb[jr].x; u.y = (u.y - tm[tap]) * tr[tap] * lw[jr].y + lb[jr].y;
+          u.z = (u.z - tm[tap]) * tr[tap] * lw[jr].z + lb[jr].z; u.w = (u.w - tm[tap]) * tr[tap] * lw[jr].w + lb[jr].w;
         }
         acc[0] = fmaf(wt[0][tap], u.x, acc[0]); acc[1] = fmaf(wt[1][tap], u.y, acc[1]);
         acc[2] = fmaf(wt[2][tap], u.z, acc[2]); acc[3] = fmaf(wt[3][tap], u.w, acc[3]);
@@ -252,8 +291,13 @@ dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
     if (c < C) {
       float4 y;
       if (has_ln) {
-        y.x = z[j].x * rs * nw[j].x + nb[j].x; y.y = z[j].y * rs * nw[j].y + nb[j].y;
-        y.z = z[j].z * rs * nw[j].z + nb[j].z; y.w = z[j].w * rs * nw[j].w + nb[j].w;
+        const int jr = WSM ? 0 : j;
+        if (WSM) {
+          nw[0] = *reinterpret_cast<const float4*>(wsm + o * 5 * C + 3 * C + c);
+          nb[0] = *reinterpret_cast<const float4*>(wsm + o * 5 * C + 4 * C + c);
+        }
+        y.x = z[j].x * rs * nw[jr].x + nb[jr].x; y.y = z[j].y * rs * nw[jr].y + nb[jr].y;
+        y.z = z[j].z * rs * nw[jr].z + nb[jr].z; y.w = z[j].w * rs * nw[jr].w + nb[jr].w;
       } else {
         y = make_float4(z[j].x + mu, z[j].y + mu, z[j].z + mu, z[j].w + mu);
       }
@@ -562,8 +606,15 @@ extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg
   const int R = narrow ? 8 : 4;
   const int tiles_per_seg = (p.seg_len_out + R - 1) / R;
   const int n_in = R * stride + 2;
-  const size_t smem = (static_cast<size_t>(n_in) * C + 2 * n_in) * sizeof(float);
+  size_t smem = (static_cast<size_t>(n_in) * C + 2 * n_in) * sizeof(float);
+  if (!narrow) smem += static_cast<size_t>(5 * n_out + 2 * n_pre) * C * sizeof(float);      // the CTA's weights
   const int nwarps = n_in > R * n_out ? n_in : R * n_out;     // one warp per staged row and per (row, output) pair
+  static size_t smem_set = 0;
+  if (!narrow && smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_ln_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) { set_error("dwconv_ln: smem %zu: %s", smem, cudaGetErrorString(e)); return static_cast<int>(e); }
+    smem_set = smem;
+  }
   dim3 grid(static_cast<unsigned>(nseg * tiles_per_seg), ngroups);
   if (narrow)
     launch_pdl(dwconv_ln_kernel<2>, dim3(grid), dim3(32 * nwarps), smem, reinterpret_cast<cudaStream_t>(stream), p);
