@@ -61,6 +61,8 @@ def masked_conv1d(sd: SD, p: str, x, mask, stride=1, groups=1):
         m = F.interpolate(mask.to(x.dtype), size=x.shape[-1] // stride, mode="nearest")
     else:
         m = mask.to(x.dtype)
+    if m.shape[-1] != out.shape[-1]:       # blocks.py:56-57: a per-sequence mask [B] (Dependency_Block's co-occurrence branch)
+        m = m[:, None, None]
     return out * m, m.bool()
 
 
@@ -89,8 +91,12 @@ def masked_mhca(sd: SD, p: str, x1, x2, mask, n_head: int):
     q = q.view(B, n_head, hs, -1).transpose(2, 3)
     v = v.view(B, n_head, hs, -1).transpose(2, 3)
     att = _r(q * (1.0 / math.sqrt(hs))) @ _rb(k).transpose(-2, -1)
-    att = att.masked_fill(torch.logical_not(km[:, :, None, :]), float("-inf"))
-    att = F.softmax(att, dim=-1)
+    if T == mask.shape[-1]:                # blocks.py:229-236
+        att = att.masked_fill(torch.logical_not(km[:, :, None, :]), float("-inf"))
+        att = F.softmax(att, dim=-1)
+    else:                                  # per-sequence mask: un-masked softmax, then the whole sequence is kept / zeroed
+        att = F.softmax(att, dim=-1)
+        att = att * km[:, :, :, None].to(att.dtype)
     out = _r(att) @ _rb(v * km[:, :, :, None].to(v.dtype))
     out = out.transpose(2, 3).contiguous().view(B, C, -1)
     out = _conv(out, sd[p + ".proj.weight"], sd[p + ".proj.bias"]) * qm.to(out.dtype)
@@ -109,6 +115,27 @@ def transformer_block(sd: SD, p: str, x1, x2, mask, n_head: int):
     h = _conv(h, sd[p + ".mlp.3.weight"], sd[p + ".mlp.3.bias"])
     out = out + sd[p + ".drop_path_mlp.scale"] * (h * mf)
     return out, om
+
+
+def dependency_block(sd: SD, p: str, fpn_feats, fpn_masks, num_classes: int, n_head: int = 1):
+    """libs/modeling/dependency_block.py:42-70 — per level: expand to H=128 channels per class, a temporal TransformerBlock
+    over [B*C, H, T] and a co-occurrence TransformerBlock over [B*T, H, C] (per-sequence mask), sum, squeeze back."""
+    outs = []
+    for feats, mask in zip(fpn_feats, fpn_masks):
+        fe, mask = masked_conv1d(sd, p + ".feature_expand", feats, mask)
+        fe = F.relu(fe).view(feats.shape[0], num_classes, -1, feats.shape[-1]).contiguous()
+        B, C, H, T = fe.shape
+        tf = fe.view(-1, H, T)
+        t_out, _ = transformer_block(sd, p + ".temporal_branch", tf, tf, mask.repeat(C, 1, 1), n_head)
+        t_out = t_out.view(B, C, H, T).contiguous()
+        cf = fe.transpose(1, 3).contiguous().view(-1, H, C)
+        c_out, _ = transformer_block(sd, p + ".cooccur_branch", cf, cf, mask.flatten(), n_head)
+        c_out = c_out.view(B, T, H, C).contiguous()
+        out = t_out + c_out.transpose(1, 3).contiguous()
+        out = out.view(out.shape[0], -1, out.shape[-1])
+        out, mask = masked_conv1d(sd, p + ".feature_squeeze", out, mask)
+        outs.append(out)
+    return outs
 
 
 # ------------------------------------------------------------- multimodal_backbones.py
@@ -307,7 +334,7 @@ def heads(sd: SD, feats_av: List[torch.Tensor], masks, num_classes=100):
     return logits, offsets
 
 
-def forward_logits(sd: SD, visual, audio, mask, pos_embd=None):
+def forward_logits(sd: SD, visual, audio, mask, pos_embd=None, use_dependency=False):
     """PtTransformer.forward up to the permuted head outputs (:426-493), losses skipped.
 
     Returns (logits per level [B,T_l,ncls], offsets per level [B,T_l,ncls,2], masks per level [B,T_l]).
@@ -319,6 +346,8 @@ def forward_logits(sd: SD, visual, audio, mask, pos_embd=None):
     v, a = alignment(sd, "alignment", visual, audio, mask)
     fv, fa, ms = backbone(sd, "backbone", v, a, mask)
     feats = [torch.cat((x, y), 1) for x, y in zip(fv, fa)]
+    if use_dependency:                         # multimodal_meta_archs.py:474-475
+        feats = dependency_block(sd, "dependency_block", feats, ms, sd["cls_head.cls_head.conv.bias"].shape[0])
     logits, offsets = heads(sd, feats, ms)
     return logits, offsets, [m.squeeze(1) for m in ms]
 

@@ -95,3 +95,34 @@ def test_config5_softnms_stress(cuda, path):
             assert np.array_equal(_bits(o_s[b].cpu().numpy()), _bits(r[0]))
     finally:
         os.environ.pop("UNAV_NMS_PER_CLASS", None)
+
+
+def test_use_dependency_variant_vs_oracle(cuda):
+    """The `use_dependency: True` variant of the model: Dependency_Block between the fusion
+    outputs and the heads.  Logits / offsets vs the oracle, B=2, T=224, all 6 levels."""
+    from oracle import model_ref as R
+    cfg = default_model_cfg()
+    cfg["use_dependency"] = True
+    model = make_multimodal_meta_arch("LocPointTransformer", **cfg)
+    sd = synth.trained_like_state_dict()
+    own = model.state_dict()
+    for k, v in own.items():
+        if k.startswith("dependency_block."):
+            sd[k] = synth.trained_like_tensor(k, list(v.shape))
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda).eval()
+    b = synth.make_batch(2, 224)
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    with torch.no_grad():
+        lg, of, _ = R.forward_logits(sd, b["visual"], b["audio"], b["mask"], use_dependency=True)
+    lg, of = torch.cat(lg, 1), torch.cat(of, 1)
+    plan = model.run_hot_path(b)
+    torch.cuda.synchronize()
+    g_lg = plan["logits"].cpu().view(2, 441, 100)
+    g_of = plan["offsets"].cpu().view(2, 441, 100, 2)
+    e1 = float((g_lg - lg).abs().max() / lg.abs().max())
+    e2 = float((g_of - of).abs().max() / of.abs().max())
+    print(f"[use_dependency, bf16x3] logits rel err {e1:.3e}, offsets rel err {e2:.3e}")
+    assert e1 < 5e-4 and e2 < 2e-3
+    res, _ = model(b)                       # and the full path to detections runs
+    assert res["segments"].shape == (2, 100, 2)

@@ -167,3 +167,33 @@ def test_alignment_and_backbone_modules(cuda):
         assert _close(fv[l], rfv[l], 2e-5) and _close(fa[l], rfa[l], 2e-5)
         assert torch.equal(ms[l].cpu(), rms[l])
     _fwd.MODE = "bf16x3"
+
+
+def test_dependency_block_matches_reference_golden(cuda, golden_dir):
+    """Dependency_Block through the module-level kernels vs the reference module's own output:
+    two pyramid levels, one padded video, the per-sequence-mask co-occurrence branch, the tiled temporal mask."""
+    import os
+    import numpy as np
+    from unav_yolyolva_b200 import synth
+    from unav_yolyolva_b200.modeling import make_dependency_block
+    d = np.load(os.path.join(golden_dir, "dependency_b2.npz"))
+    blk = make_dependency_block("DependencyBlock", in_channel=1024, n_embd=128, n_embd_ks=3, num_classes=100, path_pdrop=0.1)
+    sd = {k: synth.trained_like_tensor("dependency_block." + k, list(v.shape)) for k, v in blk.state_dict().items()}
+    assert sorted(sd) == [str(n) for n in d["names"]]
+    blk.load_state_dict(sd, strict=True)
+    blk = blk.to(cuda).eval()
+    g = torch.Generator().manual_seed(77)
+    T = 32
+    feats = [torch.randn(2, 1024, T, generator=g), torch.randn(2, 1024, T // 2, generator=g)]
+    m0 = torch.ones(2, 1, T, dtype=torch.bool)
+    m0[1, 0, 21:] = False
+    masks = [m0, m0[:, :, ::2]]
+    feats = [f * m for f, m in zip(feats, masks)]
+    with torch.no_grad():
+        outs, _ = blk([f.to(cuda) for f in feats], [m.to(cuda) for m in masks])
+    torch.cuda.synchronize()
+    for o, key in zip(outs, ("out0", "out1")):
+        ref = torch.from_numpy(d[key])
+        err = float((o.cpu() - ref).abs().max() / ref.abs().max())
+        print(f"dependency block {key}: rel err {err:.3e}")
+        assert err < 2e-4

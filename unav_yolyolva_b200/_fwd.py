@@ -119,9 +119,10 @@ def ln_rows(norm, x_rows, act=K.ACT_NONE):
     return out
 
 
-def mhca_rows(mod, x1_rows, x2_rows, m_u8, B, T, pre=None, **proj_epi):
+def mhca_rows(mod, x1_rows, x2_rows, m_u8, B, T, pre=None, key_mask=True, **proj_epi):
     """MaskedMHCA (blocks.py:198-245) on rows.  pre = ((ln11_w, ln11_b), (ln12_w, ln12_b)) fuses the TransformerBlock
-    input LayerNorms (blocks.py:314)."""
+    input LayerNorms (blocks.py:314).  key_mask=False: the per-sequence-mask branch (blocks.py:233-236) — every key of a
+    kept sequence takes part in the softmax; masked sequences are zeroed by the row masks."""
     assert mod.n_qx_stride == 1 and mod.n_kv_stride == 1, "strided MaskedMHCA is not on the hot path"
     op, backend = _op()
     C, nh = mod.n_embd, mod.n_head
@@ -147,12 +148,23 @@ def mhca_rows(mod, x1_rows, x2_rows, m_u8, B, T, pre=None, **proj_epi):
             gkv["pre"], gq["pre"] = [pre[0]], [pre[1]]
         K.dwconv_ln([gkv], B, T, 1, C, op)
         K.dwconv_ln([gq], B, T, 1, C, op)
-    qp, kp, vp = (torch.empty(M, C, dtype=torch.float32, device=dev) for _ in range(3))
-    K.gemm([{"A": a, "W": _packed(lin.weight, "lin"), "bias": _vec(lin.bias), "out_f32": o}
-            for a, lin, o in ((qi, mod.query, qp), (ki, mod.key, kp), (vi, mod.value, vp))], M, C, C, op, K.ACT_NONE, False, backend)
     ao = K.new_operand(M, C, op, dev)
     hs = C // nh
-    K.attention([{"q": qp, "k": kp, "v": vp, "kmask": m_u8, "out": ao}], B, T, T, nh, hs, 1.0 / math.sqrt(hs), op)
+    km = m_u8 if key_mask else None
+    lins = (mod.query, mod.key, mod.value)
+    if backend == K.GEMM_TCGEN05 and T <= 256 and hs in (64, 128):
+        # tensor-core attention: q, k as operand rows, values written transposed per item by the GEMM epilogue
+        qo, ko = K.new_operand(M, C, op, dev), K.new_operand(M, C, op, dev)
+        vt = K.new_operand(B * C, T, op, dev)
+        outs = ({"out_op": qo}, {"out_op": ko}, {"out_opT": vt, "t_seg": T})
+        K.gemm([dict({"A": a, "W": _packed(lin.weight, "lin"), "bias": _vec(lin.bias)}, **o)
+                for a, lin, o in zip((qi, ki, vi), lins, outs)], M, C, C, op, K.ACT_NONE, False, backend)
+        K.attention_tc([{"q": qo, "k": ko, "vt": vt, "kmask": km, "out": ao}], B, T, T, nh, hs, 1.0 / math.sqrt(hs), op)
+    else:
+        qp, kp, vp = (torch.empty(M, C, dtype=torch.float32, device=dev) for _ in range(3))
+        K.gemm([{"A": a, "W": _packed(lin.weight, "lin"), "bias": _vec(lin.bias), "out_f32": o}
+                for a, lin, o in zip((qi, ki, vi), lins, (qp, kp, vp))], M, C, C, op, K.ACT_NONE, False, backend)
+        K.attention([{"q": qp, "k": kp, "v": vp, "kmask": km, "out": ao}], B, T, T, nh, hs, 1.0 / math.sqrt(hs), op)
     return _gemm(ao, _packed(mod.proj.weight, "lin"), M, C, C, bias=_vec(mod.proj.bias), rowmask=m_u8, **proj_epi)
 
 
@@ -192,13 +204,14 @@ def transformer_block(mod, x1, x2, mask, pos_embd=None):
     op, backend = _op()
     B, C, T = x1.shape
     M = B * T
-    m = mask_rows(mask)
+    seq_mask = mask.shape[-1] != T            # a per-sequence mask [B] (blocks.py:56-57, :233-236): Dependency_Block
+    m = (mask.reshape(B, 1).expand(B, T).to(torch.uint8).contiguous().reshape(-1) if seq_mask else mask_rows(mask))
     r1 = to_rows(x1)
     r2 = r1 if x2 is x1 else to_rows(x2)
     sa = _vec(mod.drop_path_attn.scale) if hasattr(mod.drop_path_attn, "scale") else None
     sm = _vec(mod.drop_path_mlp.scale) if hasattr(mod.drop_path_mlp, "scale") else None
     pre = ((_vec(mod.ln11.weight), _vec(mod.ln11.bias)), (_vec(mod.ln12.weight), _vec(mod.ln12.bias)))
-    o1 = mhca_rows(mod.attn, r1, r2, m, B, T, pre=pre, res=r1, colscale=sa, res_masked=True)
+    o1 = mhca_rows(mod.attn, r1, r2, m, B, T, pre=pre, key_mask=not seq_mask, res=r1, colscale=sa, res_masked=True)
     hn = K.new_operand(M, C, op, x1.device)
     K.layernorm_rows([{"x": o1, "w": _vec(mod.ln2.weight), "b": _vec(mod.ln2.bias), "out_op": hn}], M, C, op)
     fc1, fc2 = mod.mlp[0], mod.mlp[3]
@@ -206,7 +219,34 @@ def transformer_block(mod, x1, x2, mask, pos_embd=None):
     hm = K.new_operand(M, H, op, x1.device)
     K.gemm([{"A": hn, "W": _packed(fc1.weight, "lin"), "bias": _vec(fc1.bias), "out_op": hm}], M, H, C, op, K.ACT_GELU, False, backend)
     out = _gemm(hm, _packed(fc2.weight, "lin"), M, fc2.weight.shape[0], H, bias=_vec(fc2.bias), rowmask=m, res=o1, colscale=sm)
-    return from_rows(out, B, T), mask.bool()
+    return from_rows(out, B, T), (mask.reshape(B, 1, 1) if seq_mask else mask).bool()
+
+
+def dependency_block_forward(mod, fpn_feats, fpn_masks):
+    """dependency_block.py:42-70.  Per pyramid level: feature_expand (k=3 conv 2C -> 128*num_classes, ReLU fused in the
+    GEMM epilogue: relu(conv*mask) = relu(conv)*mask), a temporal TransformerBlock over [B*classes, 128, T], a
+    co-occurrence TransformerBlock over [B*T, 128, classes] with the per-sequence mask, sum, feature_squeeze.  The
+    reshapes / transposes between the three views are the reference's own (torch views and copies); the mask of the
+    temporal branch is `mask.repeat(C, 1, 1)` exactly as the reference builds it (:51)."""
+    assert len(fpn_feats) == len(fpn_masks)
+    outs = []
+    for feats, mask in zip(fpn_feats, fpn_masks):
+        _need_cuda(feats)
+        B, Cin, T = feats.shape
+        C = mod.num_classes
+        m_u8 = mask_rows(mask)
+        fe_rows = conv_rows(mod.feature_expand.conv, to_rows(feats), B, T, m_u8, act=K.ACT_RELU)     # [B*T, C*H]
+        H = fe_rows.shape[1] // C
+        fe = from_rows(fe_rows, B, T).view(B, C, H, T)
+        tf = fe.view(B * C, H, T)
+        t_out, _ = transformer_block(mod.temporal_branch, tf, tf, mask.repeat(C, 1, 1))
+        cf = fe.transpose(1, 3).contiguous().view(B * T, H, C)
+        c_out, _ = transformer_block(mod.cooccur_branch, cf, cf, mask.flatten())
+        out = t_out.view(B, C, H, T) + c_out.view(B, T, H, C).transpose(1, 3)
+        out = out.reshape(B, C * H, T)
+        sq = conv_rows(mod.feature_squeeze.conv, to_rows(out), B, T, m_u8)
+        outs.append(from_rows(sq, B, T))
+    return tuple(outs), fpn_masks
 
 
 # ------------------------------------------------------------------------------ multimodal_backbones.py

@@ -52,7 +52,7 @@ class HotPathEngine:
             raise ValueError(f"unknown precision mode {mode!r}; choose from {sorted(MODES)}")
         self.mode = mode
         self.op, self.backend = MODES[mode]
-        self.use_graph = use_graph
+        self.use_graph = use_graph and not getattr(model, "use_dependency", False)   # the Dependency_Block path is eager
         self.nms_stream = None          # side stream of the streaming mode (run(..., overlap_nms=True))
         self.model = model
         dev = next(model.parameters()).device
@@ -342,6 +342,35 @@ class HotPathEngine:
         self._launch_nms(P, P["vid_meta"])
 
     def _launch_forward(self, P):
+        self._launch_trunk(P)
+        if self.model.use_dependency:
+            self._launch_dependency(P)
+        self._launch_heads(P)
+
+    def _launch_dependency(self, P):
+        """Dependency_Block between the fusion outputs and the heads (multimodal_meta_archs.py:474-475), through the
+        module-level kernels (``_fwd.dependency_block_forward``; eager, not graph-captured).  The block's outputs replace
+        the fusion outputs in place, in the same [visual rows | audio rows] split the heads' gather reads."""
+        from . import _fwd
+        B, C, L, Tl = P["B"], self.C, self.L, self.Tl
+        o = P["o_final"]
+        feats, masks = [], []
+        for l in range(L):
+            n = B * Tl[l]
+            feats.append(_fwd.from_rows(torch.cat((o[l][:n], o[l][n:2 * n]), dim=1), B, Tl[l]))       # cat(V, A) (:469)
+            masks.append(self._mask(P, l)[:n].view(B, 1, Tl[l]).bool())
+        prev, _fwd.MODE = _fwd.MODE, self.mode
+        try:
+            outs, _ = self.model.dependency_block(feats, masks)
+        finally:
+            _fwd.MODE = prev
+        for l in range(L):
+            n = B * Tl[l]
+            r = _fwd.to_rows(outs[l])
+            o[l][:n].copy_(r[:, :C])
+            o[l][n:2 * n].copy_(r[:, C:])
+
+    def _launch_trunk(self, P):
         w, op, B, T, C, L = self.w, self.op, P["B"], self.T, self.C, self.L
         NB, Tl, Ttot = 2 * B, self.Tl, self.Ttot
         N1 = T + 1
@@ -517,7 +546,13 @@ class HotPathEngine:
                              Mn, C, op, act=ACT_SILU)
             self._csp(P, f"fu.bu{l}", P["BUin"][l + 1], P["G_bu"], l * (C // 2), self.bu_heads[l], mt, l + 1, o[l + 1], None)
 
+        P["o_final"] = o
+
+    def _launch_heads(self, P):
         # ================================================================== heads (meta_archs.py:166-178, :245-259)
+        w, op, B, C, L = self.w, self.op, P["B"], self.C, self.L
+        Tl, Ttot = self.Tl, self.Ttot
+        o = P["o_final"]
         self._stage = "heads"
         Mh = B * Ttot
         jobs = []

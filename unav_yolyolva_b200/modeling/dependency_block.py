@@ -1,9 +1,10 @@
 """``DependencyBlock`` registry entry (/root/reference/libs/modeling/dependency_block.py:6-70).
 
 The block is disabled in both reference configs (``use_dependency: False``,
-configs/avel_unav100.yaml:15) and is listed as "next" in SURVEY.md §8(f) rank 3.  The class keeps the
-constructor and parameter names so that a ``use_dependency=True`` checkpoint loads; its forward is not
-implemented on the CUDA path yet and says so loudly.
+configs/avel_unav100.yaml:15); SURVEY.md §8(f) rank 3.  Same constructor and parameter names, so a
+``use_dependency=True`` checkpoint loads; the forward runs on the CUDA kernels through the module-level path
+(``_fwd.dependency_block_forward``: GEMM / dwconv+LN / tensor-core attention kernels with torch views in between — not
+the fused engine, and not tuned: it doubles the model's FLOPs).
 """
 from torch import nn
 
@@ -25,6 +26,5 @@ class Dependency_Block(nn.Module):
                                             padding=n_embd_ks // 2, bias=False)
 
     def forward(self, fpn_feats, fpn_masks):
-        raise NotImplementedError(
-            "Dependency_Block.forward is not on the B200 hot path yet (use_dependency=False in the reference "
-            "configs; SURVEY.md §8f rank 3)")
+        from .. import _fwd
+        return _fwd.dependency_block_forward(self, fpn_feats, fpn_masks)

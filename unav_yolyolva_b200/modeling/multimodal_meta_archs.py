@@ -207,8 +207,6 @@ class PtTransformer(nn.Module):
         from ..engine import HotPathEngine
         key = (str(self.device), self.precision, self.use_cuda_graph)
         if self._engine is None or self._engine_key != key:
-            if self.use_dependency:
-                raise NotImplementedError("use_dependency=True is not on the B200 hot path yet (SURVEY.md §8f)")
             self._engine = HotPathEngine(self, mode=self.precision, use_graph=self.use_cuda_graph)
             self._engine_key = key
         return self._engine
