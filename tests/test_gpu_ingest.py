@@ -1,5 +1,7 @@
 """CudaPrefetcher (unav_yolyolva_b200/ingest.py): the overlapped upload must hand the model exactly the bytes a
 synchronous ``.to(device)`` would, in order, for ragged last batches too, and the detections must not change."""
+import os
+
 import pytest
 import torch
 
@@ -137,3 +139,44 @@ def test_device_collate_rejects_cpu_and_mismatched_lengths():
     it[1]["feats"]["audio"] = it[1]["feats"]["audio"][:, :-1]
     with pytest.raises(ValueError):
         DeviceCollator(224, "cuda:0")(it)
+
+
+def test_valid_one_epoch_dropin(tmp_path):
+    """runner.valid_one_epoch (the reference's evaluation loop, overlapped) over un-collated items with the device-side
+    collate and the device mAP evaluator: same detections and the same mAP as the synchronous loop."""
+    import json
+    import numpy as np
+    from unav_yolyolva_b200 import runner
+    from unav_yolyolva_b200.ingest import DeviceCollator
+    from unav_yolyolva_b200.utils import ANETdetection
+    dev = torch.device("cuda", 0)
+    model = make_multimodal_meta_arch("LocPointTransformer", **default_model_cfg())
+    model.load_state_dict(synth.trained_like_state_dict(), strict=True)
+    model = model.to(dev).eval()
+    sizes, first, lists, batches = [4, 4, 4, 2], 0, [], []
+    for n in sizes:
+        lists.append(synth.make_items(n, first))
+        batches.append(synth.make_batch(n, 224, first_index=first, with_gt=False))
+        first += n
+    # synchronous reference loop -> detections; ground truth = its top detections, so mAP is not trivially zero
+    sync = {"video-id": [], "t-start": [], "t-end": [], "label": [], "score": []}
+    db = {}
+    for b in batches:
+        res, _ = model(b)
+        for i, vid in enumerate(b["video_id"]):
+            seg, lab, sc = res["segments"][i].cpu(), res["labels"][i].cpu(), res["scores"][i].cpu()
+            sync["video-id"].extend([vid] * seg.shape[0])
+            sync["t-start"].append(seg[:, 0]); sync["t-end"].append(seg[:, 1]); sync["label"].append(lab); sync["score"].append(sc)
+            db[vid] = {"subset": "test", "duration": b["duration"][i],
+                       "annotations": [{"segment": [float(seg[r, 0]), float(seg[r, 1]) + 0.3], "label_id": int(lab[r]), "label": str(int(lab[r]))}
+                                       for r in (0, 2, 5)]}
+    for k in ("t-start", "t-end", "label", "score"):
+        sync[k] = torch.cat(sync[k]).numpy()
+    jf = os.path.join(tmp_path, "ants.json")
+    json.dump({"database": db}, open(jf, "w"))
+    ev = ANETdetection(jf, "test", tiou_thresholds=np.linspace(0.1, 0.9, 9), device=dev)
+    _, want = ev.evaluate(sync, verbose=False)
+    ap_want = ev.ap.copy()
+    mAP, losses = runner.valid_one_epoch(iter(lists), model, 0, evaluator=ev, collate=DeviceCollator(224, dev), print_freq=100)
+    assert mAP == want and np.array_equal(ev.ap, ap_want) and mAP > 0.05
+    assert set(losses) >= {"cls_loss", "reg_loss", "final_loss"}

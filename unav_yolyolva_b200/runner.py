@@ -72,3 +72,65 @@ def detections_to_anet(dets: torch.Tensor, video_ids: List[str]) -> Dict[str, ob
         "score": d[..., 2].reshape(-1).numpy(),
         "label": d[..., 3].reshape(-1).long().numpy(),
     }
+
+
+def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluator=None, output_file=None, tb_writer=None,
+                    print_freq=2, device=None, collate=None):
+    """Drop-in for the reference's evaluation loop (/root/reference/libs/utils/train_utils.py:380-463) with the three
+    serial stages of that loop overlapped: the upload of batch j+1 (``CudaPrefetcher``, optionally with the device-side
+    collate), the forward of batch j (``PtTransformer.submit``: soft-NMS and the copy of the detections to pinned host
+    memory on a side stream) and the host-side bookkeeping of batch j-1.  Same arguments and return value
+    ``(mAP, losses)``; ``model`` may be the bare ``PtTransformer`` or wrapped in ``nn.DataParallel`` (``model.module``).
+    ``evaluator``: the reference's ``ANETdetection`` or ``unav_yolyolva_b200.utils.ANETdetection`` (matching on the
+    device).  ``ext_score_file`` post-processing is out of scope and raises."""
+    import pickle
+    import time
+
+    import numpy as np
+
+    from .ingest import CudaPrefetcher
+    assert (evaluator is not None) or (output_file is not None)
+    if ext_score_file is not None:
+        raise NotImplementedError("external-score post-processing (libs/utils/postprocessing.py) is not on the hot path")
+    net = model.module if hasattr(model, "module") else model
+    net.eval()
+    dev = torch.device(device) if device is not None else net.device
+    results = {"video-id": [], "t-start": [], "t-end": [], "label": [], "score": []}
+
+    def unpack(handle, video_ids):
+        out = handle.result()                               # host tensors in pinned memory, this step only
+        for vid_idx, vid in enumerate(video_ids):
+            n = out["segments"][vid_idx].shape[0]
+            if n > 0:
+                results["video-id"].extend([vid] * n)
+                results["t-start"].append(out["segments"][vid_idx][:, 0].clone())
+                results["t-end"].append(out["segments"][vid_idx][:, 1].clone())
+                results["label"].append(out["labels"][vid_idx].clone())
+                results["score"].append(out["scores"][vid_idx].clone())
+
+    start = time.time()
+    prev = None
+    for iter_idx, batch in enumerate(CudaPrefetcher(val_loader, dev, collate=collate)):
+        with torch.no_grad():
+            cur = (net.submit(batch), batch["video_id"])
+        if prev is not None:
+            unpack(*prev)
+        prev = cur
+        if iter_idx != 0 and iter_idx % print_freq == 0:
+            print("Test: [{0:05d}]\\tTime {1:.3f} s / batch".format(iter_idx, (time.time() - start) / print_freq))
+            start = time.time()
+    if prev is not None:
+        unpack(*prev)
+    for k in ("t-start", "t-end", "label", "score"):
+        results[k] = torch.cat(results[k]).numpy() if results[k] else np.zeros(0)
+    if evaluator is not None:
+        _, mAP = evaluator.evaluate(results, verbose=True)
+    else:
+        with open(output_file, "wb") as f:
+            pickle.dump(results, f)
+        mAP = 0.0
+    if tb_writer is not None:
+        tb_writer.add_scalar("validation/mAP", mAP, curr_epoch)
+    losses = {k: torch.zeros((), device=dev) for k in ("cls_loss", "reg_loss", "final_loss", "inter_contr_loss",
+                                                       "intra_contr_loss", "score_loss_video", "score_loss_audio")}
+    return mAP, losses
