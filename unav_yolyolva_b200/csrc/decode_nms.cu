@@ -54,6 +54,31 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int* warp_tot, int* to
   return base + within;
 }
 
+// block-wide exclusive scan of a small per-thread count in thread order; returns this thread's offset, total in *total
+__device__ __forceinline__ int block_scan_cnt(int v, int* warp_tot, int* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[w] = incl;
+  __syncthreads();
+  int base = 0, tot = 0;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) {
+    const int c = warp_tot[i];
+    if (i < w) base += c;
+    tot += c;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + incl - v;
+}
+
+constexpr int DEC_E = 4;      // consecutive candidates per thread and emit round (one block scan per DEC_THREADS*DEC_E)
+
 __global__ void __launch_bounds__(DEC_THREADS)
 decode_kernel(const __grid_constant__ DecodeParams p) {
   pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
@@ -116,45 +141,63 @@ decode_kernel(const __grid_constant__ DecodeParams p) {
     need_eq = s_need;
   }
 
-  // ---- emit in flat-index order
+  // ---- emit in flat-index order: DEC_E consecutive candidates per thread, two block scans per round
   int eq_seen = 0, out_pos = 0;
-  for (int i0 = 0; i0 < n; i0 += DEC_THREADS) {
-    const int i = i0 + tid;
-    float pr = 0.f;
-    bool above = false, eq = false;
-    if (i < n) {
-      pr = p.use_smem ? dec_p[i] : decode_prob(p, b, row0, i);
-      if (pr > p.thresh) {
-        const unsigned key = __float_as_uint(pr);
-        above = (count <= p.topk) || key > vstar;
-        eq = (count > p.topk) && key == vstar;
+  for (int i0 = 0; i0 < n; i0 += DEC_THREADS * DEC_E) {
+    const int ib = i0 + tid * DEC_E;
+    float pr[DEC_E];
+    bool above[DEC_E], eq[DEC_E];
+    int eq_cnt = 0;
+#pragma unroll
+    for (int e = 0; e < DEC_E; ++e) {
+      const int i = ib + e;
+      pr[e] = 0.f; above[e] = false; eq[e] = false;
+      if (i < n) {
+        pr[e] = p.use_smem ? dec_p[i] : decode_prob(p, b, row0, i);
+        if (pr[e] > p.thresh) {
+          const unsigned key = __float_as_uint(pr[e]);
+          above[e] = (count <= p.topk) || key > vstar;
+          eq[e] = (count > p.topk) && key == vstar;
+        }
       }
+      eq_cnt += eq[e];
     }
     int eq_tot;
-    const int eq_rank = block_scan_flag(eq, warp_tot, &eq_tot);
-    const bool sel = above || (eq && (eq_seen + eq_rank) < need_eq);
+    int eq_rank = eq_seen + block_scan_cnt(eq_cnt, warp_tot, &eq_tot);
     eq_seen += eq_tot;
-    float left = 0.f, right = 0.f;
-    bool keep = false;
-    int cls = 0;
-    if (sel) {
-      const int row = row0 + i / p.ncls;
-      cls = i % p.ncls;
-      const long long r = static_cast<long long>(b) * p.Ttot + row;
-      const float* off = p.class_aware ? p.offsets + (r * p.ncls + cls) * 2 : p.offsets + r * 2;
-      const float t = p.points[row * 4 + 0], st = p.points[row * 4 + 3];
-      left = __fsub_rn(t, __fmul_rn(off[0], st));
-      right = __fadd_rn(t, __fmul_rn(off[1], st));
-      keep = __fsub_rn(right, left) > p.dur_thresh;
+    float left[DEC_E], right[DEC_E];
+    bool keep[DEC_E];
+    int keep_cnt = 0;
+#pragma unroll
+    for (int e = 0; e < DEC_E; ++e) {
+      const bool sel = above[e] || (eq[e] && eq_rank < need_eq);
+      eq_rank += eq[e];
+      keep[e] = false;
+      if (sel) {
+        const int i = ib + e;
+        const int row = row0 + i / p.ncls;
+        const int cls = i % p.ncls;
+        const long long r = static_cast<long long>(b) * p.Ttot + row;
+        const float* off = p.class_aware ? p.offsets + (r * p.ncls + cls) * 2 : p.offsets + r * 2;
+        const float t = p.points[row * 4 + 0], st = p.points[row * 4 + 3];
+        left[e] = __fsub_rn(t, __fmul_rn(off[0], st));
+        right[e] = __fadd_rn(t, __fmul_rn(off[1], st));
+        keep[e] = __fsub_rn(right[e], left[e]) > p.dur_thresh;
+      }
+      keep_cnt += keep[e];
     }
     int keep_tot;
-    const int pos = block_scan_flag(keep, warp_tot, &keep_tot);
-    if (keep) {
-      const long long s = static_cast<long long>(b) * p.cap + slot0 + out_pos + pos;
-      p.cand_segs[s * 2 + 0] = left;
-      p.cand_segs[s * 2 + 1] = right;
-      p.cand_scores[s] = pr;
-      p.cand_labels[s] = cls;
+    int pos = out_pos + block_scan_cnt(keep_cnt, warp_tot, &keep_tot);
+#pragma unroll
+    for (int e = 0; e < DEC_E; ++e) {
+      if (keep[e]) {
+        const long long s = static_cast<long long>(b) * p.cap + slot0 + pos;
+        p.cand_segs[s * 2 + 0] = left[e];
+        p.cand_segs[s * 2 + 1] = right[e];
+        p.cand_scores[s] = pr[e];
+        p.cand_labels[s] = (ib + e) % p.ncls;
+        ++pos;
+      }
     }
     out_pos += keep_tot;
   }
