@@ -1,4 +1,4 @@
-"""Turn the raw ncu output of scripts/gpu_prof3.sh (gpurun_out/) into the committed summaries under profiles/.
+"""Turn the raw ncu output of scripts/gpu_profile.sh (gpurun_out/) into the committed summaries under profiles/.
 
 usage: python scripts/make_profile_summary.py <tag>        e.g. r01b
 """
@@ -49,7 +49,7 @@ cagg = collections.defaultdict(float)
 for k, (n, us) in agg.items():
     cagg[CLS[k.split('<')[0]]] += us
 out = [f"# Round 1 — ncu launch list of one forward (batch 16, T=224, mode bf16x3) [{tag}]", "",
-       "Command (B200, `gpurun`, `scripts/gpu_prof3.sh`): `ncu --metrics gpu__time_duration.sum --clock-control none -k "
+       "Command (B200, `gpurun`, `scripts/gpu_profile.sh`): `ncu --metrics gpu__time_duration.sum --clock-control none -k "
        "regex:^(gemm_|attention_|...) -c 520 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline`, run after the same "
        f"command exited 0 without ncu.  One forward = {per_step} launches; the table is launches {per_step}..{2 * per_step - 1} of the "
        f"process (the second eager pass), per-launch rows in `{tag}_launches_b16_bf16x3.csv`.  ncu times are cold-cache and "
