@@ -126,3 +126,58 @@ def test_use_dependency_variant_vs_oracle(cuda):
     assert e1 < 5e-4 and e2 < 2e-3
     res, _ = model(b)                       # and the full path to detections runs
     assert res["segments"].shape == (2, 100, 2)
+
+
+def test_extreme_video_lengths_vs_oracle(cuda):
+    """Edge cases of the valid-length mask: a 1-frame video, a 2-frame video, one exactly max_seq_len long and a typical
+    one in the same batch.  Logits / offsets / masks vs the oracle (padded positions included: the reference leaves LayerNorm
+    biases there), decode + NMS bit-exact given the device logits."""
+    from oracle import model_ref as R
+    model = make_multimodal_meta_arch("LocPointTransformer", **default_model_cfg())
+    sd = synth.trained_like_state_dict()
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda).eval()
+    b = synth.make_batch(4, 224, with_gt=False)
+    for i, L in enumerate((1, 2, 224, 97)):
+        g = torch.Generator().manual_seed(900 + i)
+        b["visual"][i].zero_(); b["audio"][i].zero_(); b["mask"][i].zero_()
+        b["visual"][i, :, :L] = 0.3 * torch.randn(2048, L, generator=g).abs()
+        b["audio"][i, :, :L] = 0.5 * torch.randn(128, L, generator=g).abs()
+        b["mask"][i, 0, :L] = True
+        b["duration"][i] = (L * 8 + 24) / 25.0
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    with torch.no_grad():
+        lg, of, ms = R.forward_logits(sd, b["visual"], b["audio"], b["mask"])
+    lg, of, ms = torch.cat(lg, 1), torch.cat(of, 1), torch.cat(ms, 1)
+    plan = model.run_hot_path(b)
+    torch.cuda.synchronize()
+    g_lg = plan["logits"].cpu().view(4, 441, 100)
+    g_of = plan["offsets"].cpu().view(4, 441, 100, 2)
+    assert torch.equal(plan["m_heads"].cpu().view(4, 441).bool(), ms)
+    e1 = float((g_lg - lg).abs().max() / lg.abs().max())
+    e2 = float((g_of - of).abs().max() / of.abs().max())
+    print(f"[extreme lengths] logits rel err {e1:.3e}, offsets rel err {e2:.3e}")
+    assert e1 < 5e-5 and e2 < 2e-4
+    assert not torch.isnan(g_lg).any() and not torch.isnan(g_of).any()
+    # detections of the device path = oracle decode + NMS on the device logits (per video; counts may differ per video,
+    # so go through the plan, not through forward()'s equal-count contract)
+    pts = R.make_points(224)
+    counts = plan["out_counts"].cpu()
+    for i in range(4):
+        lv_l = [g_lg[i, o:o + t] for o, t in zip(model.engine.level_off, model.engine.Tl)]
+        lv_o = [g_of[i, o:o + t] for o, t in zip(model.engine.level_off, model.engine.Tl)]
+        lv_m = [ms[i, o:o + t] for o, t in zip(model.engine.level_off, model.engine.Tl)]
+        segs, scores, labels, _ = R.decode_single_video(pts, lv_m, lv_l, lv_o)
+        # candidate SET from the oracle decode; the device's own scores (CUDA expf sigmoid, 1 ulp from torch's CPU sigmoid)
+        # go into the oracle NMS so that its inputs are identical
+        cs = plan["cand_segs"][i].cpu().numpy(); csc = plan["cand_scores"][i].cpu().numpy(); cl = plan["cand_labels"][i].cpu().numpy()
+        keep = cl >= 0
+        assert keep.sum() == len(labels)
+        assert np.array_equal(np.sort(cl[keep]), np.sort(labels.numpy()))
+        assert np.abs(np.sort(csc[keep]) - np.sort(scores.numpy())).max() < 1e-6
+        r = nms_ref.batched_nms(cs[keep], csc[keep], cl[keep].astype(np.int64), TEST_CFG["iou_threshold"], TEST_CFG["min_score"],
+                                TEST_CFG["max_seg_num"], True, TEST_CFG["nms_sigma"])
+        k = int(counts[i])
+        assert k == len(r[1]), (i, k, len(r[1]))
+        assert np.array_equal(plan["out_scores"][i, :k].cpu().numpy().view(np.uint32), r[1].view(np.uint32))
+        assert np.array_equal(plan["out_labels"][i, :k].cpu().numpy(), r[2])
