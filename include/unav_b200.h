@@ -112,7 +112,13 @@ typedef struct UnavGemmGroup {
    *   out_opT[((m / t_seg) * ncols + (n - t_col0)) * ld_opT + (m % t_seg)] = acc + bias[n]
    * i.e. per item of t_seg rows a [ncols, t_seg] matrix — the V^T layout unav_attention_tc consumes. */
   void* out_opT;   long long ld_opT;
-  int t_seg; int t_col0; int t_ncols; int pad_;
+  int t_seg; int t_col0; int t_ncols;
+  /* conv_T > 0 (UNAV_GEMM_TCGEN05 only): implicit k=3 convolution with per-segment zero padding (MaskedConv1D, stride 1,
+   * blocks.py:30-31).  A is then the PLAIN operand [M, K/3] of the convolution's input (M = segments * conv_T rows) and
+   * W the [N, K] weight with K = 3 * Cin laid out tap-major (column tap*Cin + c); row m = (s, t) of the product uses
+   * A rows (s, t-1), (s, t), (s, t+1), zero outside the segment.  Same result, bit for bit, as a GEMM over the
+   * materialised im2col operand. */
+  int conv_T;
 } UnavGemmGroup;
 
 /* groups: host array of ngroups (<= UNAV_MAX_GROUPS) problems of identical M, N, K.

@@ -208,3 +208,37 @@ def test_transposed_operand_output(cuda, backend, op):
             got = got + outT[:, outT.shape[1] // 2: outT.shape[1] // 2 + T].float().cpu()
     tol = 2e-2 if op == K.BF16 else 1e-5
     assert (got - ref).abs().max() <= tol * ref.abs().max()
+
+
+@pytest.mark.parametrize("op", [K.BF16X2, K.BF16, K.F16X2])
+@pytest.mark.parametrize("nseg,T,Cin,N", [(6, 28, 256, 256), (4, 224, 512, 512), (5, 7, 256, 128), (3, 130, 64, 200), (2, 112, 1024, 512)])
+def test_implicit_conv3_equals_im2col_gemm(cuda, op, nseg, T, Cin, N):
+    """conv_T: the k=3 convolution read straight from the plain operand through a 4-D tensor map (zero fill outside each
+    segment) must give the SAME bits as the GEMM over the materialised im2col operand, and match a torch conv1d."""
+    g = torch.Generator().manual_seed(T + Cin)
+    M = nseg * T
+    x = torch.randn(M, Cin, generator=g)
+    W = torch.randn(N, 3 * Cin, generator=g) / (3 * Cin) ** 0.5
+    bias = torch.randn(N, generator=g)
+    rowmask = (torch.rand(M, generator=g) > 0.2).to(torch.uint8)
+    xop = K.pack_operand(x.to(cuda), op)
+    Wop = K.pack_operand(W.to(cuda), op)
+    ic = K.new_operand(M, 3 * Cin, op, cuda)
+    K.rowcopy([{"src": x.to(cuda), "dst": ic, "nseg": nseg, "seg_len_in": T, "seg_len_out": T, "ntaps": 3, "tap_stride": Cin, "C": Cin}], op)
+    o_ic, o_cv = torch.empty(M, N, device=cuda), torch.empty(M, N, device=cuda)
+    oop = K.new_operand(M, N, op, cuda)
+    common = {"W": Wop, "bias": bias.to(cuda), "rowmask": rowmask.to(cuda)}
+    K.gemm([dict(common, A=ic, out_f32=o_ic)], M, N, 3 * Cin, op, K.ACT_GELU, False, K.GEMM_TCGEN05)
+    K.gemm([dict(common, A=xop, out_f32=o_cv, out_op=oop, conv_T=T)], M, N, 3 * Cin, op, K.ACT_GELU, False, K.GEMM_TCGEN05)
+    torch.cuda.synchronize()
+    assert torch.equal(o_ic, o_cv)
+    dt = K.OP_TORCH_DTYPE[op]
+    def rt(t):
+        hi = t.to(dt).float()
+        return hi + ((t - hi).to(dt).float() if op in K.SPLIT_DTYPES else 0)
+    xr = rt(x).view(nseg, T, Cin).transpose(1, 2).double()
+    wr = rt(W).view(N, 3, Cin).permute(0, 2, 1).double()
+    ref = torch.nn.functional.conv1d(xr, wr, bias.double(), padding=1).transpose(1, 2).reshape(M, N)
+    ref = torch.nn.functional.gelu(ref * rowmask.double()[:, None]).float()
+    tol = {K.BF16: 2e-5, K.BF16X2: 6e-5}.get(op, 2e-5)
+    assert (o_cv.cpu() - ref).abs().max().item() <= tol * ref.abs().max().item() + 1e-6

@@ -32,7 +32,7 @@ class GemmGroup(C.Structure):
                 ("rowscale", c_vp), ("gate", c_vp), ("res", c_vp), ("ldres", c_ll), ("colscale", c_vp),
                 ("out_f32", c_vp), ("ld_f32", c_ll), ("out_op", c_vp), ("ld_op", c_ll),
                 ("gate_groups", c_i), ("gate_width", c_i), ("out_opT", c_vp), ("ld_opT", c_ll), ("t_seg", c_i),
-                ("t_col0", c_i), ("t_ncols", c_i), ("pad_", c_i)]
+                ("t_col0", c_i), ("t_ncols", c_i), ("conv_T", c_i)]
 
 
 class LnGroup(C.Structure):

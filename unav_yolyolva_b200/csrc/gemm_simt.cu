@@ -127,6 +127,7 @@ extern "C" int unav_gemm(const UnavGemmGroup* groups, int ngroups, int M, int N,
   for (int i = 0; i < ngroups; ++i) {
     UNAV_REQUIRE(groups[i].A && groups[i].W, "unav_gemm: null operand in group %d", i);
     UNAV_REQUIRE(groups[i].out_f32 || groups[i].out_op || groups[i].out_opT, "unav_gemm: group %d has no output", i);
+    UNAV_REQUIRE(groups[i].conv_T == 0 || backend == UNAV_GEMM_TCGEN05, "unav_gemm: implicit convolution (conv_T) needs the tcgen05 backend");
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (backend == UNAV_GEMM_TCGEN05)

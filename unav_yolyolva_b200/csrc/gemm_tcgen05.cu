@@ -45,6 +45,11 @@ struct TcGroup {
 struct TcParams {
   TcGroup g[UNAV_MAX_GROUPS];
   int M, N, K, op_dtype, act, res_masked, nseg, stages, once;
+  // implicit k=3 convolution (conv_T > 0): A is the PLAIN operand [items*conv_T, Cin] (K = 3*Cin); a tile is 128 time steps
+  // of one item and the k-loop fetches tap t from rows t0 + t - 1 through a 4-D map {Cin, T, items, halves}: rows outside
+  // [0, T) are zero-filled by the TMA unit = the per-video zero padding of MaskedConv1D (blocks.py:30-31).  No im2col
+  // operand is materialised; the accumulation order (K = tap*Cin + c ascending) is that of the im2col GEMM, bit for bit.
+  int conv_T, conv_cin, conv_tiles;
   long long* phase;    // diagnostics (unav_gemm_set_phase_trace): 8 clock64 stamps per CTA, or nullptr
   int phase_cap;
 };
@@ -90,6 +95,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -204,7 +214,7 @@ __device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const flo
 // row-contiguous 128-bit accesses.
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& g, uint32_t tmem_cols, int m0, int n0,
-                                              int warp, int lane, float* stg_base) {
+                                              int warp, int lane, float* stg_base, long long m_limit) {
   constexpr int PITCH = BN + 4;              // floats; 16-byte groups of consecutive rows fall in distinct banks
   constexpr int HALF = BN / 2;               // columns per warp
   constexpr int LPR = HALF / 4;              // lanes per row in phase B (16 | 8)
@@ -247,7 +257,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& 
     // transposed operand output (V^T for the tensor-core attention): lanes run along the token axis, so each
     // store instruction writes 32 consecutive keys of one channel row
     const long long mt = static_cast<long long>(m0) + q * 32 + lane;
-    if (mt < p.M) {
+    if (mt < m_limit) {
       const int ncols = e.t_ncols > 0 ? e.t_ncols : p.N;
       const long long item = mt / e.t_seg, t = mt % e.t_seg;
       const long long spl = e.ld_opT / 2;
@@ -270,7 +280,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& 
                     (!has_gate || e.gate_width % 4 == 0);
   if (fast && (e.out_f32 || e.out_op)) {
     const long long m_base = static_cast<long long>(m0) + q * 32;
-    const int rows = static_cast<int>(min(32ll, static_cast<long long>(p.M) - m_base));
+    const int rows = static_cast<int>(min(32ll, m_limit - m_base));
     const float* sl = stg + cl * 4;
     const bool split = op_is_split(p.op_dtype);
     constexpr bool f16 = kHalfF16;
@@ -292,7 +302,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& 
 #pragma unroll 2
     for (int r = rsub; r < 32; r += RPP) {
       const long long m = static_cast<long long>(m0) + q * 32 + r;
-      if (m >= p.M) break;
+      if (m >= m_limit) break;
       const float4 a4 = *reinterpret_cast<const float4*>(stg + r * PITCH + cl * 4);
       float v[4] = {a4.x, a4.y, a4.z, a4.w};
       const float mk = e.rowmask ? (e.rowmask[m] ? 1.f : 0.f) : 1.f;
@@ -360,9 +370,14 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   const uint32_t accum_bar = bar_base + 8u * (2 * TC_MAX_STAGES);
   const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 1);
 
-  const int m0 = blockIdx.x * TC_BM;
+  const bool conv = p.conv_T > 0;
+  const int c_item = conv ? blockIdx.x / p.conv_tiles : 0;
+  const int c_t0 = conv ? (blockIdx.x % p.conv_tiles) * TC_BM : 0;
+  const int m0 = conv ? c_item * p.conv_T + c_t0 : blockIdx.x * TC_BM;                  // first output row of the tile
+  const long long m_limit = conv ? static_cast<long long>(c_item) * p.conv_T + min(p.conv_T, c_t0 + TC_BM) : p.M;
   const int n0 = blockIdx.y * BN;
-  const int nkb = (p.K + BK - 1) / BK;
+  const int nkb_c = conv ? (p.conv_cin + BK - 1) / BK : 0;                             // k-blocks per tap
+  const int nkb = conv ? 3 * nkb_c : (p.K + BK - 1) / BK;
   const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   long long* ph_out = (p.phase && cta_lin < p.phase_cap) ? p.phase + 8ll * cta_lin : nullptr;
   if (ph_out && threadIdx.x == 0) {
@@ -410,8 +425,14 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
         mbar_wait(empty_bar(s), ph ^ 1);
         mbar_expect_tx(full_bar(s), stage_bytes);
         const uint32_t sa = base + s * stage_bytes;
-        tma_load_3d(sa, &g.tmA, full_bar(s), it * BK, m0, 0);              // [A_hi | A_lo] (or A alone)
-        tma_load_3d(sa + w_off, &g.tmW, full_bar(s), it * BK, n0, 0);      // [W_hi | W_lo]
+        if (conv) {
+          const int tap = it / nkb_c, kb = it - tap * nkb_c;
+          tma_load_4d(sa, &g.tmA, full_bar(s), kb * BK, c_t0 + tap - 1, c_item, 0);
+          tma_load_3d(sa + w_off, &g.tmW, full_bar(s), tap * p.conv_cin + kb * BK, n0, 0);
+        } else {
+          tma_load_3d(sa, &g.tmA, full_bar(s), it * BK, m0, 0);              // [A_hi | A_lo] (or A alone)
+          tma_load_3d(sa + w_off, &g.tmW, full_bar(s), it * BK, n0, 0);      // [W_hi | W_lo]
+        }
       }
     }
     __syncwarp();     // lanes 1..31 wait here for the producer lane: the block barrier below must see whole warps
@@ -464,7 +485,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (ph_out && threadIdx.x == 64) ph_out[5] = clock_stamp();       // accumulator ready
-    epilogue_tile<BN>(p, g, tmem_base, m0, n0, warp, lane, reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))));
+    epilogue_tile<BN>(p, g, tmem_base, m0, n0, warp, lane, reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))), m_limit);
   }
   if (ph_out && threadIdx.x == 64) ph_out[6] = clock_stamp();         // this warp's epilogue done
   tc_fence_before();
@@ -613,7 +634,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
     float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)));
     for (int hf = 0; hf < 2; ++hf) {
       if (n0 + hf * 128 >= p.N) break;
-      epilogue_tile<128>(p, g, tmem_base + hf * 128, m0, n0 + hf * 128, warp, lane, stg);
+      epilogue_tile<128>(p, g, tmem_base + hf * 128, m0, n0 + hf * 128, warp, lane, stg, p.M);
       __syncwarp();
     }
   }
@@ -660,6 +681,28 @@ static int encode_map(CUtensorMap* map, const void* ptr, long long rows, long lo
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld K=%lld ld=%lld", (int)r, ptr, rows, K, ld);
+    return UNAV_ERR_DRIVER;
+  }
+  return 0;
+}
+
+// 4-D map of a convolution input [segments*T, Cin] (plain operand): dims {Cin, T, segments, halves}; a box is 128 time
+// steps of one segment, and rows before / after the segment come back as zeros.
+static int encode_conv_map(CUtensorMap* map, const void* ptr, long long segs, long long T, long long cin, long long ld, int bk,
+                           bool split, int box_halves) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return UNAV_ERR_DRIVER;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(segs),
+                        static_cast<cuuint64_t>(split ? 2 : 1)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(T) * ld * 2,
+                           static_cast<cuuint64_t>(split ? ld / 2 : ld) * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(TC_BM), 1u, static_cast<cuuint32_t>(box_halves)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (conv) failed (%d): ptr=%p segs=%lld T=%lld cin=%lld ld=%lld", (int)r, ptr, segs, T, cin, ld);
     return UNAV_ERR_DRIVER;
   }
   return 0;
@@ -716,7 +759,7 @@ static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + BN - 1) / BN, ngroups);
+  dim3 grid(p.conv_T > 0 ? (p.M / p.conv_T) * p.conv_tiles : (p.M + TC_BM - 1) / TC_BM, (p.N + BN - 1) / BN, ngroups);
   // Ring depth: multi-CTA-per-SM grids keep <= ~100 KB per CTA so two CTAs share an SM (one's epilogue overlaps the
   // other's k-loop); grids of at most one CTA per SM take a deeper ring.  The epilogue staging tile (128 x (BN+4)
   // floats) must also fit in the ring's bytes.
@@ -788,7 +831,12 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
   p.M = M; p.N = N; p.K = K; p.op_dtype = op_dtype; p.act = act; p.res_masked = res_masked;
   p.nseg = op_passes(op_arg);       // 1 pass on split operands reads the hi halves only
   p.phase = g_phase_buf; p.phase_cap = g_phase_cap;
-  const bool pair = use_pair(M, N, K, ngroups);
+  const int conv_T = groups[0].conv_T;
+  for (int i = 0; i < ngroups; ++i) UNAV_REQUIRE(groups[i].conv_T == conv_T, "gemm_tcgen05: groups must share conv_T");
+  if (conv_T > 0)
+    UNAV_REQUIRE(M % conv_T == 0 && K % 3 == 0 && (K / 3) % 32 == 0, "gemm_tcgen05: implicit conv needs M %% T == 0 and Cin %% 32 == 0");
+  p.conv_T = conv_T; p.conv_cin = conv_T > 0 ? K / 3 : 0; p.conv_tiles = conv_T > 0 ? (conv_T + TC_BM - 1) / TC_BM : 0;
+  const bool pair = conv_T == 0 && use_pair(M, N, K, ngroups);
   const TcChoice ch = choose_tile(M, N, K, ngroups, p.nseg);
   const int bn = pair ? 128 : ch.bn, bk = pair ? P2_BK : (ch.sched == 2 ? 32 : 64);
   p.once = ch.sched ? 1 : 0;
@@ -798,12 +846,14 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
                  "gemm_tcgen05: A/W must be 16-byte aligned");
     UNAV_REQUIRE(g.lda % 8 == 0 && g.ldw % 8 == 0, "gemm_tcgen05: lda/ldw must be multiples of 8 (got %lld, %lld)", g.lda, g.ldw);
     if (op_is_split(op_dtype))
-      UNAV_REQUIRE(g.lda % 16 == 0 && g.ldw % 16 == 0 && g.lda / 2 >= K && g.ldw / 2 >= K,
+      UNAV_REQUIRE(g.lda % 16 == 0 && g.ldw % 16 == 0 && g.lda / 2 >= (conv_T > 0 ? K / 3 : K) && g.ldw / 2 >= K,
                    "gemm_tcgen05: split operands need ld %% 16 == 0 and ld/2 >= K");
     int rc;
     const bool split = op_is_split(op_dtype);
     const int halves = p.nseg > 1 ? 2 : 1;             // one pass over split operands fetches the hi halves only
-    if ((rc = encode_map(&p.g[i].tmA, g.A, M, K, g.lda, TC_BM, bk, split, halves))) return rc;
+    if (conv_T > 0) {
+      if ((rc = encode_conv_map(&p.g[i].tmA, g.A, M / conv_T, conv_T, K / 3, g.lda, bk, split, halves))) return rc;
+    } else if ((rc = encode_map(&p.g[i].tmA, g.A, M, K, g.lda, TC_BM, bk, split, halves))) return rc;
     if ((rc = encode_map(&p.g[i].tmW, g.W, N, K, g.ldw, bn, bk, split, halves))) return rc;
     p.g[i].epi = make_epi(g);
   }

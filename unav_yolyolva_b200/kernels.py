@@ -181,6 +181,7 @@ def gemm(groups: Sequence[dict], M: int, N: int, K: int, op_dtype: int, act: int
         s.out_op, s.ld_op = _vp(g.get("out_op")), _vld(g.get("out_op"))
         s.out_opT, s.ld_opT = _vp(g.get("out_opT")), _vld(g.get("out_opT"))
         s.t_seg, s.t_col0, s.t_ncols = g.get("t_seg", 0), g.get("t_col0", 0), g.get("t_ncols", 0)
+        s.conv_T = g.get("conv_T", 0)
     lib = A.load(op_dtype)
     es = 4 if op_dtype == F32 else (4 if op_dtype in SPLIT_DTYPES else 2)
     es_in = 2 if (op_dtype in SPLIT_DTYPES and passes == 1) else es     # one pass reads the hi halves only
