@@ -3,7 +3,7 @@
 ``HotPathEngine`` turns a ``PtTransformer`` (parameter holder with the reference's state_dict layout) into
 a static launch plan over hand-written CUDA kernels (C ABI, ``kernels.py``): Alignment multiway transformer
 -> conv/transformer stem -> depthwise pyramid -> two fusion passes (batched as 2B) -> cls/reg heads -> decode
--> per-class soft-NMS.  About 330 kernel launches per batch replace the reference's ~51 k ATen calls
+-> per-class soft-NMS.  256 kernel launches per batch replace the reference's ~51 k ATen calls
 (SURVEY.md §2.2); the whole sequence is captured once per batch size into a CUDA graph and replayed.
 
 Data layout: activations are token-major FP32 ``[rows, C]`` matrices (rows = time steps of
