@@ -35,7 +35,7 @@ loop(30, True, False, True, "prefetch + d2h (no flush)")
 loop(30, False, False, True, "inline H2D + d2h (no flush)")
 loop(30, True, False, False, "prefetch, no d2h, no flush")
 # raw pieces
-plan = model.engine._plans[B]
+plan = model.engine._plans[(B, 0)]
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(30): plan["graph"].replay()
 torch.cuda.synchronize(); print("graph replay only", (time.perf_counter() - t0) / 30 * 1e3)

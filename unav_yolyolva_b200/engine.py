@@ -53,7 +53,6 @@ class HotPathEngine:
         self.mode = mode
         self.op, self.backend = MODES[mode]
         self.use_graph = use_graph and not getattr(model, "use_dependency", False)   # the Dependency_Block path is eager
-        self.nms_stream = None          # side stream of the streaming mode (run(..., overlap_nms=True))
         self.model = model
         dev = next(model.parameters()).device
         if dev.type != "cuda":
@@ -78,7 +77,7 @@ class HotPathEngine:
         self._stage = "alignment"
         self.w: Dict[str, torch.Tensor] = {}
         self._pack_weights()
-        self._plans: Dict[int, dict] = {}
+        self._plans: Dict[tuple, dict] = {}
 
     # ------------------------------------------------------------------------------ weights
     def _pack_weights(self):
@@ -194,9 +193,11 @@ class HotPathEngine:
         w[f"{name}.sm"] = _flat(sd[p + "drop_path_mlp.scale"])
 
     # ------------------------------------------------------------------------------ buffers
-    def _plan(self, B: int) -> dict:
-        if B in self._plans:
-            return self._plans[B]
+    def _plan(self, B: int, slot: int = 0) -> dict:
+        """Static buffers (and later the CUDA graphs, streams, events) of one batch size.  ``slot`` > 0: an independent
+        second set, so that two batches can be in flight at once (streaming mode)."""
+        if (B, slot) in self._plans:
+            return self._plans[(B, slot)]
         dev, op, T, C, L = self.dev, self.op, self.T, self.C, self.L
         NB = 2 * B
         f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
@@ -302,7 +303,7 @@ class HotPathEngine:
         P["out_counts"] = torch.zeros(B, dtype=torch.int32, device=dev)
         P["nms_ws"] = torch.zeros(K.softnms_workspace_bytes(B, self.ncls, Kd), dtype=torch.uint8, device=dev)
         P["graph"] = None
-        self._plans[B] = P
+        self._plans[(B, slot)] = P
         return P
 
     # ------------------------------------------------------------------------------ helpers
@@ -648,28 +649,32 @@ class HotPathEngine:
     # ------------------------------------------------------------------------------ public
     @torch.no_grad()
     def run(self, visual: torch.Tensor, audio: torch.Tensor, mask: torch.Tensor, vid_meta: torch.Tensor,
-            overlap_nms: bool = False):
+            overlap_nms: bool = False, slot: int = 0):
         """visual [B,2048,T] f32, audio [B,128,T] f32, mask [B,1,T] bool, vid_meta [B,4] f32
         (feat_stride, feat_num_frames, fps, duration) — any device; copied into the plan's static inputs.
         Returns the plan dict (device-resident outputs: out_segs/out_scores/out_labels/out_counts, logits, offsets).
 
-        overlap_nms=False: everything is enqueued on the current stream (one CUDA graph).
-        overlap_nms=True : streaming mode for back-to-back batches.  The forward + decode run on the current stream, the
-        soft-NMS kernel (one CTA per video: 16 of 148 SMs, a <=100-round dependency chain) on ``self.nms_stream`` so it
-        overlaps the NEXT batch's forward; the next decode waits for it before overwriting the candidates.  Consumers
-        of out_* must order themselves after ``plan["ev_nms"]`` (or enqueue on ``self.nms_stream``)."""
+        overlap_nms=False: everything is enqueued on the current stream (one CUDA graph); ``slot`` must be 0.
+        overlap_nms=True : streaming mode for back-to-back batches.  Plan ``slot`` owns a forward stream and an NMS stream:
+        the input copies, the CUDA graph of the forward and the decode run on the former, the soft-NMS kernel (one CTA
+        per video: 16 of 148 SMs, a <=100-round dependency chain) on the latter, so it overlaps the next batch's forward.
+        Alternating two slots keeps two batches in flight: the latency-bound short-pyramid-level kernels of one (a few
+        CTAs each, ~40 % of a step) run under the big GEMMs of the other.  The caller's stream only waits for the input
+        copies (it may recycle its input tensors afterwards); consumers of out_* order themselves after
+        ``plan["ev_nms"]`` or enqueue on ``plan["nms_stream"]``."""
         B = visual.shape[0]
         assert visual.shape[2] == self.T and audio.shape[2] == self.T, "sequence length must equal max_seq_len"
-        P = self._plan(B)
+        assert overlap_nms or slot == 0
+        P = self._plan(B, slot)
         with torch.cuda.device(self.dev):
             cur = torch.cuda.current_stream()
-            if P.get("ev_nms") is not None and not overlap_nms:
-                cur.wait_event(P["ev_nms"])                   # a streamed NMS of this plan may still be running
-                P["ev_nms"] = None
-            P["visual"].copy_(visual, non_blocking=True)
-            P["audio"].copy_(audio, non_blocking=True)
-            P["mask_in"].copy_(mask.reshape(B, self.T), non_blocking=True)
             if not overlap_nms:
+                if P.get("ev_nms") is not None:
+                    cur.wait_event(P["ev_nms"])                   # a streamed step of this plan may still be running
+                    P["ev_nms"] = None
+                P["visual"].copy_(visual, non_blocking=True)
+                P["audio"].copy_(audio, non_blocking=True)
+                P["mask_in"].copy_(mask.reshape(B, self.T), non_blocking=True)
                 P["vid_meta"].copy_(vid_meta, non_blocking=True)
                 if not self.use_graph:
                     self._launch_all(P)
@@ -690,33 +695,44 @@ class HotPathEngine:
                 P["meta2"] = torch.zeros(2, B, 4, dtype=torch.float32, device=self.dev)
                 P["ev_dec"] = torch.cuda.Event()
                 P["step"] = 0
-                if self.nms_stream is None:
-                    self.nms_stream = torch.cuda.Stream(self.dev)
+                P["fwd_stream"] = torch.cuda.Stream(self.dev)
+                P["nms_stream"] = torch.cuda.Stream(self.dev)
+            if self.use_graph and P.get("graph_fwd") is None:
+                self._launch_all(P)                             # warm-up on the caller's stream
+                torch.cuda.synchronize(self.dev)
+                n0 = K.launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_forward(P)
+                P["launches_per_step"] = K.launch_count() - n0 + 2
+                P["graph_fwd"] = g
+            fs, ns = P["fwd_stream"], P["nms_stream"]
             meta = P["meta2"][P["step"] & 1]
             P["step"] += 1
-            meta.copy_(vid_meta, non_blocking=True)
-            if not self.use_graph:
-                self._launch_forward(P)
-            else:
-                if P.get("graph_fwd") is None:
-                    self._launch_all(P)
-                    torch.cuda.synchronize(self.dev)
-                    n0 = K.launch_count()
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self._launch_forward(P)
-                    P["launches_per_step"] = K.launch_count() - n0 + 2
-                    P["graph_fwd"] = g
-                P["graph_fwd"].replay()
-            if P.get("ev_nms") is not None:
-                cur.wait_event(P["ev_nms"])                   # the previous batch's NMS has consumed the candidates
-            self._launch_decode(P)
-            P["ev_dec"].record(cur)
-            with torch.cuda.stream(self.nms_stream):
-                self.nms_stream.wait_event(P["ev_dec"])
+            ev_in = torch.cuda.Event()
+            ev_in.record(cur)
+            fs.wait_event(ev_in)                                # the inputs are ready in the caller's stream order
+            with torch.cuda.stream(fs):
+                P["visual"].copy_(visual, non_blocking=True)
+                P["audio"].copy_(audio, non_blocking=True)
+                P["mask_in"].copy_(mask.reshape(B, self.T), non_blocking=True)
+                meta.copy_(vid_meta, non_blocking=True)
+                ev_cp = torch.cuda.Event()
+                ev_cp.record(fs)
+                if self.use_graph:
+                    P["graph_fwd"].replay()
+                else:
+                    self._launch_forward(P)
+                if P.get("ev_nms") is not None:
+                    fs.wait_event(P["ev_nms"])                  # this slot's previous NMS has consumed the candidates
+                self._launch_decode(P)
+                P["ev_dec"].record(fs)
+            cur.wait_event(ev_cp)                               # caller-side tensors may be recycled after the copies
+            with torch.cuda.stream(ns):
+                ns.wait_event(P["ev_dec"])
                 self._launch_nms(P, meta)
                 ev = torch.cuda.Event()
-                ev.record(self.nms_stream)
+                ev.record(ns)
                 P["ev_nms"] = ev
         return P
 

@@ -44,8 +44,6 @@ class CudaPrefetcher:
         self.keys = keys
         self.depth = depth
         self.collate = collate
-        if collate is not None and collate.slots < depth:
-            raise ValueError("the DeviceCollator needs at least as many slots as the prefetcher's depth")
         self.stream = torch.cuda.Stream(self.device)
         self._slots = [dict() for _ in range(depth)]          # slot -> {key: device tensor}
         self._free = [None] * depth                            # slot -> event: consumer done with the slot
@@ -130,25 +128,24 @@ class DeviceCollator:
     ``CudaPrefetcher(loader, device, collate=collator)`` runs it one batch ahead on the copy stream.
     """
 
-    def __init__(self, max_seq_len: int, device, max_div_factor: int = 1, padding_val: float = 0.0, slots: int = 2):
+    def __init__(self, max_seq_len: int, device, max_div_factor: int = 1, padding_val: float = 0.0):
         self.T = int(max_seq_len)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("DeviceCollator needs a CUDA device (no CPU fallback)")
         self.max_div_factor = int(max_div_factor)
         self.pad = float(padding_val)
-        self.slots = slots
-        self._host: List[Optional[torch.Tensor]] = [None] * slots       # pinned staging (floats + header)
-        self._dev: List[dict] = [dict() for _ in range(slots)]
+        self._host: dict = {}                                   # slot -> pinned staging (header + feature blocks)
+        self._dev: dict = {}                                    # slot -> device staging + padded outputs
 
     def _buffers(self, slot: int, B: int, Cv: int, Ca: int, T: int, nfloat: int):
         hdr = 4 * B                                                    # offsets (2 x i64 per video = 4 floats) per modality ...
         need = nfloat + 2 * hdr + 2 * B                                # ... + lens (i32)
-        h = self._host[slot]
+        h = self._host.get(slot)
         if h is None or h.numel() < need:
             h = torch.empty(int(need * 1.25) + 1024, dtype=torch.float32).pin_memory()
             self._host[slot] = h
-        d = self._dev[slot]
+        d = self._dev.setdefault(slot, {})
         if d.get("key") != (B, Cv, Ca, T) or d["stage"].numel() < h.numel():
             d.clear()
             d["key"] = (B, Cv, Ca, T)

@@ -109,18 +109,18 @@ def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluato
                 results["score"].append(out["scores"][vid_idx].clone())
 
     start = time.time()
-    prev = None
-    for iter_idx, batch in enumerate(CudaPrefetcher(val_loader, dev, collate=collate)):
+    pending = []
+    depth = max(1, getattr(net, "streams", 1))                 # steps kept in flight before the oldest result is read
+    for iter_idx, batch in enumerate(CudaPrefetcher(val_loader, dev, collate=collate, depth=depth + 1)):
         with torch.no_grad():
-            cur = (net.submit(batch), batch["video_id"])
-        if prev is not None:
-            unpack(*prev)
-        prev = cur
+            pending.append((net.submit(batch), batch["video_id"]))
+        if len(pending) > depth:
+            unpack(*pending.pop(0))
         if iter_idx != 0 and iter_idx % print_freq == 0:
-            print("Test: [{0:05d}]\\tTime {1:.3f} s / batch".format(iter_idx, (time.time() - start) / print_freq))
+            print("Test: [{0:05d}]\tTime {1:.3f} s / batch".format(iter_idx, (time.time() - start) / print_freq))
             start = time.time()
-    if prev is not None:
-        unpack(*prev)
+    while pending:
+        unpack(*pending.pop(0))
     for k in ("t-start", "t-end", "label", "score"):
         results[k] = torch.cat(results[k]).numpy() if results[k] else np.zeros(0)
     if evaluator is not None:
