@@ -395,12 +395,18 @@ def main():
                 "frac": ach / peaks["hbm_gbs"], "traffic": None}
     try:
         tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
-        if tj.get("kernel") == top and B == 16 and args.mode == "bf16x3":
-            roof["traffic"] = tj["dram_bytes_per_launch"]
+        tk = tj.get("per_kernel", {}).get(top)
+        if tk and B == 16 and args.mode == "bf16x3":
+            roof["traffic"] = tk["dram_bytes_per_launch"]
             roof["traffic_source"] = tj["source"]
             roof["algorithmic_bytes_per_launch"] = a[2] / a[3]
     except Exception:                                   # noqa: BLE001
         pass
+    gemm_cls = [k for k in agg if k.startswith("gemm_")]
+    roof["gemm_class"] = {"share_of_step": round(sum(shares[k] for k in gemm_cls), 4),
+                          "tflops_algorithmic": sum(agg[k][1] for k in gemm_cls) / (sum(agg[k][0] for k in gemm_cls) / 1e3) / 1e12,
+                          "launches": sum(agg[k][3] for k in gemm_cls) // reps,
+                          "mma_passes": 3 if args.mode in ("bf16x3", "f16x3") else None}
     roof.update({"events": trace_kind, "class_us_per_step": a[0] / reps * 1e3, "traced_step_us": tot_ms / reps * 1e3,
                  "peak_source": peaks["source"], "launches_timed": a[3] // reps, "avg_launch_us": a[0] / a[3] * 1e3,
                  "share_of_step": shares[top], "kernel_time_shares": shares,

@@ -84,6 +84,11 @@ int unav_check_device(int dev);
 /* number of kernel launches issued by this library in the calling process so far */
 long long unav_launch_count(void);
 
+/* Which kernel the calling thread's last UNAV_GEMM_TCGEN05 call launched (the tile is chosen inside the library):
+ * 0 gemm_tcgen05_kernel<64,64>, 1 <128,32>, 2 <128,64>, 3 gemm_tcgen05_pair_kernel, 4 <64,32>; -1 if none yet.
+ * bench.py uses it to attribute its per-launch CUDA-event times to the kernels ncu lists. */
+int unav_gemm_last_variant(void);
+
 /* Diagnostics for the tcgen05 kernels (scripts/gemm_phases.py): while a buffer is set, every CTA with linear index
  * below capacity_ctas writes 8 int64: GEMM {smid, clock64 at: start, setup done, first operands landed, last MMA
  * issued, accumulator ready, first epilogue warp done, all warps done}; attention {smid, start, setup done (TMEM

@@ -10,7 +10,7 @@ echo "gemm dram exit $?"
 IDX=$(python - <<'PY'
 import json
 tr = json.load(open('gpurun_out/trace.json'))
-g = [t for t in tr if t['kernel'] == 'gemm_tcgen05']
+g = [t for t in tr if t['kernel'].startswith('gemm_tcgen05')]
 k = max(range(len(g)), key=lambda i: g[i]['us'])
 print(k)
 import sys

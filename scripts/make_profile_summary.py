@@ -19,7 +19,7 @@ CLS = {'gemm_tcgen05_kernel': 'gemm_tcgen05', 'gemm_tcgen05_pair_kernel': 'gemm_
 
 
 def short(n):
-    return n.split('(')[0].replace('void ', '')
+    return n.split('(')[0].replace('void ', '').replace('(int)', '')
 
 
 def to_bytes(v, u):
@@ -45,9 +45,15 @@ for n, v, g, b in step:
     a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += v
 tot = sum(a[1] for a in agg.values())
 ev = bench['roofline']['kernel_time_shares']
+
+
+def cls(k):          # bench.py names GEMM spans after the kernel (template arguments included), the rest by wrapper
+    return k if k.startswith('gemm_tcgen05') else CLS[k.split('<')[0]]
+
+
 cagg = collections.defaultdict(float)
 for k, (n, us) in agg.items():
-    cagg[CLS[k.split('<')[0]]] += us
+    cagg[cls(k)] += us
 out = [f"# Round 1 — ncu launch list of one forward (batch 16, T=224, mode bf16x3) [{tag}]", "",
        "Command (B200, `gpurun`, `scripts/gpu_profile.sh`): `ncu --metrics gpu__time_duration.sum --clock-control none -k "
        "regex:^(gemm_|attention_|...) -c 520 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline`, run after the same "
@@ -57,12 +63,12 @@ out = [f"# Round 1 — ncu launch list of one forward (batch 16, T=224, mode bf1
        "| kernel | launches | total us | avg us | share (ncu) | share of its class (ncu) | class share (CUDA events, bench.py) |",
        "|---|---:|---:|---:|---:|---:|---:|"]
 for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    c = CLS[k.split('<')[0]]
+    c = cls(k)
     out.append(f"| `{k}` | {n} | {us:.1f} | {us / n:.1f} | {us / tot:.3f} | {cagg[c] / tot:.3f} ({c}) | {ev.get(c, 0):.4f} |")
 out.append(f"| **total** | {len(step)} | {tot:.1f} | | 1.000 | | |")
 top = bench['roofline']['kernel']
-out += ["", f"Dominant class in `bench.py`'s `roofline`: `{top}` — ncu share {cagg[top] / tot:.3f} vs CUDA-event share "
-        f"{ev[top]:.4f}: they agree.", ""]
+out += ["", f"Dominant kernel in `bench.py`'s `roofline`: `{top}` — ncu share {cagg[top] / tot:.3f} vs CUDA-event share "
+        f"{ev[top]:.4f}.", ""]
 
 # ---- DRAM bytes of every GEMM launch
 rows = [r for r in csv.reader(open('gpurun_out/gemm_dram.csv')) if len(r) > 5]
@@ -72,7 +78,7 @@ per = collections.OrderedDict()
 for r in rows[1:]:
     d = per.setdefault(r[ii], {'kernel': short(r[ki]), 'grid': r[gi]})
     d[r[mi]] = (float(r[vi].replace(',', '')), r[ui])
-gtr = [t for t in trace if t['kernel'] == 'gemm_tcgen05']
+gtr = [t for t in trace if t['kernel'].startswith('gemm_tcgen05')]
 ids = list(per)[:len(gtr)]
 with open(f'profiles/{tag}_gemm_dram.csv', 'w') as f:
     f.write('gemm_index,kernel,grid,groups x [M,N,K],algorithmic_bytes,dram_read_bytes,dram_write_bytes,duration_us\n')
@@ -92,8 +98,16 @@ out += [f"## DRAM traffic of the GEMM class (`{tag}_gemm_dram.csv`)", "",
         f"algorithmic operand+output bytes ({alg / len(gtr) / 1e6:.2f} MB per launch) — ratio {(rd + wr) / alg:.2f}: no wasted "
         f"re-reads from HBM (outputs mostly stay in the 126 MB L2 for the next kernel).  Algorithmic FLOPs {fl / 1e9:.1f} G per "
         f"forward in {tm:.0f} us (ncu, cold) = {fl / tm / 1e6:.1f} TFLOP/s; x3 MMA passes executed in bf16x3 mode.", ""]
-json.dump({"kernel": "gemm_tcgen05", "launches_per_step": len(gtr), "dram_bytes_per_launch": (rd + wr) / len(gtr),
+per_kernel = collections.defaultdict(lambda: [0, 0.0, 0.0])
+for i, t in zip(ids, gtr):
+    a = per_kernel[per[i]['kernel']]
+    a[0] += 1
+    a[1] += to_bytes(*per[i]['dram__bytes_read.sum']) + to_bytes(*per[i]['dram__bytes_write.sum'])
+    a[2] += t['bytes']
+json.dump({"class": "gemm_tcgen05", "launches_per_step": len(gtr), "dram_bytes_per_launch": (rd + wr) / len(gtr),
            "dram_read_bytes_per_step": rd, "dram_write_bytes_per_step": wr, "algorithmic_bytes_per_launch": alg / len(gtr),
+           "per_kernel": {k: {"launches": v[0], "dram_bytes_per_launch": v[1] / v[0], "algorithmic_bytes_per_launch": v[2] / v[0]}
+                          for k, v in per_kernel.items()},
            "source": f"profiles/{tag}_gemm_dram.csv (ncu, batch 16, bf16x3)"},
           open('profiles/traffic.json', 'w'), indent=1)
 

@@ -75,6 +75,7 @@ _PROTOS = {
     "unav_last_error": (C.c_char_p, []),
     "unav_check_device": (c_i, [c_i]),
     "unav_launch_count": (c_ll, []),
+    "unav_gemm_last_variant": (c_i, []),
     "unav_set_phase_trace": (c_i, [c_vp, c_i]),
     "unav_gemm": (c_i, [C.POINTER(GemmGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "unav_layernorm_rows": (c_i, [C.POINTER(LnGroup), c_i, c_i, c_i, c_f, c_i, c_i, c_vp]),

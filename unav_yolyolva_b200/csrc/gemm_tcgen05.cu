@@ -823,6 +823,10 @@ static bool use_pair(int M, int N, int K, int ngroups) {
   return tiles128 >= 296 && K >= 1024;
 }
 
+// which kernel the last tcgen05 GEMM call of this thread used (unav_gemm_last_variant): 0 <64,64>, 1 <128,32>, 2 <128,64>,
+// 3 CTA pair, 4 <64,32>; -1 before the first call / for the CUDA-core backend
+thread_local int g_last_variant = -1;
+
 int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, int op_arg, int act,
                  int res_masked, cudaStream_t stream) {
   const int op_dtype = op_base(op_arg);
@@ -857,6 +861,7 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
     if ((rc = encode_map(&p.g[i].tmW, g.W, N, K, g.ldw, bn, bk, split, halves))) return rc;
     p.g[i].epi = make_epi(g);
   }
+  g_last_variant = pair ? 3 : (bn == 128 ? (bk == 32 ? 1 : 2) : (bk == 32 ? 4 : 0));
   if (pair) return launch_pair(p, ngroups, stream);
   if (bk == 32) return bn == 64 ? launch_tc<64, 32>(p, ngroups, stream) : launch_tc<128, 32>(p, ngroups, stream);
   return bn == 64 ? launch_tc<64, 64>(p, ngroups, stream) : launch_tc<128, 64>(p, ngroups, stream);
@@ -864,3 +869,4 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
 
 }  // namespace unav
 
+extern "C" int unav_gemm_last_variant(void) { return unav::g_last_variant; }

@@ -17,6 +17,11 @@ from ._cabi import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, BF16, BF16X2, F16, F
 OP_TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, BF16X2: torch.bfloat16, F16: torch.float16, F16X2: torch.float16}
 
 
+# kernel names as ncu lists them, by unav_gemm_last_variant()
+GEMM_KERNELS = {0: "gemm_tcgen05_kernel<64, 64>", 1: "gemm_tcgen05_kernel<128, 32>", 2: "gemm_tcgen05_kernel<128, 64>",
+                3: "gemm_tcgen05_pair_kernel", 4: "gemm_tcgen05_kernel<64, 32>"}
+
+
 def with_passes(op_dtype: int, passes: int = 0) -> int:
     """op_dtype argument carrying a pass count for split operands (include/unav_b200.h UNAV_PASSES): 0 = all three."""
     return op_dtype | (passes << 8) if op_dtype in SPLIT_DTYPES else op_dtype
@@ -66,6 +71,9 @@ class _Span:
             self.b = torch.cuda.Event(enable_timing=True, **kw)
             self.a.record()
         return self
+
+    def rename(self, name):
+        self.args = (name,) + self.args[1:]
 
     def __exit__(self, *exc):
         if _TRACE is not None and exc[0] is None:
@@ -186,10 +194,12 @@ def gemm(groups: Sequence[dict], M: int, N: int, K: int, op_dtype: int, act: int
     es = 4 if op_dtype == F32 else (4 if op_dtype in SPLIT_DTYPES else 2)
     es_in = 2 if (op_dtype in SPLIT_DTYPES and passes == 1) else es     # one pass reads the hi halves only
     out_b = sum((4 if g.get("out_f32") is not None else 0) + (es if g.get("out_op") is not None else 0) for g in groups)
-    with _Span("gemm_tcgen05" if backend == GEMM_TCGEN05 else "gemm_simt", 2.0 * M * N * K * n,
-               n * (M * K + N * K) * es_in + M * N * out_b, f"{n}x[{M},{N},{K}]" + (f"p{passes}" if passes else "")):
+    with _Span("gemm_tcgen05" if backend == GEMM_TCGEN05 else "gemm_simt_kernel", 2.0 * M * N * K * n,
+               n * (M * K + N * K) * es_in + M * N * out_b, f"{n}x[{M},{N},{K}]" + (f"p{passes}" if passes else "")) as sp:
         A.check(lib.unav_gemm(arr, n, M, N, K, with_passes(op_dtype, passes), act, int(res_masked), backend, _stream()),
                 "unav_gemm")
+        if _TRACE is not None and backend == GEMM_TCGEN05:      # the library chose the tile: name the span after the kernel
+            sp.rename(GEMM_KERNELS.get(lib.unav_gemm_last_variant(), "gemm_tcgen05"))
 
 
 # -------------------------------------------------------------------------------------- LayerNorm
