@@ -139,11 +139,12 @@ def dependency_block(sd: SD, p: str, fpn_feats, fpn_masks, num_classes: int, n_h
 
 
 # ------------------------------------------------------------- multimodal_backbones.py
-def alignment(sd: SD, p: str, visual, audio, mask, num_layers=2, heads=8):
+def alignment(sd: SD, p: str, visual, audio, mask, num_layers=2, heads=8, return_cls=False):
     """libs/modeling/multimodal_backbones.py:1144-1207 (inference part only).
 
     visual [B,2048,T], audio [B,128,T], mask [B,1,T] bool -> two [B,512,T] maps.
-    The loss-only tail (:1209-1233) is not part of the hot path.
+    The loss-only tail (:1209-1233) is restated in ``oracle/losses_ref.py``; ``return_cls=True`` also returns the
+    [CLSV] / [CLST] tokens after the multiway layers ([B,1,512] each, :1189-1190, :1201-1202) that it needs.
     """
     video = visual.transpose(1, 2)
     text = audio.transpose(1, 2)
@@ -210,6 +211,8 @@ def alignment(sd: SD, p: str, visual, audio, mask, num_layers=2, heads=8):
                          (C,), sd[p + ".fc_video.3.weight"], sd[p + ".fc_video.3.bias"])
     text = F.layer_norm(F.relu(_linear(text, sd[p + ".fc_text.0.weight"], sd[p + ".fc_text.0.bias"])),
                         (C,), sd[p + ".fc_text.3.weight"], sd[p + ".fc_text.3.bias"])
+    if return_cls:
+        return video.transpose(1, 2), text.transpose(1, 2), rv[:, :1], rt[:, :1]
     return video.transpose(1, 2), text.transpose(1, 2)
 
 

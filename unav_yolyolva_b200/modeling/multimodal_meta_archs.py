@@ -9,7 +9,10 @@ decode -> per-class soft-NMS -> seconds, all device resident; nothing is compute
 there is no CPU fallback.  Deviations from the reference, all outside the detection results:
 
 * ``losses``: the reference computes the training losses even in eval (:504-509).  They are loss-only work
-   and are returned here as zero scalars under the same 7 keys.
+  (SURVEY.md §8f rank 4): when the collate dict carries the GT tensors and ``model.eval_losses`` is True (default) they are
+  evaluated on the device behind the engine's forward (``..losses.eval_losses``: batched torch ops, no host
+  synchronisation) and returned under the reference's 7 keys; otherwise (``eval_losses = False``, a dict without GT, the
+  asynchronous ``submit`` path) the 7 keys hold zero scalars.
 * a video with fewer than ``max_seg_num`` detections makes the reference's ``torch.cat`` raise (:869-873); the
   same condition raises a ``RuntimeError`` here (the padded device outputs stay available through
   ``model.engine``).
@@ -26,13 +29,12 @@ from torch import nn
 from .blocks import LayerNorm, MaskedConv1D, Scale
 from .models import make_dependency_block, make_multimodal_backbone, register_multimodal_meta_arch
 from .multimodal_backbones import Alignment
-
-LOSS_KEYS = ("cls_loss", "reg_loss", "final_loss", "inter_contr_loss", "intra_contr_loss", "score_loss_video",
-             "score_loss_audio")
+from .. import losses as _losses
+from ..losses import GT_KEYS, LOSS_KEYS
 
 
 class NCE(nn.Module):
-    """Loss-only parameter holder (:19-35)."""
+    """Loss-only parameter holder (:19-35); evaluated by ``..losses._nce``."""
 
     def __init__(self):
         super().__init__()
@@ -40,7 +42,7 @@ class NCE(nn.Module):
 
 
 class Dual_Contrastive_Loss(nn.Module):
-    """Loss-only parameter holder (:37-98); kept so reference checkpoints load strictly."""
+    """Loss-only parameter holder (:37-98); evaluated by ``..losses.losses_from_activations``."""
 
     def __init__(self, args=None):
         super().__init__()
@@ -96,8 +98,9 @@ class PtTransformerRegHead(nn.Module):
 class PendingDetections:
     """Handle returned by ``PtTransformer.submit``: detections of one step, landing in pinned host memory."""
 
-    def __init__(self, slot, event):
+    def __init__(self, slot, event, losses=None):
         self._slot, self._event = slot, event
+        self.losses = losses        # the reference's `losses` dict (0-d device tensors) if requested at submit(), else None
 
     def done(self) -> bool:
         return self._event.query()
@@ -126,6 +129,8 @@ class PtTransformer(nn.Module):
     # 16: 4.9 ms/step with one, 3.87 with two, 3.67 with three, 3.66 with four)
     streams = 3
     use_cuda_graph = True
+    # evaluate the reference's (loss-only) `losses` dict in forward() when the batch carries GT tensors
+    eval_losses = True
 
     def __init__(self, backbone_type, dependency_type, backbone_arch, scale_factor, input_dim_V, input_dim_A,
                  max_seq_len, n_head, embd_kernel_size, embd_dim, embd_with_ln, head_dim, regression_range,
@@ -220,9 +225,14 @@ class PtTransformer(nn.Module):
         if self.training:
             raise NotImplementedError("training is outside the inference hot path (SURVEY.md §2 C16)")
         plan = self.run_hot_path(video_list)
+        if self.eval_losses and all(k in video_list for k in GT_KEYS):
+            if not self.class_aware:
+                raise NotImplementedError("eval losses are implemented for class_aware=True (both reference configs)")
+            losses = _losses.eval_losses(self, plan, video_list)          # same stream, behind the forward; before the host sync below
+        else:
+            dev = self.device
+            losses = {k: torch.zeros((), device=dev) for k in LOSS_KEYS}
         results = self.collect_results(plan)
-        dev = self.device
-        losses = {k: torch.zeros((), device=dev) for k in LOSS_KEYS}
         return results, losses
 
     def _host_slot(self, B):
@@ -264,7 +274,7 @@ class PtTransformer(nn.Module):
         return plan
 
     @torch.no_grad()
-    def submit(self, video_list):
+    def submit(self, video_list, with_losses: bool = False):
         """Asynchronous form of ``forward`` for evaluation loops: enqueue the step and the device->host copy of its
         detections into pinned memory, return immediately.  ``handle.result()`` waits for that step only, so the host
         work of step j+1 (collate, upload, launch) overlaps the device work of step j:
@@ -276,7 +286,10 @@ class PtTransformer(nn.Module):
                 prev = cur
 
         Up to ``streams + 1`` handles may be outstanding (the staging buffers are a ring of ``streams + 2``); keeping
-        ``streams`` steps in flight before consuming the oldest result gives the best throughput."""
+        ``streams`` steps in flight before consuming the oldest result gives the best throughput.
+        ``with_losses=True`` also evaluates the reference's loss dict for this batch (``..losses.eval_losses``) on the plan's
+        forward stream, behind the decode; ``handle.losses`` then holds 0-d device tensors, ordered after ``handle.result()``
+        only through a device synchronisation or ``.item()`` on them."""
         if self.training:
             raise NotImplementedError("training is outside the inference hot path (SURVEY.md §2 C16)")
         B = video_list["visual"].shape[0]
@@ -285,6 +298,12 @@ class PtTransformer(nn.Module):
         # step runs on its plan's side stream; the copies of its outputs to the host follow it there
         self._submit_n += 1
         plan = self.run_hot_path(video_list, _slot=slot, _overlap_nms=True, _plan_slot=self._submit_n % max(1, self.streams))
+        losses = None
+        if with_losses:
+            if not self.class_aware:
+                raise NotImplementedError("eval losses are implemented for class_aware=True (both reference configs)")
+            with torch.cuda.stream(plan["fwd_stream"]):
+                losses = _losses.eval_losses(self, plan, video_list)
         ns = plan["nms_stream"]
         with torch.cuda.stream(ns):
             slot["segments"].copy_(plan["out_segs"], non_blocking=True)
@@ -292,7 +311,7 @@ class PtTransformer(nn.Module):
             slot["labels"].copy_(plan["out_labels"], non_blocking=True)
             slot["counts"].copy_(plan["out_counts"], non_blocking=True)
             ev = torch.cuda.Event(); ev.record(ns); slot["event"] = ev
-        return PendingDetections(slot, ev)
+        return PendingDetections(slot, ev, losses)
 
     def collect_results(self, plan):
         counts = plan["out_counts"].cpu()

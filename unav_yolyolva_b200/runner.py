@@ -75,14 +75,18 @@ def detections_to_anet(dets: torch.Tensor, video_ids: List[str]) -> Dict[str, ob
 
 
 def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluator=None, output_file=None, tb_writer=None,
-                    print_freq=2, device=None, collate=None):
+                    print_freq=2, device=None, collate=None, losses="last"):
     """Drop-in for the reference's evaluation loop (/root/reference/libs/utils/train_utils.py:380-463) with the three
     serial stages of that loop overlapped: the upload of batch j+1 (``CudaPrefetcher``, optionally with the device-side
     collate), the forward of batch j (``PtTransformer.submit``: soft-NMS and the copy of the detections to pinned host
     memory on a side stream) and the host-side bookkeeping of batch j-1.  Same arguments and return value
     ``(mAP, losses)``; ``model`` may be the bare ``PtTransformer`` or wrapped in ``nn.DataParallel`` (``model.module``).
     ``evaluator``: the reference's ``ANETdetection`` or ``unav_yolyolva_b200.utils.ANETdetection`` (matching on the
-    device).  ``ext_score_file`` post-processing is out of scope and raises."""
+    device).  ``ext_score_file`` post-processing is out of scope and raises.
+    ``losses``: the reference returns the loss dict of the LAST batch (:466; it evaluates the losses of every batch and drops
+    them).  "last" evaluates it for the last batch only, "all" for every batch (then ``loss_normalizer``, which the
+    reference also updates in eval, :637-640, follows the reference's state exactly), "none" returns zeros.  Batches without
+    GT tensors (the device-side collate does not produce them) give zeros."""
     import pickle
     import time
 
@@ -111,9 +115,33 @@ def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluato
     start = time.time()
     pending = []
     depth = max(1, getattr(net, "streams", 1))                 # steps kept in flight before the oldest result is read
-    for iter_idx, batch in enumerate(CudaPrefetcher(val_loader, dev, collate=collate, depth=depth + 1)):
+    from .losses import GT_KEYS, LOSS_KEYS
+    assert losses in ("last", "all", "none")
+    last_losses = None
+
+    flags = []                      # is_last per raw batch, in loader order (the prefetcher draws them one ahead)
+
+    def tagged(loader):             # one host batch of look-ahead on the loader side, so the device slots are not held longer
+        it = iter(loader)
+        try:
+            prev = next(it)
+        except StopIteration:
+            return
+        for cur in it:
+            flags.append(False)
+            yield prev
+            prev = cur
+        flags.append(True)
+        yield prev
+
+    for iter_idx, batch in enumerate(CudaPrefetcher(tagged(val_loader), dev, collate=collate, depth=depth + 1)):
+        is_last = flags[iter_idx]
+        want = (losses == "all" or (losses == "last" and is_last)) and all(k in batch for k in GT_KEYS)
         with torch.no_grad():
-            pending.append((net.submit(batch), batch["video_id"]))
+            h = net.submit(batch, with_losses=want)
+            pending.append((h, batch["video_id"]))
+            if h.losses is not None:
+                last_losses = h.losses
         if len(pending) > depth:
             unpack(*pending.pop(0))
         if iter_idx != 0 and iter_idx % print_freq == 0:
@@ -131,6 +159,6 @@ def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluato
         mAP = 0.0
     if tb_writer is not None:
         tb_writer.add_scalar("validation/mAP", mAP, curr_epoch)
-    losses = {k: torch.zeros((), device=dev) for k in ("cls_loss", "reg_loss", "final_loss", "inter_contr_loss",
-                                                       "intra_contr_loss", "score_loss_video", "score_loss_audio")}
-    return mAP, losses
+    if last_losses is None:
+        last_losses = {k: torch.zeros((), device=dev) for k in LOSS_KEYS}
+    return mAP, last_losses

@@ -166,6 +166,50 @@ def make_batch(B: int, T: int = 224, first_index: int = 0, num_classes: int = 10
     return batch
 
 
+def add_event_targets(batch: dict, first_index: int = 0, key_labels=None, num_classes: int = 100,
+                      regression_range=((0, 4), (4, 8), (8, 16), (16, 32), (32, 64), (64, 10000))) -> dict:
+    """Replace the placeholder GT tensors of ``make_batch`` with 1-3 seeded events per video, in the layout the reference's
+    dataset + collate produce (/root/reference/libs/datasets/data_utils.py:141-160 for ``scores`` / ``start_end`` /
+    ``m_labels``; per-point ``gt_cls_labels`` / ``gt_offsets`` = distances to the event boundaries in units of the level's
+    stride, positive where the point lies inside the event and the larger distance falls in the level's regression range).
+    Only the loss-only tail of the reference forward reads these tensors (multimodal_meta_archs.py:504-509).
+    ``key_labels[i]``, if given, is the class of video i's first event."""
+    lens = batch["lengths"]
+    B, T = batch["mask"].shape[0], batch["mask"].shape[-1]
+    pts = torch.cat([p[0] for p in batch["points"]], dim=0)                    # [Ttot, 4] = (t, lo, hi, stride)
+    Ttot = pts.shape[0]
+    scores = torch.zeros(B, T)
+    start_end = torch.zeros(B, T)
+    m_labels = torch.zeros(B, T, num_classes)
+    gt_off = torch.zeros(B, Ttot, num_classes, 2)
+    gt_cls = torch.zeros(B, Ttot, num_classes)
+    for i, L in enumerate(lens):
+        g = torch.Generator().manual_seed(99991 + first_index + i)
+        n_ev = int(torch.randint(1, 4, (1,), generator=g))
+        starts = sorted(float(x) for x in (2 + torch.rand(n_ev, generator=g) * (L - 16)))
+        for e, s in enumerate(starts):
+            dur = 4.0 + float(torch.rand(1, generator=g)) * (L / 2 - 4)
+            end = min(s + dur, L - 1.0)
+            c = int(torch.randint(0, num_classes, (1,), generator=g))
+            if e == 0 and key_labels is not None:
+                c = int(key_labels[i])
+            si, ei = int(s), int(end)
+            scores[i, si:ei] = 1
+            start_end[i, si:ei + 1] = 1
+            m_labels[i, si:ei] = 0
+            m_labels[i, si:ei, c] = 1
+            left = (pts[:, 0] - s) / pts[:, 3]
+            right = (end - pts[:, 0]) / pts[:, 3]
+            far = torch.maximum(left, right)
+            pos = (left >= 0) & (right >= 0) & (far >= pts[:, 1]) & (far <= pts[:, 2]) & (pts[:, 0] < L)
+            gt_cls[i, pos, c] = 1
+            gt_off[i, pos, c, 0] = left[pos]
+            gt_off[i, pos, c, 1] = right[pos]
+    batch.update({"scores": scores, "start_end": start_end, "m_labels": m_labels, "gt_offsets": gt_off,
+                  "gt_cls_labels": gt_cls})
+    return batch
+
+
 def make_items(B: int, first_index: int = 0, len_lo: int = 60, len_hi: int = 187) -> list:
     """The same synthetic videos as ``make_batch`` as a list of un-collated dataset items (ragged features), the
     input of the reference's ``collate_fcn`` (/root/reference/libs/datasets/data_utils.py:123) and of
