@@ -1,5 +1,6 @@
-"""BASELINE.json configs 4 and 5 as parity cases: long-sequence stress (max_seq_len = 2304, all FPN levels) and
-soft-NMS stress (100 classes, 10 100 overlapping candidates per video, low score threshold)."""
+"""BASELINE.json configs 3, 4 and 5 as parity cases: the test-split-sized workload sharded by video (size-independent
+properties at full size), long-sequence stress (max_seq_len = 2304, all FPN levels) and soft-NMS stress (100 classes,
+10 100 overlapping candidates per video, low score threshold)."""
 import os
 
 import numpy as np
@@ -181,3 +182,66 @@ def test_extreme_video_lengths_vs_oracle(cuda):
         assert k == len(r[1]), (i, k, len(r[1]))
         assert np.array_equal(plan["out_scores"][i, :k].cpu().numpy().view(np.uint32), r[1].view(np.uint32))
         assert np.array_equal(plan["out_labels"][i, :k].cpu().numpy(), r[2])
+
+
+def test_config3_full_split_sharding_properties(cuda, tmp_path):
+    """Config 3 at full size (2 158 videos) through the public sharded pipeline
+    (``runner.evaluate_split``: device collate -> prefetch -> submit -> gather).  The oracle needs ~90 s for this many videos,
+    so the full-size run is checked through properties: every video lands exactly once with K ranked detections inside
+    [0, duration]; the result does not depend on how the split is sharded / batched (two virtual ranks with strided shards
+    and a different batch size reproduce the unsharded run BIT for bit); a sample of 32 videos equals the oracle-checked
+    synchronous ``model(batch)`` path; the device mAP of the gathered detections is the same for both runs."""
+    import json
+    from unav_yolyolva_b200 import runner
+    from unav_yolyolva_b200.utils import ANETdetection
+    N = 2158
+    model = make_multimodal_meta_arch("LocPointTransformer", **default_model_cfg())
+    model.load_state_dict(synth.trained_like_state_dict(), strict=True)
+    model = model.to(cuda).eval()
+    cache = {}
+
+    def load(idxs):
+        for i in idxs:
+            if i not in cache:
+                cache[i] = synth.make_items(1, i)[0]
+        return [cache[i] for i in idxs]
+
+    dets, valid = runner.evaluate_split(model, N, load, batch_size=16)
+    torch.cuda.synchronize()
+    assert dets.shape == (N, 100, 4) and bool(valid.all())
+    d = dets.cpu()
+    dur = torch.tensor([cache[i]["duration"] for i in range(N)])
+    assert bool((d[..., 2] > 0).all()), "every video keeps max_seg_num detections on this workload"
+    assert bool((d[:, :-1, 2] >= d[:, 1:, 2]).all()), "ranked by score"
+    assert bool((d[..., 0] >= 0).all()) and bool((d[..., 1] <= dur[:, None] + 1e-6).all()) and bool((d[..., 0] <= d[..., 1]).all())
+    lab = d[..., 3]
+    assert bool((lab == lab.round()).all()) and int(lab.min()) >= 0 and int(lab.max()) < 100
+    # two virtual ranks, strided shards, another batch size: same bits
+    parts = []
+    for r in range(2):
+        idx = runner.shard_indices(N, r, 2)
+        parts.append((idx, runner.run_shard(model, idx, load, batch_size=12)))
+    torch.cuda.synchronize()
+    merged = torch.zeros_like(dets)
+    for idx, loc in parts:
+        merged[torch.tensor(idx, device=cuda)] = loc
+    assert torch.equal(merged.view(torch.int32), dets.view(torch.int32))
+    # a sample against the synchronous path that the oracle tests pin (tests/test_gpu_model.py)
+    for first in (0, 1071, 2142):
+        res, _ = model(synth.make_batch(16, 224, first_index=first, with_gt=False))
+        want = runner.pack_detections(res["segments"], res["scores"], res["labels"])
+        assert torch.equal(want.view(torch.int32), dets[first:first + 16].view(torch.int32))
+    # mAP of the gathered detections with the device evaluator: GT = detections ranked 1 / 4 / 9 of every 4th video, jittered
+    db = {}
+    for v in range(0, N, 4):
+        db[cache[v]["video_id"]] = {"subset": "test", "duration": cache[v]["duration"], "annotations": [
+            {"segment": [float(d[v, r, 0]), float(d[v, r, 1]) * 1.05 + 0.1], "label_id": int(d[v, r, 3]), "label": str(int(d[v, r, 3]))}
+            for r in (0, 3, 8)]}
+    jf = os.path.join(tmp_path, "gt.json")
+    json.dump({"database": db}, open(jf, "w"))
+    ev = ANETdetection(jf, "test", tiou_thresholds=np.linspace(0.1, 0.9, 9), device=cuda)
+    sel = list(range(0, N, 4))
+    ids = [cache[v]["video_id"] for v in sel]
+    _, m1 = ev.evaluate(runner.detections_to_anet(dets[sel], ids), verbose=False)
+    _, m2 = ev.evaluate(runner.detections_to_anet(merged[sel], ids), verbose=False)
+    assert m1 == m2 and 0.2 < m1 <= 1.0

@@ -137,6 +137,7 @@ class DeviceCollator:
         self.pad = float(padding_val)
         self._host: dict = {}                                   # slot -> pinned staging (header + feature blocks)
         self._dev: dict = {}                                    # slot -> device staging + padded outputs
+        self._uploaded: dict = {}                               # slot -> event: the staging buffer's last upload has been read
 
     def _buffers(self, slot: int, B: int, Cv: int, Ca: int, T: int, nfloat: int):
         hdr = 4 * B                                                    # offsets (2 x i64 per video = 4 floats) per modality ...
@@ -169,6 +170,8 @@ class DeviceCollator:
             T = (max_len + (st - 1)) // st * st
         nfloat = sum(lens) * (Cv + Ca)
         h, d = self._buffers(slot, B, Cv, Ca, T, nfloat)
+        if slot in self._uploaded:                                     # the host must not rewrite pinned memory a copy still reads
+            self._uploaded[slot].synchronize()
         # header: [offsets_v i64 x B | offsets_a i64 x B | lens i32 x B], then the feature blocks
         hb = h.view(torch.uint8)
         off_v = hb[0:8 * B].view(torch.int64)
@@ -191,6 +194,9 @@ class DeviceCollator:
             pos += n
         st = d["stage"]
         st[:pos].copy_(h[:pos], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._uploaded[slot] = ev
         sb = st.view(torch.uint8)
         d_off_v, d_off_a, d_ln = sb[0:8 * B].view(torch.int64), sb[8 * B:16 * B].view(torch.int64), sb[16 * B:20 * B].view(torch.int32)
         mask_u8 = d["mask"].view(B, T)

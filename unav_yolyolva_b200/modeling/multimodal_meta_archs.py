@@ -98,8 +98,11 @@ class PtTransformerRegHead(nn.Module):
 class PendingDetections:
     """Handle returned by ``PtTransformer.submit``: detections of one step, landing in pinned host memory."""
 
-    def __init__(self, slot, event, losses=None):
+    def __init__(self, slot, event, losses=None, plan=None):
         self._slot, self._event = slot, event
+        # the engine plan of this step: device consumers may chain work on ``plan["nms_stream"]`` and read ``plan["out_*"]``
+        # there (valid until the plan's next step, which is enqueued behind it on the same stream)
+        self.plan = plan
         self.losses = losses        # the reference's `losses` dict (0-d device tensors) if requested at submit(), else None
 
     def done(self) -> bool:
@@ -311,7 +314,7 @@ class PtTransformer(nn.Module):
             slot["labels"].copy_(plan["out_labels"], non_blocking=True)
             slot["counts"].copy_(plan["out_counts"], non_blocking=True)
             ev = torch.cuda.Event(); ev.record(ns); slot["event"] = ev
-        return PendingDetections(slot, ev, losses)
+        return PendingDetections(slot, ev, losses, plan)
 
     def collect_results(self, plan):
         counts = plan["out_counts"].cpu()

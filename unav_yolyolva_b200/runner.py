@@ -162,3 +162,56 @@ def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluato
     if last_losses is None:
         last_losses = {k: torch.zeros((), device=dev) for k in LOSS_KEYS}
     return mAP, last_losses
+
+
+def run_shard(model, indices: List[int], load_items, batch_size: int = 16, device=None) -> torch.Tensor:
+    """Detections of the videos ``indices`` (this rank's shard) as one device tensor [len(indices), K, 4]
+    (seg0, seg1, score, label), through the overlapped public pipeline: ``load_items(list_of_indices)`` returns un-collated
+    dataset items (/root/reference/libs/datasets/datasets.py:28-46 layout), ``DeviceCollator`` pads them on the device,
+    ``CudaPrefetcher`` uploads batch j+1 under the forward of batch j, ``PtTransformer.submit`` keeps ``model.streams``
+    batches in flight.  Videos with fewer than K detections keep zero rows (score 0)."""
+    from .ingest import CudaPrefetcher, DeviceCollator
+    net = model.module if hasattr(model, "module") else model
+    dev = torch.device(device) if device is not None else net.device
+    K_ = net.test_max_seg_num
+    out = torch.zeros(len(indices), K_, 4, dtype=torch.float32, device=dev)
+    chunks = [indices[i:i + batch_size] for i in range(0, len(indices), batch_size)]
+    depth = max(1, getattr(net, "streams", 1))
+    cur = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(cur)                                       # `out` is zero-filled on the caller's stream
+    ar = torch.arange(K_, device=dev)[None]
+    pending, tails, row = [], {}, 0
+    loader = (load_items(c) for c in chunks)
+    coll = DeviceCollator(net.max_seq_len, dev, max_div_factor=net.max_div_factor)
+    for j, batch in enumerate(CudaPrefetcher(loader, dev, collate=coll, depth=depth + 1)):
+        n = len(chunks[j])
+        with torch.no_grad():
+            h = net.submit(batch)
+            P = h.plan
+            ns = P["nms_stream"]
+            with torch.cuda.stream(ns):                     # device -> device, behind this step's soft-NMS
+                ns.wait_event(ready)
+                d = pack_detections(P["out_segs"], P["out_scores"], P["out_labels"])
+                out[row:row + n] = d * (ar < P["out_counts"][:, None])[..., None]
+                ev = torch.cuda.Event()
+                ev.record(ns)
+                tails[id(ns)] = ev
+        pending.append(h)
+        row += n
+        if len(pending) > depth:
+            pending.pop(0)._event.synchronize()             # bounds the host's lead over the device
+    for ev in tails.values():
+        cur.wait_event(ev)
+    return out
+
+
+def evaluate_split(model, n_videos: int, load_items, batch_size: int = 16, device=None):
+    """BASELINE.json config 3: a whole split sharded by video index over the ranks of the current process group (or one
+    process), one all-gather of the detections.  Returns (detections [n_videos, K, 4] ordered by video index, valid [n_videos])
+    on every rank; rank 0 hands them to ``ANETdetection.evaluate`` via ``detections_to_anet``."""
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    idx = shard_indices(n_videos, rank, world)
+    local = run_shard(model, idx, load_items, batch_size, device)
+    return gather_detections(local, torch.tensor(idx, dtype=torch.int64, device=local.device), n_videos)
