@@ -138,6 +138,29 @@ def test_tcgen05_cta_pair_kernel(cuda, monkeypatch, op, M, N, Kd, groups):
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("op", [K.BF16X2, K.BF16, K.F16X2])
+@pytest.mark.parametrize("M,N,Kd,groups", [(3584, 512, 512, 2), (7168, 384, 1536, 1), (2000, 1280, 224, 1), (4900, 512, 520, 1)])
+def test_tcgen05_cta_pair_kernel_128_wide(cuda, monkeypatch, op, M, N, Kd, groups):
+    """cta_group::2 kernel with 256 x 128 tiles per CTA pair (each CTA stages 64 rows of W): ragged M / K, N not a multiple
+    of 256, grouped launches, full epilogue; the SAME bits as the one-CTA kernel.  Experiment knob only (UNAV_TC_PAIR=2): no
+    gain on the step and it hangs when several engine plans are in flight, so no policy selects it."""
+    from unav_yolyolva_b200 import _cabi
+    monkeypatch.setenv("UNAV_TC_PAIR", "2")
+    _run(cuda, M, N, Kd, op, K.GEMM_TCGEN05, full_epi=True, act=K.ACT_GELU, groups=groups)
+    g = torch.Generator().manual_seed(10)
+    A, W = torch.randn(M, Kd, generator=g), torch.randn(N, Kd, generator=g) / Kd ** 0.5
+    Aop, Wop = K.pack_operand(A.to(cuda), op), K.pack_operand(W.to(cuda), op)
+    outs = []
+    for pair in ("2", "0"):
+        monkeypatch.setenv("UNAV_TC_PAIR", pair)
+        o = [torch.empty(M, N, device=cuda) for _ in range(groups)]
+        K.gemm([{"A": Aop, "W": Wop, "out_f32": oi} for oi in o], M, N, Kd, op, K.ACT_NONE, False, K.GEMM_TCGEN05)
+        outs.append((o, _cabi.load(op).unav_gemm_last_variant()))
+    torch.cuda.synchronize()
+    assert outs[0][1] == 5 and outs[1][1] in (0, 1, 2, 4)
+    assert all(torch.equal(a, b) for a, b in zip(outs[0][0], outs[1][0]))
+
+
 def test_library_rejects_the_other_builds_dtypes(cuda):
     """Each build serves only its own half type: the BF16 library must refuse F16 operands instead of misreading them."""
     from unav_yolyolva_b200 import _cabi

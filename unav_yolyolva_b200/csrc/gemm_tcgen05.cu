@@ -546,8 +546,12 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc,
 constexpr int P2_BK = 32;
 constexpr int P2_PART = 128 * P2_BK * 2;     // one 128-row operand part of a stage: 8 KB
 
+// PN = columns of the pair's tile: 256 (each CTA stages 128 rows of W) or 128 (64 rows of W per CTA: the CTA count of the
+// 128 x 128 one-CTA grid with 3/4 of its shared-memory fill and 3/4 of its MMA operand reads).
+template <int PN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 2)
 gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
+  constexpr int W_PART = (PN / 2) * P2_BK * 2;          // this CTA's half of one W part of a stage
   extern __shared__ uint8_t smem_raw[];
   const TcGroup& g = p.g[blockIdx.z];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -555,7 +559,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int NS = p.stages;
   const int nparts = p.nseg > 1 ? 2 : 1;
-  const uint32_t stage_bytes = 2u * nparts * P2_PART;                 // [A parts | W parts]
+  const uint32_t stage_bytes = nparts * (P2_PART + W_PART);           // [A parts | W parts]
   const uint32_t w_off = nparts * P2_PART;
   const uint32_t bar_base = base + stage_bytes * NS;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -564,8 +568,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
   const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 1);
 
   const int m0 = (blockIdx.x >> 1) * 256 + static_cast<int>(rank) * 128;      // this CTA's accumulator rows
-  const int n0 = blockIdx.y * 256;                                            // the pair's columns
-  const int wn0 = n0 + static_cast<int>(rank) * 128;                          // this CTA's half of W
+  const int n0 = blockIdx.y * PN;                                             // the pair's columns
+  const int wn0 = n0 + static_cast<int>(rank) * (PN / 2);                     // this CTA's half of W
   const int nkb = (p.K + P2_BK - 1) / P2_BK;
 
   if (warp == 0 && lane == 0) {
@@ -576,7 +580,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(PN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -605,7 +609,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       // ===== MMA issuer (rank 0 only) =====
-      const uint32_t idesc = make_idesc(256, 256, kHalfF16);
+      const uint32_t idesc = make_idesc(256, PN, kHalfF16);
       for (int it = 0; it < nkb; ++it) {
         const int s = it % NS;
         const uint32_t ph = (it / NS) & 1;
@@ -617,7 +621,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
         for (int seg = 0; seg < 3; ++seg) {
           if (seg >= p.nseg) break;
           const uint64_t adesc = make_smem_desc<P2_BK>(sa + (seg == 1 ? P2_PART : 0));
-          const uint64_t bdesc = make_smem_desc<P2_BK>(sa + w_off + (seg == 2 ? P2_PART : 0));
+          const uint64_t bdesc = make_smem_desc<P2_BK>(sa + w_off + (seg == 2 ? W_PART : 0));
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             tc_mma_f16_pair(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || seg > 0 || k > 0) ? 1u : 0u);
@@ -628,11 +632,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
     }
     __syncwarp();
   } else {
-    // ===== epilogue (both CTAs): two 128-column halves of this CTA's 128 x 256 accumulator =====
+    // ===== epilogue (both CTAs): the 128-column halves of this CTA's 128 x PN accumulator =====
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)));
-    for (int hf = 0; hf < 2; ++hf) {
+    for (int hf = 0; hf < PN / 128; ++hf) {
       if (n0 + hf * 128 >= p.N) break;
       epilogue_tile<128>(p, g, tmem_base + hf * 128, m0, n0 + hf * 128, warp, lane, stg, p.M);
       __syncwarp();
@@ -642,7 +646,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
   cluster_sync_all();            // the peer may still read this CTA's smem / signal its barriers until both are done
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(PN) : "memory");
   }
 }
 
@@ -783,11 +787,12 @@ static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
   return finish_launch("gemm_tcgen05");
 }
 
+template <int PN>
 static int launch_pair(TcParams& p, int ngroups, cudaStream_t stream) {
   static bool attr_set = false;
   constexpr int MAX_SMEM = 110 * 1024;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<PN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tcgen05_pair): %s", cudaGetErrorString(e));
       return static_cast<int>(e);
@@ -795,7 +800,7 @@ static int launch_pair(TcParams& p, int ngroups, cudaStream_t stream) {
     attr_set = true;
   }
   const int nparts = p.nseg > 1 ? 2 : 1;
-  const int per_stage = 2 * nparts * P2_PART;
+  const int per_stage = nparts * (P2_PART + (PN / 2) * P2_BK * 2);
   const int nkb = (p.K + P2_BK - 1) / P2_BK;
   int stages = (100 * 1024) / per_stage;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -804,8 +809,8 @@ static int launch_pair(TcParams& p, int ngroups, cudaStream_t stream) {
   while (stages * per_stage < 128 * (128 + 4) * 4) ++stages;      // room for the epilogue staging tile
   p.stages = stages;
   p.once = p.nseg > 1 ? 1 : 0;
-  dim3 grid(2 * ((p.M + 255) / 256), (p.N + 255) / 256, ngroups);
-  launch_pdl(gemm_tcgen05_pair_kernel, dim3(grid), dim3(TC_THREADS), stages * per_stage + 256 + 1024, stream, p);
+  dim3 grid(2 * ((p.M + 255) / 256), (p.N + PN - 1) / PN, ngroups);
+  launch_pdl(gemm_tcgen05_pair_kernel<PN>, dim3(grid), dim3(TC_THREADS), stages * per_stage + 256 + 1024, stream, p);
   count_launch();
   return finish_launch("gemm_tcgen05_pair");
 }
@@ -813,18 +818,19 @@ static int launch_pair(TcParams& p, int ngroups, cudaStream_t stream) {
 // CTA pairs where they pay (scripts/gemm_probe.py, UNAV_TC_PAIR=0/1): grids of at least two 128 x 128 CTAs per SM with a
 // long k-loop — [7056,1024,3072] 134 -> 108 us (410 TFLOP/s algorithmic, 1230 executed), 2x[7056,512,1536] 77 -> 65 us.  The
 // K = 512 shapes are epilogue-bound and gain nothing; grids of ~1.5 CTAs per SM lose the second resident CTA's overlap.
-static bool use_pair(int M, int N, int K, int ngroups) {
+// Returns the pair tile width: 0 (one-CTA kernels), 256 or 128.
+static int use_pair(int M, int N, int K, int ngroups) {
   int v = -1;
-  if (const char* env = getenv("UNAV_TC_PAIR")) v = atoi(env);       // experiment knob: 0 never, 1 whenever possible
-  if (N % 256 != 0 || M < 256) return false;
-  if (v == 0) return false;
-  if (v == 1) return true;
-  const long long tiles128 = static_cast<long long>((M + 127) / 128) * (N / 128) * ngroups;
-  return tiles128 >= 296 && K >= 1024;
+  if (const char* env = getenv("UNAV_TC_PAIR")) v = atoi(env);       // experiment knob: 0 never, 1 256-wide whenever possible,
+  if (M < 256 || v == 0) return 0;                                   // 2 also 128-wide pairs for the other full grids
+  const long long tiles128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128) * ngroups;
+  if (N % 256 == 0 && (v == 1 || (tiles128 >= 296 && K >= 1024))) return 256;
+  if (v == 2 && N % 128 == 0 && tiles128 >= 148) return 128;
+  return 0;
 }
 
 // which kernel the last tcgen05 GEMM call of this thread used (unav_gemm_last_variant): 0 <64,64>, 1 <128,32>, 2 <128,64>,
-// 3 CTA pair, 4 <64,32>; -1 before the first call / for the CUDA-core backend
+// 3 CTA pair 256 wide, 4 <64,32>, 5 CTA pair 128 wide; -1 before the first call / for the CUDA-core backend
 thread_local int g_last_variant = -1;
 
 int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, int op_arg, int act,
@@ -840,9 +846,9 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
   if (conv_T > 0)
     UNAV_REQUIRE(M % conv_T == 0 && K % 3 == 0 && (K / 3) % 32 == 0, "gemm_tcgen05: implicit conv needs M %% T == 0 and Cin %% 32 == 0");
   p.conv_T = conv_T; p.conv_cin = conv_T > 0 ? K / 3 : 0; p.conv_tiles = conv_T > 0 ? (conv_T + TC_BM - 1) / TC_BM : 0;
-  const bool pair = conv_T == 0 && use_pair(M, N, K, ngroups);
+  const int pair = conv_T == 0 ? use_pair(M, N, K, ngroups) : 0;
   const TcChoice ch = choose_tile(M, N, K, ngroups, p.nseg);
-  const int bn = pair ? 128 : ch.bn, bk = pair ? P2_BK : (ch.sched == 2 ? 32 : 64);
+  const int bn = pair ? pair / 2 : ch.bn, bk = pair ? P2_BK : (ch.sched == 2 ? 32 : 64);
   p.once = ch.sched ? 1 : 0;
   for (int i = 0; i < ngroups; ++i) {
     const UnavGemmGroup& g = groups[i];
@@ -861,8 +867,9 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
     if ((rc = encode_map(&p.g[i].tmW, g.W, N, K, g.ldw, bn, bk, split, halves))) return rc;
     p.g[i].epi = make_epi(g);
   }
-  g_last_variant = pair ? 3 : (bn == 128 ? (bk == 32 ? 1 : 2) : (bk == 32 ? 4 : 0));
-  if (pair) return launch_pair(p, ngroups, stream);
+  g_last_variant = pair == 256 ? 3 : pair == 128 ? 5 : (bn == 128 ? (bk == 32 ? 1 : 2) : (bk == 32 ? 4 : 0));
+  if (pair == 256) return launch_pair<256>(p, ngroups, stream);
+  if (pair == 128) return launch_pair<128>(p, ngroups, stream);
   if (bk == 32) return bn == 64 ? launch_tc<64, 32>(p, ngroups, stream) : launch_tc<128, 32>(p, ngroups, stream);
   return bn == 64 ? launch_tc<64, 64>(p, ngroups, stream) : launch_tc<128, 64>(p, ngroups, stream);
 }
