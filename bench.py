@@ -402,6 +402,18 @@ def main():
             roof["algorithmic_bytes_per_launch"] = a[2] / a[3]
     except Exception:                                   # noqa: BLE001
         pass
+    # every kernel class against the roofline that bounds it (north_star: "% roofline / kernel"): algorithmic FLOPs and bytes
+    # of the class (kernels.py spans) over its summed launch time in the traced replay; bound = whichever of tensor / HBM
+    # the class sits closer to (small-M problems report max(flops / peak, bytes / bandwidth))
+    per_kernel = {}
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        sec = v[0] / 1e3
+        tf, gbs = v[1] / sec / 1e12, v[2] / sec / 1e9
+        ft, fb = tf / peaks["tf_sustained"], gbs / peaks["hbm_gbs"]
+        per_kernel[k] = {"launches": v[3] // len(passes), "us_per_step": round(v[0] / len(passes) * 1e3, 1), "share": shares[k],
+                         "tflops": round(tf, 2), "gbs": round(gbs, 1), "bound": "tensor" if ft >= fb else "hbm",
+                         "frac": round(max(ft, fb), 4)}
+    roof["per_kernel"] = per_kernel
     gemm_cls = [k for k in agg if k.startswith("gemm_")]
     roof["gemm_class"] = {"share_of_step": round(sum(shares[k] for k in gemm_cls), 4),
                           "tflops_algorithmic": sum(agg[k][1] for k in gemm_cls) / (sum(agg[k][0] for k in gemm_cls) / 1e3) / 1e12,

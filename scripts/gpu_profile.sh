@@ -22,3 +22,16 @@ ncu --set full --clock-control none --import-source on -k 'regex:^gemm_tcgen05' 
 echo "full capture exit $?"
 ncu --set full --clock-control none --import-source on -k "regex:^dwconv_ln" -c 3 -o gpurun_out/prof_attn_dw -f $CMD > gpurun_out/ncu4.log 2>&1
 echo "attn/dw capture exit $?"
+# the kernel bench.py's roofline names as dominant (gemm_tcgen05_kernel<128, 32>): its heaviest launch, and one LayerNorm launch
+IDX2=$(python - <<'PY'
+import json
+tr = json.load(open('gpurun_out/trace.json'))
+g = [t for t in tr if t['kernel'].startswith('gemm_tcgen05')]
+c = [i for i in range(len(g)) if g[i]['kernel'] == 'gemm_tcgen05_kernel<128, 32>']
+print(max(c, key=lambda i: g[i]['us']) if c else 0)
+PY
+)
+timeout 300 ncu --set full --clock-control none --import-source on -k 'regex:^gemm_tcgen05' -s $IDX2 -c 1 -o gpurun_out/prof_gemm_dom -f $CMD > gpurun_out/ncu5.log 2>&1
+echo "dominant-kernel capture (gemm launch $IDX2) exit $?"
+timeout 300 ncu --set full --clock-control none --import-source on -k 'regex:^ln_rows' -s 4 -c 1 -o gpurun_out/prof_ln -f $CMD > gpurun_out/ncu6.log 2>&1
+echo "ln_rows capture exit $?"

@@ -135,7 +135,9 @@ KEEP = ['Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dra
         'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
         'smsp__issue_active.avg.pct_of_peak_sustained_active']
 for rep, name in (('gpurun_out/prof_gemm_top.ncu-rep', f'{tag}_gemm_top_ncu_full.csv'),
-                  ('gpurun_out/prof_attn_dw.ncu-rep', f'{tag}_attention_dwconv_ncu_full.csv')):
+                  ('gpurun_out/prof_attn_dw.ncu-rep', f'{tag}_attention_dwconv_ncu_full.csv'),
+                  ('gpurun_out/prof_gemm_dom.ncu-rep', f'{tag}_gemm_dominant_ncu_full.csv'),
+                  ('gpurun_out/prof_ln.ncu-rep', f'{tag}_ln_rows_ncu_full.csv')):
     try:
         hh, uu, vals = raw_page(rep)
     except Exception as e:  # noqa
