@@ -57,6 +57,38 @@ def test_layernorm_rows_all_outputs(cuda, C, op):
     assert (_read_op(oi, 3 * C, op) - col).abs().max() < tol
 
 
+@pytest.mark.parametrize("C", [256, 512, 1024, 384])
+@pytest.mark.parametrize("act", [K.ACT_NONE, K.ACT_RELU, K.ACT_GELU, K.ACT_SILU])
+def test_layernorm_rows_exact_width_kernels_same_bits(cuda, monkeypatch, C, act):
+    """The exact-width / compile-time-activation instantiations (C = 256, 512, 1024) write the same bits as the generic
+    kernel (UNAV_LN_GENERIC=1) on every output; C = 384 takes the generic kernel either way."""
+    g = torch.Generator().manual_seed(C + act)
+    nseg, T = 5, 23
+    M = nseg * T
+    x = (torch.randn(M, C, generator=g) * 2 + 0.3).to(cuda)
+    add = torch.randn(M, C, generator=g).to(cuda)
+    w, b = (torch.rand(C, generator=g) + 0.5).to(cuda), (torch.randn(C, generator=g) * 0.1).to(cuda)
+    post = torch.randn(T, C, generator=g).to(cuda)
+    mask = (torch.rand(M, generator=g) > 0.3).to(torch.uint8).to(cuda)
+    edge = _edges(nseg, T).to(cuda)
+    outs = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("UNAV_LN_GENERIC", "1")
+        else:
+            monkeypatch.delenv("UNAV_LN_GENERIC", raising=False)
+        of, oo, oi = torch.zeros(M, C, device=cuda), K.new_operand(M, C, K.BF16X2, cuda), K.new_operand(M, 3 * C, K.BF16X2, cuda)
+        K.layernorm_rows([{"x": x, "add": add, "w": w, "b": b, "post": post, "post_rows": T, "rowmask": mask, "edge": edge,
+                           "out_f32": of, "out_op": oo, "out_im2col": oi}], M, C, K.BF16X2, act=act)
+        o2 = torch.zeros(M, C, device=cuda)
+        K.layernorm_rows([{"x": x, "w": w, "b": b, "out_f32": o2}], M, C, K.F32, act=act)
+        outs.append((of, oo, oi, o2))
+    torch.cuda.synchronize()
+    for a, b_ in zip(*outs):
+        assert torch.equal(a.view(torch.int16) if a.dtype == torch.bfloat16 else a.view(torch.int32),
+                           b_.view(torch.int16) if b_.dtype == torch.bfloat16 else b_.view(torch.int32))
+
+
 def test_layernorm_rows_seg_mapping_and_groups(cuda):
     g = torch.Generator().manual_seed(9)
     B, T, C = 3, 20, 512

@@ -17,25 +17,30 @@ struct LnParams {
   float eps;
 };
 
-__global__ void __launch_bounds__(128)
-ln_rows_kernel(const __grid_constant__ LnParams p) {
-  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
-  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
+// NV = float4 chunks per lane.  EXACT: C == 128 * NV, no column predicates (the widths the hot path uses: 256, 512, 1024);
+// otherwise the generic MAXV-chunk loop with `c < C` tests.  ACT >= 0: compile-time activation; -1: p.act at run time.
+// The arithmetic (summation order, rounding) is the same in every instantiation, so the results are bit-identical.
+// History (profiles/r01f_ln_rows_ncu_full.csv): the single generic kernel executed 836 warp instructions per 512-wide row
+// (8 predicated chunks, run-time activation / output dispatch per chunk) at 82 registers = 5 CTAs of 128 threads per SM,
+// 22 us for [7168, 512]: issue- and latency-bound at 1.2 TB/s.
+template <int NV, int ACT, bool EXACT>
+__device__ __forceinline__ void ln_rows_body(const LnParams& p) {
   const UnavLnGroup& g = p.g[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const long long r = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (r >= p.M) return;
-  const int C = p.C;
+  const int C = EXACT ? NV * 128 : p.C;
+  const int act = ACT >= 0 ? ACT : p.act;
   long long src = r;
   if (g.x_seg_rows > 0) src = (r / g.x_seg_rows) * g.x_seg_stride + (r % g.x_seg_rows) + g.x_row_off;
   const float* xr = g.x + src * g.ldx;
   const float* ar = g.add ? g.add + r * g.ldadd : nullptr;
-  float4 v[MAXV];
+  float4 v[NV];
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
+  for (int j = 0; j < NV; ++j) {
     const int c = (j * 32 + lane) * 4;
-    if (c < C) {
+    if (EXACT || c < C) {
       float4 t = *reinterpret_cast<const float4*>(xr + c);
       if (ar) {
         const float4 a = *reinterpret_cast<const float4*>(ar + c);
@@ -48,9 +53,9 @@ ln_rows_kernel(const __grid_constant__ LnParams p) {
   const float mean = warp_sum(s) / C;
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
+  for (int j = 0; j < NV; ++j) {
     const int c = (j * 32 + lane) * 4;
-    if (c < C) {
+    if (EXACT || c < C) {
       v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
       q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
     }
@@ -60,37 +65,53 @@ ln_rows_kernel(const __grid_constant__ LnParams p) {
   const float* pr = g.post ? g.post + static_cast<long long>(r % g.post_rows) * C : nullptr;
   const uint8_t edge = g.edge ? g.edge[r] : 0;
   const size_t es = op_elem_size(p.op_dtype);
+  float* f32_row = g.out_f32 ? g.out_f32 + r * g.ld_f32 : nullptr;
   char* op_row = g.out_op ? reinterpret_cast<char*>(g.out_op) + static_cast<size_t>(r) * g.ld_op * es : nullptr;
   char* ic_row = g.out_im2col ? reinterpret_cast<char*>(g.out_im2col) + static_cast<size_t>(r) * g.ld_im2col * es : nullptr;
   const long long ic_rowbytes = g.ld_im2col * static_cast<long long>(es);
+  const long long sp_op = g.ld_op / 2, sp_ic = g.ld_im2col / 2;
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
+  for (int j = 0; j < NV; ++j) {
     const int c = (j * 32 + lane) * 4;
-    if (c < C) {
+    if (EXACT || c < C) {
       const float4 w = *reinterpret_cast<const float4*>(g.w + c);
       const float4 b = *reinterpret_cast<const float4*>(g.b + c);
       float4 y;
-      y.x = apply_act(v[j].x * rstd * w.x + b.x, p.act);
-      y.y = apply_act(v[j].y * rstd * w.y + b.y, p.act);
-      y.z = apply_act(v[j].z * rstd * w.z + b.z, p.act);
-      y.w = apply_act(v[j].w * rstd * w.w + b.w, p.act);
+      y.x = apply_act(v[j].x * rstd * w.x + b.x, act);
+      y.y = apply_act(v[j].y * rstd * w.y + b.y, act);
+      y.z = apply_act(v[j].z * rstd * w.z + b.z, act);
+      y.w = apply_act(v[j].w * rstd * w.w + b.w, act);
       if (pr) {
         const float4 t = *reinterpret_cast<const float4*>(pr + c);
         y.x += t.x * mk; y.y += t.y * mk; y.z += t.z * mk; y.w += t.w * mk;
       }
-      if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + r * g.ld_f32 + c) = y;
-      if (op_row) store_op4(op_row, p.op_dtype, c, g.ld_op / 2, y);
+      if (f32_row) *reinterpret_cast<float4*>(f32_row + c) = y;
+      if (op_row) store_op4(op_row, p.op_dtype, c, sp_op, y);
       if (ic_row) {
-        const long long sp = g.ld_im2col / 2;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        store_op4(ic_row, p.op_dtype, C + c, sp, y);
-        if (edge & 1) store_op4(ic_row, p.op_dtype, c, sp, z);
-        else store_op4(ic_row - ic_rowbytes, p.op_dtype, 2 * C + c, sp, y);
-        if (edge & 2) store_op4(ic_row, p.op_dtype, 2 * C + c, sp, z);
-        else store_op4(ic_row + ic_rowbytes, p.op_dtype, c, sp, y);
+        store_op4(ic_row, p.op_dtype, C + c, sp_ic, y);
+        if (edge & 1) store_op4(ic_row, p.op_dtype, c, sp_ic, z);
+        else store_op4(ic_row - ic_rowbytes, p.op_dtype, 2 * C + c, sp_ic, y);
+        if (edge & 2) store_op4(ic_row, p.op_dtype, 2 * C + c, sp_ic, z);
+        else store_op4(ic_row + ic_rowbytes, p.op_dtype, c, sp_ic, y);
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(128)
+ln_rows_kernel(const __grid_constant__ LnParams p) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
+  ln_rows_body<MAXV, -1, false>(p);
+}
+
+template <int NV, int ACT>
+__global__ void __launch_bounds__(128, NV == 8 ? 6 : 8)       // <= 64 registers (NV <= 4) / 80: 8 / 6 CTAs per SM instead of 5
+ln_rows_exact_kernel(const __grid_constant__ LnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  ln_rows_body<NV, ACT, true>(p);
 }
 
 // =============================================================================================
@@ -315,29 +336,40 @@ struct CopyParams {
   int op_dtype;
 };
 
-__global__ void __launch_bounds__(256)
-rowcopy_kernel(const __grid_constant__ CopyParams p) {
-  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
-  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
-  const UnavCopyJob& jb = p.j[blockIdx.y];
-  const int cv = jb.C / 4;
-  const long long per_row = static_cast<long long>(jb.ntaps) * cv;
-  const long long total = static_cast<long long>(jb.nseg) * jb.seg_len_out * per_row;
-  const size_t es = op_elem_size(p.op_dtype);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = i / per_row;
-    const int rem = static_cast<int>(i % per_row);
-    const int tap = rem / cv, c = (rem % cv) * 4;
-    const int seg = static_cast<int>(row / jb.seg_len_out), t = static_cast<int>(row % jb.seg_len_out);
+// IdxT: index arithmetic type.  Every job of the hot path has far fewer than 2^31 float4 elements, and the three 64-bit
+// divide / modulo pairs per element were most of the kernel's instructions; 64-bit indices remain for larger jobs.
+template <typename IdxT>
+__device__ __forceinline__ void rowcopy_body(const UnavCopyJob& jb, int op_dtype, long long total_ll) {
+  const IdxT cv = jb.C / 4;
+  const IdxT per_row = static_cast<IdxT>(jb.ntaps) * cv;
+  const IdxT total = static_cast<IdxT>(total_ll);
+  const IdxT seg_out = static_cast<IdxT>(jb.seg_len_out);
+  const size_t es = op_elem_size(op_dtype);
+  const long long sp = jb.ld_dst / 2;
+  for (IdxT i = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<IdxT>(gridDim.x) * blockDim.x) {
+    const IdxT row = i / per_row;
+    const int rem = static_cast<int>(i - row * per_row);
+    const int tap = rem / static_cast<int>(cv), c = (rem - tap * static_cast<int>(cv)) * 4;
+    const IdxT segi = row / seg_out;
+    const int seg = static_cast<int>(segi), t = static_cast<int>(row - segi * seg_out);
     const int ti = (t * jb.num) / jb.den + tap - jb.ntaps / 2;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ti >= 0 && ti < jb.seg_len_in)
       v = *reinterpret_cast<const float4*>(jb.src + (static_cast<long long>(seg) * jb.seg_len_in + ti) * jb.ld_src + c);
     const long long drow = static_cast<long long>(seg) * jb.dst_seg_stride + jb.dst_row_off + t;
     char* dr = reinterpret_cast<char*>(jb.dst) + static_cast<size_t>(drow) * jb.ld_dst * es;
-    store_op4(dr, p.op_dtype, static_cast<long long>(tap) * jb.tap_stride + c, jb.ld_dst / 2, v);
+    store_op4(dr, op_dtype, static_cast<long long>(tap) * jb.tap_stride + c, sp, v);
   }
+}
+
+__global__ void __launch_bounds__(256)
+rowcopy_kernel(const __grid_constant__ CopyParams p) {
+  pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
+  pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
+  const UnavCopyJob& jb = p.j[blockIdx.y];
+  const long long total = static_cast<long long>(jb.nseg) * jb.seg_len_out * jb.ntaps * (jb.C / 4);
+  if (total + static_cast<long long>(gridDim.x) * blockDim.x < (1LL << 31)) rowcopy_body<unsigned int>(jb, p.op_dtype, total);
+  else rowcopy_body<long long>(jb, p.op_dtype, total);
 }
 
 // =============================================================================================
@@ -586,7 +618,21 @@ extern "C" int unav_layernorm_rows(const UnavLnGroup* groups, int ngroups, int M
   }
   p.M = M; p.C = C; p.act = act; p.op_dtype = op_dtype; p.eps = eps;
   dim3 grid((M + 3) / 4, ngroups);
-  launch_pdl(ln_rows_kernel, dim3(grid), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool generic_only = getenv("UNAV_LN_GENERIC") != nullptr;               // A/B knob (tests compare the bits)
+#define UNAV_LN_CASE(NV, ACT)                                                              \
+  if (C == 128 * NV && act == ACT) {                                                       \
+    launch_pdl(ln_rows_exact_kernel<NV, ACT>, dim3(grid), dim3(128), 0, st, p);            \
+    count_launch();                                                                        \
+    return finish_launch("layernorm_rows");                                                \
+  }
+  if (!generic_only) {
+    UNAV_LN_CASE(2, UNAV_ACT_NONE) UNAV_LN_CASE(2, UNAV_ACT_RELU) UNAV_LN_CASE(2, UNAV_ACT_GELU) UNAV_LN_CASE(2, UNAV_ACT_SILU)
+    UNAV_LN_CASE(4, UNAV_ACT_NONE) UNAV_LN_CASE(4, UNAV_ACT_RELU) UNAV_LN_CASE(4, UNAV_ACT_GELU) UNAV_LN_CASE(4, UNAV_ACT_SILU)
+    UNAV_LN_CASE(8, UNAV_ACT_NONE) UNAV_LN_CASE(8, UNAV_ACT_RELU) UNAV_LN_CASE(8, UNAV_ACT_GELU) UNAV_LN_CASE(8, UNAV_ACT_SILU)
+  }
+#undef UNAV_LN_CASE
+  launch_pdl(ln_rows_kernel, dim3(grid), dim3(128), 0, st, p);
   count_launch();
   return finish_launch("layernorm_rows");
 }
