@@ -12,7 +12,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01b"
 CLS = {'gemm_tcgen05_kernel': 'gemm_tcgen05', 'gemm_tcgen05_pair_kernel': 'gemm_tcgen05', 'collate_pad_kernel': 'collate_pad', 'gemm_simt_kernel': 'gemm_simt',
        'dwconv_ln_kernel': 'dwconv_ln',
        'attention_tcgen05_kernel': 'attention_tc', 'attention_kernel': 'attention', 'softnms_lazy_kernel': 'softnms',
-       'softnms_kernel': 'softnms', 'merge_kernel': 'softnms', 'ln_rows_kernel': 'layernorm_rows', 'rowcopy_kernel': 'rowcopy',
+       'softnms_kernel': 'softnms', 'merge_kernel': 'softnms', 'ln_rows_kernel': 'layernorm_rows', 'ln_rows_exact_kernel': 'layernorm_rows', 'rowcopy_kernel': 'rowcopy',
        'maxsig_tcgen05_kernel': 'maxsig_gate_tc', 'maxsig_kernel': 'maxsig_gate', 'decode_kernel': 'decode',
        'pool_match_kernel': 'pool_match', 'transpose_cast_kernel': 'transpose_cast', 'align_embed_kernel': 'align_embed',
        'build_masks_kernel': 'build_masks'}
