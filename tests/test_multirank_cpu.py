@@ -59,3 +59,14 @@ def test_anet_packing_roundtrip():
     d = runner.pack_detections(segs, scores, labels)
     r = runner.detections_to_anet(d, ["a", "b", "c"])
     assert len(r["video-id"]) == 12 and r["label"].tolist() == labels.reshape(-1).tolist()
+
+
+def test_tag_last_lookahead():
+    """runner.tag_last: items pass through unchanged, flags[i] is known before item i is consumed, only the last is True."""
+    for n in (0, 1, 2, 5):
+        flags, seen = [], []
+        for i, x in enumerate(runner.tag_last(iter(range(n)), flags)):
+            assert len(flags) == i + 1          # the flag of item i exists when item i arrives
+            seen.append(x)
+        assert seen == list(range(n))
+        assert flags == [False] * (n - 1) + [True] * (1 if n else 0)

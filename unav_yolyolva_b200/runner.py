@@ -74,6 +74,23 @@ def detections_to_anet(dets: torch.Tensor, video_ids: List[str]) -> Dict[str, ob
     }
 
 
+def tag_last(loader, flags: list):
+    """Yield the items of ``loader`` unchanged while appending to ``flags``, in order, whether each one is the last — with one
+    HOST item of look-ahead, so that a consumer behind a prefetcher (which holds device slots) learns it without holding a
+    slot longer.  ``flags[i]`` is set before item i is yielded."""
+    it = iter(loader)
+    try:
+        prev = next(it)
+    except StopIteration:
+        return
+    for cur in it:
+        flags.append(False)
+        yield prev
+        prev = cur
+    flags.append(True)
+    yield prev
+
+
 def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluator=None, output_file=None, tb_writer=None,
                     print_freq=2, device=None, collate=None, losses="last"):
     """Drop-in for the reference's evaluation loop (/root/reference/libs/utils/train_utils.py:380-463) with the three
@@ -120,20 +137,7 @@ def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluato
     last_losses = None
 
     flags = []                      # is_last per raw batch, in loader order (the prefetcher draws them one ahead)
-
-    def tagged(loader):             # one host batch of look-ahead on the loader side, so the device slots are not held longer
-        it = iter(loader)
-        try:
-            prev = next(it)
-        except StopIteration:
-            return
-        for cur in it:
-            flags.append(False)
-            yield prev
-            prev = cur
-        flags.append(True)
-        yield prev
-
+    tagged = lambda loader: tag_last(loader, flags)
     for iter_idx, batch in enumerate(CudaPrefetcher(tagged(val_loader), dev, collate=collate, depth=depth + 1)):
         is_last = flags[iter_idx]
         want = (losses == "all" or (losses == "last" and is_last)) and all(k in batch for k in GT_KEYS)
