@@ -35,10 +35,11 @@ def split16(x):       # hi + lo, both fp16: what a 3-pass (or the A side of a 2-
     return hi + (x - hi).half().float()
 
 def run(cfg):
-    """cfg: stage -> passes (1: A_hi.B_hi, 2: (A_hi+A_lo).B_hi, 3: split on both sides); missing stage = exact."""
+    """cfg: stage -> passes (1: A_hi.B_hi, 2: (A_hi+A_lo).B_hi, 3: split on both sides, 4: A_hi.(B_hi+B_lo) = two passes with
+    only the WEIGHT side split); missing stage = exact."""
     def ha(x):
         n = cfg.get(STAGE[-1])
-        return x if n is None else (fp16(x) if n == 1 else split16(x))
+        return x if n is None else (fp16(x) if n in (1, 4) else split16(x))
     def hb(x):
         n = cfg.get(STAGE[-1])
         return x if n is None else (fp16(x) if n <= 2 else split16(x))
@@ -53,6 +54,6 @@ rel = lambda a, r: float((a - r).abs().max() / r.abs().max())
 ALL = ("alignment", "backbone", "fusion_module", "heads")
 print("fp16-split operands, MMA passes per stage (alignment, backbone, fusion_module, heads):")
 import itertools
-for combo in [(3,3,3,3),(1,1,1,1),(2,2,2,2),(1,1,2,2),(1,1,3,3),(1,1,2,3),(2,1,2,2),(1,1,1,2),(1,1,2,1),(2,2,3,3),(1,2,2,2),(1,1,3,2)]:
+for combo in [(3,3,3,3),(1,1,1,1),(2,2,2,2),(4,4,4,4),(1,1,2,2),(1,1,4,4),(1,1,3,3),(1,1,2,3),(1,1,4,3),(4,4,3,3),(2,1,2,2),(1,1,1,2),(1,1,2,1),(2,2,3,3),(1,2,2,2),(1,1,3,2)]:
     l, o = run(dict(zip(ALL, combo)))
     print(f"  {combo}   logits {rel(l, ref_l):.2e}  offsets {rel(o, ref_o):.2e}")
