@@ -165,10 +165,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 5))
-        r = run_cpu_arm(args.batch, steps, min(args.warmup, 1))
+        steps = max(1, min(args.steps, 16))             # a bounded sample: ~10 s of CPU work on the box's host cores
+        r = run_cpu_arm(args.batch, steps, min(args.warmup, 2))
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-                "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(config, precision_mode="fp32 (CPU)"),
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "nms": r["nms"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -427,7 +427,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r = run_cpu_arm(B, 3, 1)
+        r = run_cpu_arm(B, 12, 2)                       # ~10 s of CPU work (0.6 s per batch of 16 on 16 host cores)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "nms": r["nms"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Kst, "warmup": W,
