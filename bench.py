@@ -85,15 +85,25 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_step(sd, batch, use_ref_ext):
-    """The reference's CPU path, restated (oracle/model_ref.py) + its own compiled NMS where available."""
+def cpu_reference_step(sd, batch, use_ref_ext, with_losses=False):
+    """The reference's CPU path, restated (oracle/model_ref.py) + its own compiled NMS where available.  with_losses: also the
+    loss-only tail that the reference's eval forward executes (oracle/losses_ref.py), i.e. what `eval.py` really runs."""
     import numpy as np
     import torch
     from oracle import model_ref as R
     from oracle import nms_ref
     from unav_yolyolva_b200.config import TEST_CFG
     with torch.no_grad():
-        logits, offsets, masks = R.forward_logits(sd, batch["visual"], batch["audio"], batch["mask"])
+        if with_losses:
+            from oracle import losses_ref as LR
+            from unav_yolyolva_b200.config import MODEL_CFG, TRAIN_CFG
+            cfg = {"loss_weight": TRAIN_CFG["loss_weight"], "label_smoothing": TRAIN_CFG["label_smoothing"],
+                   "num_classes": MODEL_CFG["num_classes"], **{k: MODEL_CFG[k] for k in (
+                       "inter_contr_weight", "intra_contr_weight", "score_V_weight", "score_A_weight")}}
+            _, _, inter = LR.forward_losses(sd, batch, cfg, float(TRAIN_CFG["init_loss_norm"]))
+            logits, offsets, masks = inter["logits"], inter["offsets"], inter["masks"]
+        else:
+            logits, offsets, masks = R.forward_logits(sd, batch["visual"], batch["audio"], batch["mask"])
         pts = R.make_points(batch["visual"].shape[-1])
         out = []
         for i in range(batch["visual"].shape[0]):
@@ -139,7 +149,20 @@ def run_cpu_arm(batch_size, steps, warmup):
     for i in range(steps):
         cpu_reference_step(sd, batches[i % 2], ext)
     dt = time.perf_counter() - t0
+    # the same path including the loss-only tail the reference's eval forward also executes (reported separately)
+    n_l = max(1, min(steps, 3))
+    incl = None
+    try:
+        gtb = [synth.add_event_targets(synth.make_batch(batch_size, 224, first_index=i * batch_size), i * batch_size) for i in range(2)]
+        cpu_reference_step(sd, gtb[0], ext, with_losses=True)
+        t1 = time.perf_counter()
+        for i in range(n_l):
+            cpu_reference_step(sd, gtb[i % 2], ext, with_losses=True)
+        incl = batch_size * n_l / (time.perf_counter() - t1)
+    except Exception as e:                              # noqa: BLE001 - an extra figure must not cost the baseline itself
+        print(f"[bench] CPU arm incl. losses unavailable ({type(e).__name__}: {e})", file=sys.stderr)
     return {"value": batch_size * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": cores,
+            "value_incl_losses": incl,
             "kind": "port", "nms": "reference nms_1d_cpu (oracle/_ref)" if ext is not None else "oracle/nms_ref.c",
             "sample": f"{steps} batches of {batch_size} videos after {warmup} warm-up, torch FP32 oracle port, {cores} threads"}
 
@@ -170,7 +193,8 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
                 "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(config, precision_mode="fp32 (CPU)"),
-                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "nms": r["nms"]},
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "nms": r["nms"],
+                                 "value_incl_losses": r["value_incl_losses"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -428,7 +452,8 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         r = run_cpu_arm(B, 12, 2)                       # ~10 s of CPU work (0.6 s per batch of 16 on 16 host cores)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "nms": r["nms"]}
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "nms": r["nms"],
+               "value_incl_losses": r["value_incl_losses"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Kst, "warmup": W,
             "ms_per_step": dev_ms / Kst, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
