@@ -133,7 +133,8 @@ KEEP = ['Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dra
         'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
-        'smsp__issue_active.avg.pct_of_peak_sustained_active']
+        'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum', 'l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum.per_second']
 for rep, name in (('gpurun_out/prof_gemm_top.ncu-rep', f'{tag}_gemm_top_ncu_full.csv'),
                   ('gpurun_out/prof_attn_dw.ncu-rep', f'{tag}_attention_dwconv_ncu_full.csv'),
                   ('gpurun_out/prof_gemm_dom.ncu-rep', f'{tag}_gemm_dominant_ncu_full.csv'),
