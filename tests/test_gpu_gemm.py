@@ -1,5 +1,7 @@
 """GEMM kernels vs a plain FP32 torch reference (same op): CUDA-core FFMA path and the tcgen05/TMA path,
 ragged shapes, grouped launches and every epilogue term."""
+import os
+
 import pytest
 import torch
 
@@ -158,6 +160,34 @@ def test_tcgen05_cta_pair_kernel_128_wide(cuda, monkeypatch, op, M, N, Kd, group
         outs.append((o, _cabi.load(op).unav_gemm_last_variant()))
     torch.cuda.synchronize()
     assert outs[0][1] == 5 and outs[1][1] in (0, 1, 2, 4)
+    assert all(torch.equal(a, b) for a, b in zip(outs[0][0], outs[1][0]))
+
+
+@pytest.mark.skipif(os.environ.get("UNAV_TEST_EXPERIMENTAL") != "1",
+                    reason="128 x 256 tiles (UNAV_TC_BN=256) were written after round 1's GPU budget was spent: first validation pending")
+@pytest.mark.parametrize("op", [K.BF16X2, K.F16X2])
+@pytest.mark.parametrize("M,N,Kd,groups", [(3600, 2048, 512, 2), (7168, 512, 1536, 1), (5000, 1024, 520, 1)])
+def test_tcgen05_bn256_experiment(cuda, monkeypatch, op, M, N, Kd, groups):
+    """One-CTA 128 x 256 tiles (4/3 of the FLOP per L2 byte of the 128 x 128 tile): full epilogue vs the FP32 reference and the
+    same bits as the default tiles."""
+    from unav_yolyolva_b200 import _cabi
+    monkeypatch.setenv("UNAV_TC_BN", "256")
+    _run(cuda, M, N, Kd, op, K.GEMM_TCGEN05, full_epi=True, act=K.ACT_GELU, groups=groups)
+    g = torch.Generator().manual_seed(12)
+    A, W = torch.randn(M, Kd, generator=g), torch.randn(N, Kd, generator=g) / Kd ** 0.5
+    Aop, Wop = K.pack_operand(A.to(cuda), op), K.pack_operand(W.to(cuda), op)
+    outs = []
+    for bn in ("256", None):
+        monkeypatch.setenv("UNAV_TC_PAIR", "0")
+        if bn:
+            monkeypatch.setenv("UNAV_TC_BN", bn)
+        else:
+            monkeypatch.delenv("UNAV_TC_BN", raising=False)
+        o = [torch.empty(M, N, device=cuda) for _ in range(groups)]
+        K.gemm([{"A": Aop, "W": Wop, "out_f32": oi} for oi in o], M, N, Kd, op, K.ACT_NONE, False, K.GEMM_TCGEN05)
+        outs.append((o, _cabi.load(op).unav_gemm_last_variant()))
+    torch.cuda.synchronize()
+    assert outs[0][1] == 6 and outs[1][1] in (0, 1, 2, 4)
     assert all(torch.equal(a, b) for a, b in zip(outs[0][0], outs[1][0]))
 
 

@@ -485,7 +485,16 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (ph_out && threadIdx.x == 64) ph_out[5] = clock_stamp();       // accumulator ready
-    epilogue_tile<BN>(p, g, tmem_base, m0, n0, warp, lane, reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))), m_limit);
+    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)));
+    if constexpr (BN == 256) {       // experiment (UNAV_TC_BN=256): two 128-column halves through the 128-wide staging tile
+      for (int hf = 0; hf < 2; ++hf) {
+        if (n0 + hf * 128 >= p.N) break;
+        epilogue_tile<128>(p, g, tmem_base + hf * 128, m0, n0 + hf * 128, warp, lane, stg, m_limit);
+        __syncwarp();
+      }
+    } else {
+      epilogue_tile<BN>(p, g, tmem_base, m0, n0, warp, lane, stg, m_limit);
+    }
   }
   if (ph_out && threadIdx.x == 64) ph_out[6] = clock_stamp();         // this warp's epilogue done
   tc_fence_before();
@@ -742,6 +751,10 @@ static TcChoice choose_tile(int M, int N, int K, int ngroups, int nseg) {
   if (const char* env = getenv("UNAV_TC_BN")) {            // experiment knobs (scripts/gemm_probe.py)
     const int v = atoi(env);
     if (v == 64 || v == 128) c.bn = v;
+    // 128 x 256 tiles (4/3 of the FLOP per L2 byte of 128 x 128): NOT validated on a GPU yet — written
+    // at the end of round 1 without GPU time left; tests/test_gpu_gemm.py::test_tcgen05_bn256_experiment is skipped unless
+    // UNAV_TEST_EXPERIMENTAL=1.  Only for full grids of split operands whose N is a multiple of 256.
+    if (v == 256 && nseg > 1 && N % 256 == 0 && tiles128 > 148) { c.bn = 256; c.sched = 2; }
   }
   if (const char* env = getenv("UNAV_TC_ONCE")) {
     const int v = atoi(env);
@@ -779,7 +792,7 @@ static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > nkb) stages = nkb;
   if (stages < 2) stages = 2;
-  while (stages * per_stage < 128 * (BN + 4) * 4) ++stages;      // room for the staging tile
+  while (stages * per_stage < 128 * ((BN > 128 ? 128 : BN) + 4) * 4) ++stages;      // room for the staging tile
   while (Sm::total(stages, nparts) > MAX_SMEM) --stages;
   p.stages = stages;
   launch_pdl(gemm_tcgen05_kernel<BN, BK>, dim3(grid), dim3(TC_THREADS), Sm::total(stages, nparts), stream, p);
@@ -830,7 +843,7 @@ static int use_pair(int M, int N, int K, int ngroups) {
 }
 
 // which kernel the last tcgen05 GEMM call of this thread used (unav_gemm_last_variant): 0 <64,64>, 1 <128,32>, 2 <128,64>,
-// 3 CTA pair 256 wide, 4 <64,32>, 5 CTA pair 128 wide; -1 before the first call / for the CUDA-core backend
+// 3 CTA pair 256 wide, 4 <64,32>, 5 CTA pair 128 wide, 6 <256,32> (experiment); -1 before the first call / for the CUDA-core backend
 thread_local int g_last_variant = -1;
 
 int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, int op_arg, int act,
@@ -867,9 +880,10 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
     if ((rc = encode_map(&p.g[i].tmW, g.W, N, K, g.ldw, bn, bk, split, halves))) return rc;
     p.g[i].epi = make_epi(g);
   }
-  g_last_variant = pair == 256 ? 3 : pair == 128 ? 5 : (bn == 128 ? (bk == 32 ? 1 : 2) : (bk == 32 ? 4 : 0));
+  g_last_variant = pair == 256 ? 3 : pair == 128 ? 5 : bn == 256 ? 6 : (bn == 128 ? (bk == 32 ? 1 : 2) : (bk == 32 ? 4 : 0));
   if (pair == 256) return launch_pair<256>(p, ngroups, stream);
   if (pair == 128) return launch_pair<128>(p, ngroups, stream);
+  if (bn == 256) return launch_tc<256, 32>(p, ngroups, stream);
   if (bk == 32) return bn == 64 ? launch_tc<64, 32>(p, ngroups, stream) : launch_tc<128, 32>(p, ngroups, stream);
   return bn == 64 ? launch_tc<64, 64>(p, ngroups, stream) : launch_tc<128, 64>(p, ngroups, stream);
 }
