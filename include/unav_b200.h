@@ -32,6 +32,7 @@
  *   unav_transpose_cast    the [B,C,T] <-> [B,T,C] transposes (multimodal_backbones.py:1145-1146,
  *                          :1200-1201, :170)
  *   unav_align_embed       multimodal_backbones.py:1157-1166 (CLS + pos + type embedding)
+ *   unav_pack_operand      load-time conversion of nn.Linear / nn.Conv1d FP32 weights into GEMM operand rows
  *   unav_map_match         libs/utils/metrics.py:340-398 (greedy tIoU matching of compute_average_precision_detection)
  *   unav_collate_pad       libs/datasets/data_utils.py:178-205 (padding + mask of collate_fcn, on the device)
  *   unav_build_masks       blocks.py:45-51 (mask[::s]) and multimodal_backbones.py:568-570
@@ -260,6 +261,13 @@ int unav_rowcopy(const UnavCopyJob* jobs, int njobs, int op_dtype, void* stream)
 /* in [nb, R, Cc] FP32 (row stride ld_in) -> out [nb, Cc, R] operand dtype (row stride ld_out) */
 int unav_transpose_cast(const float* in, long long ld_in, void* out, long long ld_out,
                         int nb, int R, int Cc, int op_dtype, void* stream);
+
+/* Weight packing at model-load time (replaces the reference's implicit use of nn.Conv1d / nn.Linear FP32 weights,
+ * libs/modeling/blocks.py:30-31, multimodal_backbones.py:989-1034): src [rows, K] FP32 (row stride ld_src) -> dst operand rows
+ * of ld_dst elements in op_dtype (split formats: hi = half(x) at column c, lo = half(x - hi) at column ld_dst/2 + c); columns
+ * K..width-1 are written as zeros, so dst needs no prior memset. */
+int unav_pack_operand(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int K,
+                      int op_dtype, void* stream);
 
 /* tokens[m][b][0,:] = cls_m + pos_m[0] + type_m; tokens[m][b][1+t,:] = x0[m][b][t,:] + pos_m[1+t] + type_m
  * for m in {0: video, 1: audio}; x0 is [2, nb, T, C], tokens [2, nb, T+1, C]. */

@@ -68,3 +68,26 @@ def test_config_matches_reference_loader():
     assert set(cfg) == set(mine)
     for k in cfg:
         assert cfg[k] == mine[k] or list(cfg[k]) == list(mine[k]), k
+
+
+def test_engine_rejects_structures_outside_the_fused_plan():
+    """HotPathEngine hard-codes the avel_unav100 structure; any other valid reference config must raise, not mis-pack."""
+    import copy
+
+    import pytest
+
+    from unav_yolyolva_b200.config import default_model_cfg
+    from unav_yolyolva_b200.engine import HotPathEngine
+    from unav_yolyolva_b200.modeling import make_multimodal_meta_arch
+    from unav_yolyolva_b200.utils.nms import nms_method_code
+    HotPathEngine._validate_structure(make_multimodal_meta_arch("LocPointTransformer", **default_model_cfg()))
+    for key, val in (("head_num_layers", 2), ("use_abs_pe", False), ("class_aware", False), ("head_with_ln", False),
+                     ("backbone_arch", (3, 3, 5))):
+        cfg = copy.deepcopy(default_model_cfg())
+        cfg[key] = val
+        with pytest.raises(NotImplementedError):
+            HotPathEngine._validate_structure(make_multimodal_meta_arch("LocPointTransformer", **cfg))
+    assert nms_method_code("soft", True) == 2 and nms_method_code("hard", True) == 3
+    for bad in (("none", True), ("soft", False)):
+        with pytest.raises(NotImplementedError):
+            nms_method_code(*bad)

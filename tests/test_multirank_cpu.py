@@ -61,6 +61,18 @@ def test_anet_packing_roundtrip():
     assert len(r["video-id"]) == 12 and r["label"].tolist() == labels.reshape(-1).tolist()
 
 
+def test_anet_packing_drops_padding_rows_and_invalid_videos():
+    """Zero-score padding rows (a video with fewer than K detections) and videos that never arrived (valid mask of
+    gather_detections) must not become class-0 predictions at [0, 0]."""
+    segs = torch.rand(3, 4, 2) + 0.1; scores = torch.rand(3, 4) + 0.01; labels = torch.randint(0, 100, (3, 4))
+    d = runner.pack_detections(segs, scores, labels)
+    d[1, 2:] = 0                                   # video b produced only 2 detections
+    r = runner.detections_to_anet(d, ["a", "b", "c"], valid=torch.tensor([True, True, False]))
+    assert r["video-id"] == ["a"] * 4 + ["b"] * 2
+    assert r["score"].tolist() == d[0, :, 2].tolist() + d[1, :2, 2].tolist()
+    assert (r["score"] > 0).all()
+
+
 def test_tag_last_lookahead():
     """runner.tag_last: items pass through unchanged, flags[i] is known before item i is consumed, only the last is True."""
     for n in (0, 1, 2, 5):

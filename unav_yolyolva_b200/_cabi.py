@@ -88,6 +88,7 @@ _PROTOS = {
     "unav_rowcopy": (c_i, [C.POINTER(CopyJob), c_i, c_i, c_vp]),
     "unav_transpose_cast": (c_i, [c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_vp]),
     "unav_align_embed": (c_i, [c_vp] * 8 + [c_i, c_i, c_i, c_vp]),
+    "unav_pack_operand": (c_i, [c_vp, c_ll, c_vp, c_ll, c_ll, c_i, c_i, c_vp]),
     "unav_map_match": (c_i, [c_vp, c_vp, c_vp, c_vp, c_i, c_vp, c_i, c_i, c_i, c_vp, c_vp, c_vp]),
     "unav_collate_pad": (c_i, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_f, c_vp]),
     "unav_build_masks": (c_i, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_vp]),

@@ -484,6 +484,7 @@ def inference_from_heads(model, video_list, fpn_masks, out_cls_logits, out_offse
     o_s = torch.empty(B, Kd, 2, device=dev); o_sc = torch.empty(B, Kd, device=dev)
     o_l = torch.empty(B, Kd, dtype=torch.int64, device=dev); o_c = torch.empty(B, dtype=torch.int32, device=dev)
     ws = torch.empty(K.softnms_workspace_bytes(B, ncls, Kd), dtype=torch.uint8, device=dev)
+    from .utils.nms import nms_method_code
     K.softnms_batched(cs, csc, cl, B, cap, ncls, model.test_iou_threshold, model.test_nms_sigma, model.test_min_score,
-                      2 if model.test_nms_method == "soft" else 3, Kd, off[-1], meta, o_s, o_sc, o_l, o_c, ws)
+                      nms_method_code(model.test_nms_method, model.test_multiclass_nms), Kd, off[-1], meta, o_s, o_sc, o_l, o_c, ws)
     return model.collect_results({"out_segs": o_s, "out_scores": o_sc, "out_labels": o_l, "out_counts": o_c})

@@ -200,13 +200,9 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 
 template <int HS>
 static int launch_attention(const AttnParams& p, int ngroups, cudaStream_t stream) {
-  static bool attr_set = false;
+  static SmemAttr attr = {};
   const int smem = static_cast<int>(sizeof(AttnSmem<HS>));
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { set_error("attention<%d> smem attr: %s", HS, cudaGetErrorString(e)); return (int)e; }
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(attention_kernel<HS>, attr, smem, "attention")) return rc;
   dim3 grid((p.Tq + AT_Q - 1) / AT_Q, p.nh, p.nb * ngroups);
   launch_pdl(attention_kernel<HS>, dim3(grid), dim3(128), smem, stream, p);
   count_launch();

@@ -597,12 +597,8 @@ extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int
     d.out = s.out; d.ldo = s.ldo; d.x_first = s.x_first;
   }
   const int smem = p.q_bytes + p.kv_bytes + 128 + 4 * 128 * 4 + 1024;     // + barriers, mask words, max/sum exchange, slack
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { set_error("attention_tc: smem %d: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    smem_set = smem;
-  }
+  static SmemAttr attr = {};
+  if (int rc = ensure_dyn_smem(attention_tcgen05_kernel, attr, smem, "attention_tc")) return rc;
   dim3 grid((Tq + 127) / 128, nh, nb * ngroups);
   launch_pdl(attention_tcgen05_kernel, dim3(grid), dim3(ATC_THREADS), smem, reinterpret_cast<cudaStream_t>(stream), p);
   count_launch();
@@ -637,12 +633,8 @@ extern "C" int unav_maxsig_gate_tc(const void* x, long long ldx, int x_col0, con
   }
   if (nparts == 1) { p.tmX[1] = p.tmX[0]; p.tmG[1] = p.tmG[0]; }
   const int smem = nparts * 16384 + nparts * (nwords / 256) * 256 * 128 + 64 + 1024;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(maxsig_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { set_error("maxsig_gate_tc: smem %d: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    smem_set = smem;
-  }
+  static SmemAttr attr = {};
+  if (int rc = ensure_dyn_smem(maxsig_tcgen05_kernel, attr, smem, "maxsig_gate_tc")) return rc;
   dim3 grid((T + 127) / 128, H, nb);
   launch_pdl(maxsig_tcgen05_kernel, dim3(grid), dim3(192), smem, reinterpret_cast<cudaStream_t>(stream), p);
   count_launch();

@@ -53,6 +53,34 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: remember the largest size set per (kernel,
+// device) and raise it under a lock, so a second GPU in the process (nn.DataParallel with two ids, tests on cuda:1) and
+// concurrent host threads (DataParallel replicas) each get the attribute before their first launch.
+constexpr int kMaxDevices = 64;
+struct SmemAttr { size_t set[kMaxDevices]; };
+void smem_attr_lock();
+void smem_attr_unlock();
+template <typename KernelT>
+inline int ensure_dyn_smem(KernelT kernel, SmemAttr& st, size_t bytes, const char* what) {
+  if (bytes <= 48 * 1024) return 0;                    // the default limit needs no opt-in
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool tracked = dev >= 0 && dev < kMaxDevices;
+  smem_attr_lock();
+  int rc = 0;
+  if (!tracked || st.set[dev] < bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute(dynamic smem %zu) on device %d: %s", what, bytes, dev, cudaGetErrorString(e));
+      rc = static_cast<int>(e);
+    } else if (tracked) {
+      st.set[dev] = bytes;
+    }
+  }
+  smem_attr_unlock();
+  return rc;
+}
+
 __device__ __forceinline__ long long clock_stamp() {   // "memory": keep the read where it is written
   long long t;
   asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory");

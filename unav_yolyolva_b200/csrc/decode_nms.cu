@@ -682,12 +682,8 @@ extern "C" int unav_decode(const float* logits, const float* offsets, const uint
   size_t smem = static_cast<size_t>(max_n) * sizeof(float);
   p.use_smem = smem <= 200 * 1024;        // long sequences (T = 2304: 921 KB at level 0) recompute the sigmoid per pass
   if (!p.use_smem) smem = 0;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("decode: smem %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    smem_set = smem;
-  }
+  static unav::SmemAttr attr = {};
+  if (int rc = unav::ensure_dyn_smem(decode_kernel, attr, smem, "decode")) return rc;
   dim3 grid(L, B);
   launch_pdl(decode_kernel, dim3(grid), dim3(DEC_THREADS), smem, s, p);
   count_launch();
@@ -716,12 +712,8 @@ extern "C" int unav_softnms_batched(const float* cand_segs, const float* cand_sc
     // lazy per-video kernel when a whole video's candidates fit in shared memory (always true on the model path)
     const size_t lz = static_cast<size_t>(cap) * 16 + (static_cast<size_t>(ncls) * 4 + 1) * 4 + 64;
     if (lz <= 200 * 1024 && !getenv("UNAV_NMS_PER_CLASS")) {
-      static size_t lz_set = 0;
-      if (lz > 48 * 1024 && lz > lz_set) {
-        cudaError_t e = cudaFuncSetAttribute(softnms_lazy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz);
-        if (e != cudaSuccess) { set_error("softnms: smem %zu: %s", lz, cudaGetErrorString(e)); return (int)e; }
-        lz_set = lz;
-      }
+      static unav::SmemAttr lz_attr = {};
+      if (int rc = unav::ensure_dyn_smem(softnms_lazy_kernel, lz_attr, lz, "softnms_lazy")) return rc;
       LazyNmsParams q;
       q.cand_segs = cand_segs; q.cand_scores = cand_scores; q.cand_labels = cand_labels; q.vid_meta = vid_meta;
       q.out_segs = out_segs; q.out_scores = out_scores; q.out_labels = out_labels; q.out_counts = out_counts;
@@ -744,12 +736,8 @@ extern "C" int unav_softnms_batched(const float* cand_segs, const float* cand_sc
   p.maxn = (max_per_class > 0 && max_per_class < cap) ? max_per_class : cap;
   const size_t smem = static_cast<size_t>(p.maxn) * 4 * sizeof(float);
   UNAV_REQUIRE(smem <= 200 * 1024, "softnms: %d candidates per class exceed the shared-memory budget", p.maxn);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(softnms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("softnms: smem %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    smem_set = smem;
-  }
+  static unav::SmemAttr attr = {};
+  if (int rc = unav::ensure_dyn_smem(softnms_kernel, attr, smem, "softnms")) return rc;
   const int threads = p.maxn <= 1024 ? 32 : 256;
   dim3 grid(ncls, B);
   launch_pdl(softnms_kernel, dim3(grid), dim3(threads), smem, s, p);

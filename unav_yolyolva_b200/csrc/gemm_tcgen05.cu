@@ -765,17 +765,10 @@ static TcChoice choose_tile(int M, int N, int K, int ngroups, int nseg) {
 
 template <int BN, int BK>
 static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
-  static bool attr_set = false;
+  static SmemAttr attr = {};
   constexpr int MAX_SMEM = 200 * 1024;
   using Sm = TcSmem<BN, BK>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm_tcgen05<%d,%d>): %s", BN, BK, cudaGetErrorString(e));
-      return static_cast<int>(e);
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(gemm_tcgen05_kernel<BN, BK>, attr, MAX_SMEM, "gemm_tcgen05")) return rc;
   dim3 grid(p.conv_T > 0 ? (p.M / p.conv_T) * p.conv_tiles : (p.M + TC_BM - 1) / TC_BM, (p.N + BN - 1) / BN, ngroups);
   // Ring depth: multi-CTA-per-SM grids keep <= ~100 KB per CTA so two CTAs share an SM (one's epilogue overlaps the
   // other's k-loop); grids of at most one CTA per SM take a deeper ring.  The epilogue staging tile (128 x (BN+4)
@@ -802,16 +795,9 @@ static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
 
 template <int PN>
 static int launch_pair(TcParams& p, int ngroups, cudaStream_t stream) {
-  static bool attr_set = false;
+  static SmemAttr attr = {};
   constexpr int MAX_SMEM = 110 * 1024;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<PN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm_tcgen05_pair): %s", cudaGetErrorString(e));
-      return static_cast<int>(e);
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(gemm_tcgen05_pair_kernel<PN>, attr, MAX_SMEM, "gemm_tcgen05_pair")) return rc;
   const int nparts = p.nseg > 1 ? 2 : 1;
   const int per_stage = nparts * (P2_PART + (PN / 2) * P2_BK * 2);
   const int nkb = (p.K + P2_BK - 1) / P2_BK;

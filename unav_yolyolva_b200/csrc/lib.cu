@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -31,6 +32,10 @@ bool pdl_enabled() {
 
 long long* g_phase_buf = nullptr;    // unav_set_phase_trace: per-CTA clock stamps of the tcgen05 kernels (diagnostics)
 int g_phase_cap = 0;
+
+static std::mutex g_smem_attr_mutex;
+void smem_attr_lock() { g_smem_attr_mutex.lock(); }
+void smem_attr_unlock() { g_smem_attr_mutex.unlock(); }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

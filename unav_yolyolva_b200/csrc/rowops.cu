@@ -403,6 +403,24 @@ transpose_cast_kernel(const float* __restrict__ in, long long ld_in, void* out, 
 }
 
 // =============================================================================================
+// weight packing at load time: [rows, K] FP32 -> operand rows of ld_dst elements (hi | lo halves at ld_dst / 2 for the
+// split formats), padding columns zeroed — the whole destination row is written, so the buffer needs no prior memset
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+pack_operand_kernel(const float* __restrict__ src, long long ld_src, void* dst, long long ld_dst, long long rows, int K,
+                    int op_dtype) {
+  const long long width = op_is_split(op_dtype) ? ld_dst / 2 : ld_dst;     // padded logical width of a row
+  const size_t es = op_elem_size(op_dtype);
+  const long long total = rows * width;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / width, c = i - r * width;
+    const float v = c < K ? __ldg(src + r * ld_src + c) : 0.f;
+    store_op(reinterpret_cast<char*>(dst) + static_cast<size_t>(r) * ld_dst * es, op_dtype, c, ld_dst / 2, v);
+  }
+}
+
+// =============================================================================================
 // Alignment token embedding
 // =============================================================================================
 __global__ void __launch_bounds__(128)
@@ -655,12 +673,9 @@ extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg
   size_t smem = (static_cast<size_t>(n_in) * C + 2 * n_in) * sizeof(float);
   if (!narrow) smem += static_cast<size_t>(5 * n_out + 2 * n_pre) * C * sizeof(float);      // the CTA's weights
   const int nwarps = n_in > R * n_out ? n_in : R * n_out;     // one warp per staged row and per (row, output) pair
-  static size_t smem_set = 0;
-  if (!narrow && smem > 48 * 1024 && smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_ln_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) { set_error("dwconv_ln: smem %zu: %s", smem, cudaGetErrorString(e)); return static_cast<int>(e); }
-    smem_set = smem;
-  }
+  static SmemAttr attr = {};
+  if (!narrow)
+    if (int rc = ensure_dyn_smem(dwconv_ln_kernel<4>, attr, smem, "dwconv_ln")) return rc;
   dim3 grid(static_cast<unsigned>(nseg * tiles_per_seg), ngroups);
   if (narrow)
     launch_pdl(dwconv_ln_kernel<2>, dim3(grid), dim3(32 * nwarps), smem, reinterpret_cast<cudaStream_t>(stream), p);
@@ -701,6 +716,20 @@ extern "C" int unav_transpose_cast(const float* in, long long ld_in, void* out, 
   return finish_launch("transpose_cast");
 }
 
+extern "C" int unav_pack_operand(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int K,
+                                 int op_dtype, void* stream) {
+  UNAV_REQUIRE(src && dst && rows > 0 && K > 0 && ld_src >= K, "pack_operand: bad arguments");
+  UNAV_REQUIRE_OP(op_dtype, "pack_operand");
+  UNAV_REQUIRE(op_is_split(op_dtype) ? (ld_dst % 2 == 0 && ld_dst / 2 >= K) : ld_dst >= K, "pack_operand: ld_dst %lld too small for K = %d", ld_dst, K);
+  const long long total = rows * (op_is_split(op_dtype) ? ld_dst / 2 : ld_dst);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  launch_pdl(pack_operand_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), src, ld_src, dst,
+             ld_dst, rows, K, op_dtype);
+  count_launch();
+  return finish_launch("pack_operand");
+}
+
 extern "C" int unav_align_embed(const float* x0, const float* cls_v, const float* cls_a, const float* pos_v,
                                 const float* pos_a, const float* type_v, const float* type_a, float* tokens,
                                 int nb, int T, int C, void* stream) {
@@ -729,12 +758,8 @@ extern "C" int unav_pool_match(const float* u0, const float* u1, const float* u2
   UNAV_REQUIRE(u0 && u1 && u2 && Wm && bm && q, "pool_match: null pointer");
   UNAV_REQUIRE(P >= 1 && 3 * P <= 16, "pool_match: %d bins per level not supported", P);
   const size_t smem = (static_cast<size_t>(3 * P) * 32 + static_cast<size_t>(Tq) * 3 * P + Tq) * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(pool_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("pool_match: smem %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    smem_set = smem;
-  }
+  static SmemAttr attr = {};
+  if (int rc = ensure_dyn_smem(pool_match_kernel, attr, smem, "pool_match")) return rc;
   dim3 grid((C + 31) / 32, nb);
   launch_pdl(pool_match_kernel, dim3(grid), dim3(32 * 3 * P), smem, reinterpret_cast<cudaStream_t>(stream), u0, u1, u2, T0, T1, T2, ldu, Wm, bm, q,
                                                                               ldq, C, Tq, P);

@@ -43,8 +43,28 @@ MODES = {"fp32": (F32, GEMM_SIMT), "bf16": (BF16, GEMM_TCGEN05), "bf16x3": (BF16
 STAGE_PASSES = {"fast": {"alignment": 1, "backbone": 1}}
 
 
-def _flat(p: torch.Tensor) -> torch.Tensor:
-    return p.detach().float().reshape(-1).contiguous()
+class _Arena:
+    """Zero-initialised device memory for a plan's buffers, carved from a few large chunks (one fill per chunk instead of
+    one eager kernel per buffer); every buffer starts on a 256-byte boundary."""
+
+    CHUNK = 64 << 20
+
+    def __init__(self, device):
+        self.dev, self.chunks, self.off = device, [], 0
+
+    def alloc(self, shape, dtype) -> torch.Tensor:
+        shape = tuple(int(x) for x in shape)
+        n = 1
+        for x in shape:
+            n *= x
+        es = torch.empty((), dtype=dtype).element_size()
+        nbytes = (n * es + 255) // 256 * 256
+        if not self.chunks or self.off + nbytes > self.chunks[-1].numel():
+            self.chunks.append(torch.zeros(max(self.CHUNK, nbytes), dtype=torch.uint8, device=self.dev))
+            self.off = 0
+        t = self.chunks[-1][self.off:self.off + n * es].view(dtype).view(shape)
+        self.off += nbytes
+        return t
 
 
 class HotPathEngine:
@@ -64,6 +84,7 @@ class HotPathEngine:
         from . import _cabi
         _cabi.check(_cabi.load().unav_check_device(dev.index if dev.index is not None else torch.cuda.current_device()),
                     "unav_check_device")
+        self._validate_structure(model)
         self.T = model.max_seq_len
         self.C = model.backbone.n_embd
         self.L = len(model.fpn_strides)
@@ -82,36 +103,81 @@ class HotPathEngine:
         self._pack_weights()
         self._plans: Dict[tuple, dict] = {}
 
+    @staticmethod
+    def _validate_structure(model):
+        """The launch plan hard-codes the structure of the reference configs (configs/avel_unav100.yaml over
+        libs/core/config.py DEFAULTS).  Any other valid reference config would pack weights / launch GEMMs with the wrong K
+        or layout and give silently wrong output, so it is rejected here with the offending field named."""
+        from torch import nn
+        bb = model.backbone
+
+        def need(cond, what):
+            if not cond:
+                raise NotImplementedError(f"HotPathEngine: unsupported model structure — {what} (the fused plan covers the "
+                                          "reference's avel_unav100 configuration family only)")
+        need(len(bb.embd_V) == 2 and len(bb.embd_A) == 2, f"backbone_arch[0] = {len(bb.embd_V)} embedding convs (need 2)")
+        need(all(m.conv.kernel_size[0] == 3 and m.conv.bias is None for m in list(bb.embd_V) + list(bb.embd_A)),
+             "embedding convs must be k = 3 without bias (embd_kernel_size = 3, embd_with_ln = True)")
+        need(not isinstance(bb.embd_norm_V[0], nn.Identity), "embd_with_ln = False")
+        need(bb.use_abs_pe, "use_abs_pe = False")
+        need(bb.scale_factor == 2 and list(model.fpn_strides) == [2 ** i for i in range(len(model.fpn_strides))],
+             f"scale_factor = {bb.scale_factor} (pyramid kernels are stride 2)")
+        need(len(model.fpn_strides) >= 4, "fewer than 4 pyramid levels (guide enhancement pools the 3 finest)")
+        need(bb.n_embd == 512 and bb.n_embd % bb.n_head == 0 and bb.n_embd // bb.n_head in (64, 128), f"embd_dim = {bb.n_embd}, n_head = {bb.n_head}")
+        for h in (model.cls_head, model.reg_head):
+            need(len(h.head) == 2, f"head_num_layers = {len(h.head) + 1} (need 3)")
+            need(all(m.conv.kernel_size[0] == 3 and m.conv.bias is None for m in h.head), "head convs must be k = 3 with LayerNorm "
+                 "(head_kernel_size = 3, head_with_ln = True)")
+            need(not isinstance(h.norm[0], nn.Identity), "head_with_ln = False")
+        need(model.cls_head.cls_head.conv.kernel_size[0] == 3 and model.reg_head.offset_head.conv.kernel_size[0] == 3, "head_kernel_size != 3")
+        need(model.class_aware, "class_aware = False")
+        need(model.alignment.num_layers >= 1 and model.alignment.multiway_list[0].attn_fusion._heads == 8, "Alignment with other than 8 heads")
+
     # ------------------------------------------------------------------------------ weights
     def _pack_weights(self):
-        sd = {k: v for k, v in self.model.state_dict().items()}
+        """Weights are prepared on the HOST (reshape / permute / concatenate of the state_dict's FP32 tensors), uploaded as one
+        FP32 staging buffer, and converted into GEMM operand rows by ``unav_pack_operand`` (one launch per tensor) — no eager
+        PyTorch kernel runs on the device at load time.  Vectors (biases, LayerNorm affine, scales) stay FP32 views of the
+        uploaded buffer."""
+        src = self.model.state_dict()
+
+        class _HostSD(dict):                 # state_dict tensors as FP32 host tensors, fetched on first use
+            def __missing__(d, k):
+                d[k] = src[k].detach().to("cpu", torch.float32)
+                return d[k]
+
+        sd = _HostSD()
         w = self.w
-        op = self.op
+        self._ops, self._vecs = [], []       # (name, host tensor [N, K]) / (name, host tensor any shape)
+
+        def op_(name, t2d):
+            self._ops.append((name, t2d.contiguous()))
 
         def lin(name, key):            # nn.Linear / Conv1d k=1: [N, K(,1)]
-            t = sd[key].float()
-            w[name] = K.pack_operand(t.reshape(t.shape[0], -1), op)
+            t = sd[key]
+            op_(name, t.reshape(t.shape[0], -1))
 
         def conv3(name, key):          # Conv1d k=3 [N, Cin, 3] -> im2col layout [N, 3*Cin] (tap-major)
-            t = sd[key].float()
-            w[name] = K.pack_operand(t.permute(0, 2, 1).reshape(t.shape[0], -1).contiguous(), op)
+            t = sd[key]
+            op_(name, t.permute(0, 2, 1).reshape(t.shape[0], -1))
 
         def vec(name, key):
-            w[name] = _flat(sd[key])
+            self._vecs.append((name, sd[key].reshape(-1)))
 
         def cat_lin(name, keys):
-            w[name] = K.pack_operand(torch.cat([sd[k].float().reshape(sd[k].shape[0], -1) for k in keys], 0), op)
+            op_(name, torch.cat([sd[k].reshape(sd[k].shape[0], -1) for k in keys], 0))
 
         def cat_vec(name, keys):
-            w[name] = torch.cat([_flat(sd[k]) for k in keys])
+            self._vecs.append((name, torch.cat([sd[k].reshape(-1) for k in keys])))
 
+        self._sd, self._op_, self._vec_ = sd, op_, vec
         # ---- Alignment (multimodal_backbones.py:989-1034)
         a = "alignment."
         lin("al.pv", a + "proj_fc_video.0.weight"); vec("al.pv.b", a + "proj_fc_video.0.bias")
         lin("al.pa", a + "proj_fc_text.0.weight"); vec("al.pa.b", a + "proj_fc_text.0.bias")
         N = self.T + 1
-        w["al.pos_v"] = sd[a + "pos_embed_video"][0, :N].float().contiguous()
-        w["al.pos_a"] = sd[a + "pos_embed_text"][0, :N].float().contiguous()
+        self._vecs.append(("al.pos_v", sd[a + "pos_embed_video"][0, :N].contiguous()))
+        self._vecs.append(("al.pos_a", sd[a + "pos_embed_text"][0, :N].contiguous()))
         for nm in ("type_video", "type_text", "cls_token_video", "cls_token_text"):
             vec("al." + nm, a + nm)
         m = a + "multiway_list.0."
@@ -135,7 +201,7 @@ class HotPathEngine:
                 vec(f"bb.embdn{X}{i}.w", b + f"embd_norm_{X}.{i}.weight"); vec(f"bb.embdn{X}{i}.b", b + f"embd_norm_{X}.{i}.bias")
             for i in range(len(self.model.backbone.self_att_V)):
                 self._pack_tblock(sd, f"bb.sa{X}{i}", b + f"self_att_{X}.{i}.")
-        w["bb.pe"] = self.model.backbone.pos_embd[0].detach().float().t().contiguous()      # [T, C]
+        self._vecs.append(("bb.pe", self.model.backbone.pos_embd[0].detach().to("cpu", torch.float32).t().contiguous()))   # [T, C]
         for i in range(self.L - 1):
             vec(f"bb.down{i}.dw", b + f"downsample_list.{i}.down_conv.conv.weight")
             vec(f"bb.down{i}.w", b + f"downsample_list.{i}.down_norm.weight"); vec(f"bb.down{i}.b", b + f"downsample_list.{i}.down_norm.bias")
@@ -144,7 +210,7 @@ class HotPathEngine:
         self._pack_mhca(sd, "fu.te", f + "text_enhancer.")
         conv3("fu.ds", f + "downsample_layers.0.down_conv.conv.weight"); vec("fu.ds.b", f + "downsample_layers.0.down_conv.conv.bias")
         vec("fu.dsn.w", f + "downsample_layers.0.down_norm.weight"); vec("fu.dsn.b", f + "downsample_layers.0.down_norm.bias")
-        w["fu.match.w"] = sd[f + "match_projection.weight"].float().reshape(sd[f + "match_projection.weight"].shape[0], -1).contiguous()
+        self._vecs.append(("fu.match.w", sd[f + "match_projection.weight"].reshape(sd[f + "match_projection.weight"].shape[0], -1).contiguous()))
         vec("fu.match.b", f + "match_projection.bias")
         self.td_heads, self.bu_heads = [], []
         for kind, heads in (("top_down_layers", self.td_heads), ("bottom_up_layers", self.bu_heads)):
@@ -161,39 +227,70 @@ class HotPathEngine:
             cat_lin(f"fu.{tag}.gfc", [f + f"{kind}.{i}.attn_block.guide_fc.weight" for i in range(self.L - 1)])
             cat_vec(f"fu.{tag}.gfc.b", [f + f"{kind}.{i}.attn_block.guide_fc.bias" for i in range(self.L - 1)])
         # ---- heads (multimodal_meta_archs.py:101-259): first convs of cls and reg fused along N
-        t0 = [sd[f"{h}.head.0.conv.weight"].float().permute(0, 2, 1).reshape(self.C, -1) for h in ("cls_head", "reg_head")]
-        w["hd.c0"] = K.pack_operand(torch.cat(t0, 0).contiguous(), op)
+        t0 = [sd[f"{h}.head.0.conv.weight"].permute(0, 2, 1).reshape(self.C, -1) for h in ("cls_head", "reg_head")]
+        op_("hd.c0", torch.cat(t0, 0))
         for h, tag in (("cls_head", "cls"), ("reg_head", "reg")):
             conv3(f"hd.{tag}.c1", f"{h}.head.1.conv.weight")
             for i in range(2):
                 vec(f"hd.{tag}.n{i}.w", f"{h}.norm.{i}.weight"); vec(f"hd.{tag}.n{i}.b", f"{h}.norm.{i}.bias")
         conv3("hd.cls.out", "cls_head.cls_head.conv.weight"); vec("hd.cls.out.b", "cls_head.cls_head.conv.bias")
         conv3("hd.reg.out", "reg_head.offset_head.conv.weight"); vec("hd.reg.out.b", "reg_head.offset_head.conv.bias")
-        w["hd.scales"] = torch.stack([sd[f"reg_head.scale.{l}.scale"].float() for l in range(self.L)]).contiguous()
+        self.head_scales = [float(sd[f"reg_head.scale.{l}.scale"].reshape(-1)[0]) for l in range(self.L)]
+        self._upload_weights()
+
+    def _upload_weights(self):
+        """One host -> device copy of everything registered by _pack_weights, then one pack kernel per operand."""
+        dev, op, w = self.dev, self.op, self.w
+        al = lambda n: (n + 63) // 64 * 64                   # 256-byte granules (FP32 elements)
+        n_vec = sum(al(t.numel()) for _, t in self._vecs)
+        n_src = sum(al(t.numel()) for _, t in self._ops)
+        host = torch.empty(n_vec + n_src, dtype=torch.float32)
+        o, where = 0, {}
+        for name, t in self._vecs + self._ops:
+            host[o:o + t.numel()].copy_(t.reshape(-1))
+            where[name] = o
+            o += al(t.numel())
+        stage = host.to(dev)                                  # ONE memcpy
+        self._w_vec = stage                                   # the vectors live in its first n_vec elements
+        for name, t in self._vecs:
+            w[name] = stage[where[name]:where[name] + t.numel()].view(t.shape)
+        es = 4 if op == F32 else 2
+        alo = lambda n: (n * es + 255) // 256 * 256 // es
+        total = sum(alo(t.shape[0] * K.op_cols(t.shape[1], op)) for _, t in self._ops)
+        arena = torch.empty(total, dtype=K.OP_TORCH_DTYPE[op], device=dev)        # fully written by the pack kernels
+        self._w_op = arena
+        o = 0
+        for name, t in self._ops:
+            N, Kc = t.shape
+            cols = K.op_cols(Kc, op)
+            dst = arena[o:o + N * cols].view(N, cols)
+            K.pack_operand_into(stage[where[name]:where[name] + N * Kc].view(N, Kc), dst, op)
+            w[name] = dst
+            o += alo(N * cols)
+        torch.cuda.current_stream(dev).synchronize()          # the FP32 staging copy of the operands may be reused afterwards
+        self._ops = self._vecs = self._sd = self._op_ = self._vec_ = None
 
     def _pack_mhca(self, sd, name, p):
-        w = self.w
         for x in ("query", "key", "value"):
-            w[f"{name}.{x}.dw"] = _flat(sd[p + f"{x}_conv.conv.weight"])
-            w[f"{name}.{x}.nw"] = _flat(sd[p + f"{x}_norm.weight"]); w[f"{name}.{x}.nb"] = _flat(sd[p + f"{x}_norm.bias"])
-            t = sd[p + f"{x}.weight"].float()
-            w[f"{name}.{x}"] = K.pack_operand(t.reshape(t.shape[0], -1), self.op)
-            w[f"{name}.{x}.b"] = _flat(sd[p + f"{x}.bias"])
-        t = sd[p + "proj.weight"].float()
-        w[f"{name}.proj"] = K.pack_operand(t.reshape(t.shape[0], -1), self.op)
-        w[f"{name}.proj.b"] = _flat(sd[p + "proj.bias"])
+            self._vec_(f"{name}.{x}.dw", p + f"{x}_conv.conv.weight")
+            self._vec_(f"{name}.{x}.nw", p + f"{x}_norm.weight"); self._vec_(f"{name}.{x}.nb", p + f"{x}_norm.bias")
+            t = sd[p + f"{x}.weight"]
+            self._op_(f"{name}.{x}", t.reshape(t.shape[0], -1))
+            self._vec_(f"{name}.{x}.b", p + f"{x}.bias")
+        t = sd[p + "proj.weight"]
+        self._op_(f"{name}.proj", t.reshape(t.shape[0], -1))
+        self._vec_(f"{name}.proj.b", p + "proj.bias")
 
     def _pack_tblock(self, sd, name, p):
-        w = self.w
         self._pack_mhca(sd, name + ".attn", p + "attn.")
         for ln in ("ln11", "ln12", "ln2"):
-            w[f"{name}.{ln}.w"] = _flat(sd[p + ln + ".weight"]); w[f"{name}.{ln}.b"] = _flat(sd[p + ln + ".bias"])
+            self._vec_(f"{name}.{ln}.w", p + ln + ".weight"); self._vec_(f"{name}.{ln}.b", p + ln + ".bias")
         for i, tag in ((0, "mlp0"), (3, "mlp3")):
-            t = sd[p + f"mlp.{i}.weight"].float()
-            w[f"{name}.{tag}"] = K.pack_operand(t.reshape(t.shape[0], -1), self.op)
-            w[f"{name}.{tag}.b"] = _flat(sd[p + f"mlp.{i}.bias"])
-        w[f"{name}.sa"] = _flat(sd[p + "drop_path_attn.scale"])
-        w[f"{name}.sm"] = _flat(sd[p + "drop_path_mlp.scale"])
+            t = sd[p + f"mlp.{i}.weight"]
+            self._op_(f"{name}.{tag}", t.reshape(t.shape[0], -1))
+            self._vec_(f"{name}.{tag}.b", p + f"mlp.{i}.bias")
+        self._vec_(f"{name}.sa", p + "drop_path_attn.scale")
+        self._vec_(f"{name}.sm", p + "drop_path_mlp.scale")
 
     # ------------------------------------------------------------------------------ buffers
     def _plan(self, B: int, slot: int = 0) -> dict:
@@ -203,10 +300,11 @@ class HotPathEngine:
             return self._plans[(B, slot)]
         dev, op, T, C, L = self.dev, self.op, self.T, self.C, self.L
         NB = 2 * B
-        f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
-        u8 = lambda *s: torch.zeros(*s, dtype=torch.uint8, device=dev)
-        opb = lambda rows, Kc: K.new_operand(rows, Kc, op, dev)
-        P: dict = {"B": B}
+        ar = _Arena(dev)
+        f32 = lambda *s: ar.alloc(s, torch.float32)
+        u8 = lambda *s: ar.alloc(s, torch.uint8)
+        opb = lambda rows, Kc: ar.alloc((rows, K.op_cols(Kc, op)), K.OP_TORCH_DTYPE[op])
+        P: dict = {"B": B, "arena": ar}
         Tl, Ttot = self.Tl, self.Ttot
         # inputs (static addresses for graph replay)
         P["visual"] = f32(B, 2048, T); P["audio"] = f32(B, 128, T); P["mask_in"] = u8(B, T)
@@ -284,10 +382,10 @@ class HotPathEngine:
         P["HC2"] = opb(Mh, 3 * C); P["HR2"] = opb(Mh, 3 * C)
         P["logits"] = f32(Mh, self.ncls); P["offsets"] = f32(Mh, 2 * self.ncls)
         P["m_heads"] = u8(Mh)
-        P["rowscale"] = f32(Mh)
-        rs = P["rowscale"].view(B, Ttot)
+        rs = torch.empty(B, Ttot, dtype=torch.float32)
         for l in range(L):       # Scale_l per row (meta_archs.py:257), constant per plan
-            rs[:, self.level_off[l]:self.level_off[l + 1]] = self.w["hd.scales"][l]
+            rs[:, self.level_off[l]:self.level_off[l + 1]] = self.head_scales[l]
+        P["rowscale"] = rs.reshape(Mh).to(dev)
         pts = []
         for l in range(L):
             s = float(self.model.fpn_strides[l])
@@ -299,12 +397,12 @@ class HotPathEngine:
         topk = self.model.test_pre_nms_topk
         P["cap"] = sum(min(topk, Tl[l] * self.ncls) for l in range(L))
         P["cand_segs"] = f32(B, P["cap"], 2); P["cand_scores"] = f32(B, P["cap"])
-        P["cand_labels"] = torch.zeros(B, P["cap"], dtype=torch.int32, device=dev)
+        P["cand_labels"] = ar.alloc((B, P["cap"]), torch.int32)
         Kd = self.model.test_max_seg_num
         P["out_segs"] = f32(B, Kd, 2); P["out_scores"] = f32(B, Kd)
-        P["out_labels"] = torch.zeros(B, Kd, dtype=torch.int64, device=dev)
-        P["out_counts"] = torch.zeros(B, dtype=torch.int32, device=dev)
-        P["nms_ws"] = torch.zeros(K.softnms_workspace_bytes(B, self.ncls, Kd), dtype=torch.uint8, device=dev)
+        P["out_labels"] = ar.alloc((B, Kd), torch.int64)
+        P["out_counts"] = ar.alloc((B,), torch.int32)
+        P["nms_ws"] = ar.alloc((K.softnms_workspace_bytes(B, self.ncls, Kd),), torch.uint8)
         P["graph"] = None
         self._plans[(B, slot)] = P
         return P
@@ -594,9 +692,8 @@ class HotPathEngine:
         """Per-class soft-NMS + merge + seconds (meta_archs.py:819-875, libs/utils/nms.py:103-190) of P's candidates."""
         md = self.model
         B, Ttot = P["B"], self.Ttot
-        if md.test_nms_method == "none":
-            raise NotImplementedError("nms_method='none' is not on the hot path")
-        method = 2 if md.test_nms_method == "soft" else 3
+        from .utils.nms import nms_method_code
+        method = nms_method_code(md.test_nms_method, md.test_multiclass_nms)
         K.softnms_batched(P["cand_segs"], P["cand_scores"], P["cand_labels"], B, P["cap"], self.ncls, md.test_iou_threshold,
                           md.test_nms_sigma, md.test_min_score, method, md.test_max_seg_num, Ttot, vid_meta,
                           P["out_segs"], P["out_scores"], P["out_labels"], P["out_counts"], P["nms_ws"])
@@ -666,7 +763,11 @@ class HotPathEngine:
         copies (it may recycle its input tensors afterwards); consumers of out_* order themselves after
         ``plan["ev_nms"]`` or enqueue on ``plan["nms_stream"]``."""
         B = visual.shape[0]
-        assert visual.shape[2] == self.T and audio.shape[2] == self.T, "sequence length must equal max_seq_len"
+        if visual.shape[2] != self.T or audio.shape[2] != self.T:
+            # the reference pads every batch to max_seq_len (data_utils.py:170-176) and, for longer videos, to a multiple of
+            # max_div_factor — the static plan is built for max_seq_len only
+            raise NotImplementedError(f"HotPathEngine: sequence length {visual.shape[2]} != max_seq_len {self.T}; pad to max_seq_len "
+                                      "(videos longer than max_seq_len are not supported by the fused plan)")
         assert overlap_nms or slot == 0
         P = self._plan(B, slot)
         with torch.cuda.device(self.dev):
@@ -695,7 +796,7 @@ class HotPathEngine:
                 return P
             # ---- streaming mode
             if "meta2" not in P:
-                P["meta2"] = torch.zeros(2, B, 4, dtype=torch.float32, device=self.dev)
+                P["meta2"] = P["arena"].alloc((2, B, 4), torch.float32)
                 P["ev_dec"] = torch.cuda.Event()
                 P["step"] = 0
                 P["fwd_stream"] = torch.cuda.Stream(self.dev)

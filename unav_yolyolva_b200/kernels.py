@@ -117,20 +117,24 @@ def new_operand(rows: int, K: int, op_dtype: int, device) -> torch.Tensor:
     return torch.zeros(rows, op_cols(K, op_dtype), dtype=OP_TORCH_DTYPE[op_dtype], device=device)
 
 
+def pack_operand_into(src: torch.Tensor, dst: torch.Tensor, op_dtype: int) -> None:
+    """src [N, K] FP32 device rows (last dim contiguous) -> dst operand buffer [N, op_cols(K)] (one ``pack_operand_kernel`` launch;
+    padding columns are zeroed by the kernel)."""
+    N, K = src.shape
+    assert src.is_cuda and src.dtype == torch.float32 and src.stride(1) == 1 and dst.shape[0] == N and dst.stride(1) == 1
+    lib = A.load(op_dtype)
+    with _Span("pack_operand", 0, N * K * (4 + (4 if op_dtype in SPLIT_DTYPES else (4 if op_dtype == F32 else 2)))):
+        A.check(lib.unav_pack_operand(_p(src), src.stride(0), _p(dst), dst.stride(0), N, K, op_dtype, _stream()), "unav_pack_operand")
+
+
 def pack_operand(w: torch.Tensor, op_dtype: int) -> torch.Tensor:
     """[N, K] FP32 -> operand buffer (weight packing at load time; not on the per-batch path)."""
     N, K = w.shape
-    w = w.detach().float()
-    out = new_operand(N, K, op_dtype, w.device)
-    if op_dtype == F32:
-        out[:, :K] = w
-    else:
-        dt = OP_TORCH_DTYPE[op_dtype]
-        hi = w.to(dt)
-        out[:, :K] = hi
-        if op_dtype in SPLIT_DTYPES:
-            half = out.shape[1] // 2
-            out[:, half:half + K] = (w - hi.float()).to(dt)
+    w = w.detach()
+    if w.dtype != torch.float32 or w.stride(1) != 1:
+        w = w.float().contiguous()
+    out = torch.empty(N, op_cols(K, op_dtype), dtype=OP_TORCH_DTYPE[op_dtype], device=w.device)
+    pack_operand_into(w, out, op_dtype)
     return out
 
 

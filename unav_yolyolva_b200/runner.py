@@ -7,7 +7,9 @@ Works with the ``nccl`` backend on GPUs and with ``gloo`` on CPU tensors (tests/
 """
 from __future__ import annotations
 
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
 
 import torch
 import torch.distributed as dist
@@ -60,17 +62,25 @@ def gather_detections(local: torch.Tensor, video_index: torch.Tensor, n_videos: 
     return out, valid
 
 
-def detections_to_anet(dets: torch.Tensor, video_ids: List[str]) -> Dict[str, object]:
+def detections_to_anet(dets: torch.Tensor, video_ids: List[str], valid: Optional[torch.Tensor] = None) -> Dict[str, object]:
     """[n,K,4] -> the flat result dict ``valid_one_epoch`` hands to ``ANETdetection.evaluate``
-    (/root/reference/libs/utils/train_utils.py:400-449)."""
+    (/root/reference/libs/utils/train_utils.py:400-449).  Rows that are not detections are dropped: the zero padding of a
+    video with fewer than K detections (score 0 — a real detection's score is > pre_nms_thresh > 0) and, with ``valid``
+    (the mask returned by ``gather_detections``), videos that never arrived; otherwise they would count as class-0
+    predictions at [0, 0]."""
     d = dets.cpu()
     n, K = d.shape[:2]
+    keep = d[..., 2] > 0
+    if valid is not None:
+        keep &= valid.cpu().reshape(n, 1)
+    keep = keep.reshape(-1).numpy()
+    ids = np.repeat(np.asarray(video_ids, dtype=object), K)
     return {
-        "video-id": [v for v in video_ids for _ in range(K)],
-        "t-start": d[..., 0].reshape(-1).numpy(),
-        "t-end": d[..., 1].reshape(-1).numpy(),
-        "score": d[..., 2].reshape(-1).numpy(),
-        "label": d[..., 3].reshape(-1).long().numpy(),
+        "video-id": ids[keep].tolist(),
+        "t-start": d[..., 0].reshape(-1).numpy()[keep],
+        "t-end": d[..., 1].reshape(-1).numpy()[keep],
+        "score": d[..., 2].reshape(-1).numpy()[keep],
+        "label": d[..., 3].reshape(-1).long().numpy()[keep],
     }
 
 
