@@ -89,6 +89,11 @@ long long unav_launch_count(void);
  * 0 gemm_tcgen05_kernel<64,64>, 1 <128,32>, 2 <128,64>, 3 gemm_tcgen05_pair_kernel, 4 <64,32>; -1 if none yet.
  * bench.py uses it to attribute its per-launch CUDA-event times to the kernels ncu lists. */
 int unav_gemm_last_variant(void);
+/* Cumulative number of UNAV_GEMM_TCGEN05 launches per variant id (same numbering; 5 = 128-wide CTA pair, 6 = <256,32>,
+ * 7 = persistent CTA-pair kernel) since the library was loaded: out[0..n).  Parity tests use the difference across a run to
+ * prove which tile variants a configuration exercised. */
+#define UNAV_GEMM_VARIANTS 8
+int unav_gemm_variant_counts(long long* out, int n);
 
 /* Diagnostics for the tcgen05 kernels (scripts/gemm_phases.py): while a buffer is set, every CTA with linear index
  * below capacity_ctas writes 8 int64: GEMM {smid, clock64 at: start, setup done, first operands landed, last MMA

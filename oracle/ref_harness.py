@@ -14,8 +14,14 @@ Two jobs, both optional and both confined to this container / to ``oracle/_ref``
    i.e. in the build container — golden fixtures are generated with it
    (``tests/golden/make_golden.py``) and committed.
 
-On the GPU box ``/root/reference`` does not exist: only ``load_ref_nms()`` (the prebuilt
-``oracle/_ref/nms_1d_cpu*.so``) is available there.
+3. ``ship_reference()`` copies the reference's Python tree (``libs/``, ``configs/``, ``eval.py``) into
+   ``oracle/_ref/reference/`` — git-ignored like the ``.so`` next to it, NOT gpurun-ignored — so that the
+   UNMODIFIED reference travels to the GPU box with the snapshot: ``bench.py --impl reference`` times the
+   reference's own ``PtTransformer`` there and a ``-m gpu`` test runs its ``eval.py``.  Nothing under
+   ``oracle/_ref`` is ever committed; the recipe is this function (called from ``__graft_entry__.build()``).
+
+``reference_root()`` is ``/root/reference`` where it exists (this container) and the shipped copy otherwise
+(the GPU box).
 """
 from __future__ import annotations
 
@@ -28,12 +34,38 @@ import sys
 ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = "/root/reference"
 REF_OUT = os.path.join(ORACLE_DIR, "_ref")
+REF_SHIP = os.path.join(REF_OUT, "reference")
 STUBS = os.path.join(ORACLE_DIR, "stubs")
 _NMS_SRC = os.path.join(REF_ROOT, "libs", "utils", "csrc", "nms_cpu.cpp")
 
 
 def have_reference() -> bool:
+    """The reference SOURCE tree is on this machine (the build container)."""
     return os.path.isfile(_NMS_SRC)
+
+
+def reference_root():
+    """Directory holding the reference's ``libs`` package: the source tree here, the shipped copy on the GPU box, or None."""
+    if have_reference():
+        return REF_ROOT
+    if os.path.isfile(os.path.join(REF_SHIP, "libs", "modeling", "multimodal_meta_archs.py")):
+        return REF_SHIP
+    return None
+
+
+def ship_reference() -> str:
+    """Copy the reference's Python tree to oracle/_ref/reference (build container only; idempotent)."""
+    import shutil
+    if not have_reference():
+        raise FileNotFoundError("reference sources not present")
+    if os.path.isdir(REF_SHIP):
+        shutil.rmtree(REF_SHIP)
+    os.makedirs(REF_SHIP)
+    ignore = shutil.ignore_patterns("__pycache__", "*.pyc", "build", "*.so", "*.o", "*.egg-info")
+    for d in ("libs", "configs"):
+        shutil.copytree(os.path.join(REF_ROOT, d), os.path.join(REF_SHIP, d), ignore=ignore)
+    shutil.copy2(os.path.join(REF_ROOT, "eval.py"), os.path.join(REF_SHIP, "eval.py"))
+    return REF_SHIP
 
 
 def _find_ref_nms_so():
@@ -80,13 +112,22 @@ def load_ref_nms():
     return mod
 
 
+def reference_pythonpath():
+    """sys.path / PYTHONPATH entries that make the unmodified reference importable (also in worker processes: the stubs
+    must be real on-disk packages): stubs, the reference root, and oracle/_ref for ``nms_1d_cpu``."""
+    root = reference_root()
+    if root is None:
+        raise FileNotFoundError("neither /root/reference nor oracle/_ref/reference is available on this machine")
+    return [STUBS, root, REF_OUT]
+
+
 def import_reference():
-    """Return the reference's ``libs`` package (build container only)."""
-    if not have_reference():
-        raise FileNotFoundError("/root/reference is not available on this machine")
-    build_ref_nms()
-    assert load_ref_nms() is not None
-    for p in (STUBS, REF_ROOT):
+    """Return the reference's ``libs`` package (the source tree in the build container, the shipped copy on the GPU box)."""
+    paths = reference_pythonpath()
+    if have_reference():
+        build_ref_nms()
+    assert load_ref_nms() is not None, "oracle/_ref/nms_1d_cpu.so is missing (run __graft_entry__.build() in the build container)"
+    for p in reversed(paths):
         if p not in sys.path:
             sys.path.insert(0, p)
     return importlib.import_module("libs")

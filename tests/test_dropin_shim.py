@@ -64,3 +64,37 @@ def test_reference_checkout_with_the_two_shims(tmp_path):
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(tmp_path), STUBS, ROOT]))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and "SHIM_OK 1235" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference tree not on this machine")
+def test_eval_harness_reference_cpu_run_and_shipped_copy(tmp_path):
+    """The eval.py harness of tests/test_gpu_eval_dropin.py, CPU half: synthetic dataset + annotations + checkpoint + config ->
+    the reference's own evaluation loop on the CPU prints a non-trivial mAP table; and the copy that ships to the GPU box
+    (oracle/_ref/reference) is byte-identical to the reference's Python tree."""
+    import filecmp
+
+    import numpy as np
+    import torch
+
+    from oracle import eval_dropin as ED
+    from oracle import ref_harness, ref_runner
+    from unav_yolyolva_b200 import synth
+    ship = ref_harness.ship_reference()
+    for rel in ("eval.py", "libs/modeling/multimodal_meta_archs.py", "libs/utils/nms.py", "libs/utils/train_utils.py",
+                "libs/datasets/data_utils.py", "configs/avel_unav100.yaml"):
+        assert filecmp.cmp(os.path.join(ship, rel), os.path.join(REF_ROOT, rel), shallow=False), rel
+    tmp = str(tmp_path)
+    n = 4
+    items = ED.write_features(os.path.join(tmp, "feats"), n, first_index=300)
+    sd = synth.trained_like_state_dict()
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    res, _ = ref_runner.reference_forward(ref_runner.build_reference_model(sd), synth.make_batch(n, 224, first_index=300))
+    ED.write_annotations(os.path.join(tmp, "anno.json"), items, res["segments"].numpy(), res["labels"].numpy())
+    ED.write_checkpoint(os.path.join(tmp, "ckpt", "model.pth.tar"), sd)
+    ED.write_config(os.path.join(tmp, "cfg.yaml"), os.path.join(tmp, "anno.json"), os.path.join(tmp, "feats"), os.path.join(tmp, "out"),
+                    batch_size=4, workers=1)
+    tab = ED.run_reference_cpu(os.path.join(tmp, "cfg.yaml"), os.path.join(tmp, "ckpt", "model.pth.tar"))
+    assert len(tab) == 10 and tab["avg"] > 10.0, tab
+    overlay = ED.make_overlay(os.path.join(tmp, "checkout"))
+    assert os.path.islink(os.path.join(overlay, "eval.py"))
+    assert open(os.path.join(overlay, "libs", "utils", "nms.py")).read() == ED.SHIM_NMS

@@ -76,6 +76,7 @@ _PROTOS = {
     "unav_check_device": (c_i, [c_i]),
     "unav_launch_count": (c_ll, []),
     "unav_gemm_last_variant": (c_i, []),
+    "unav_gemm_variant_counts": (c_i, [C.POINTER(c_ll), c_i]),
     "unav_set_phase_trace": (c_i, [c_vp, c_i]),
     "unav_gemm": (c_i, [C.POINTER(GemmGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "unav_layernorm_rows": (c_i, [C.POINTER(LnGroup), c_i, c_i, c_i, c_f, c_i, c_i, c_vp]),

@@ -831,6 +831,9 @@ static int use_pair(int M, int N, int K, int ngroups) {
 // which kernel the last tcgen05 GEMM call of this thread used (unav_gemm_last_variant): 0 <64,64>, 1 <128,32>, 2 <128,64>,
 // 3 CTA pair 256 wide, 4 <64,32>, 5 CTA pair 128 wide, 6 <256,32> (experiment); -1 before the first call / for the CUDA-core backend
 thread_local int g_last_variant = -1;
+// cumulative launches per variant (unav_gemm_variant_counts): lets a parity test PROVE which tile variants a configuration
+// exercised (the batch-16 path takes <128,32> and the CTA-pair kernels, the batch <= 4 paths never do)
+static unsigned long long g_variant_counts[UNAV_GEMM_VARIANTS] = {};
 
 int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, int op_arg, int act,
                  int res_masked, cudaStream_t stream) {
@@ -867,6 +870,7 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
     p.g[i].epi = make_epi(g);
   }
   g_last_variant = pair == 256 ? 3 : pair == 128 ? 5 : bn == 256 ? 6 : (bn == 128 ? (bk == 32 ? 1 : 2) : (bk == 32 ? 4 : 0));
+  __atomic_fetch_add(&g_variant_counts[g_last_variant], 1ull, __ATOMIC_RELAXED);
   if (pair == 256) return launch_pair<256>(p, ngroups, stream);
   if (pair == 128) return launch_pair<128>(p, ngroups, stream);
   if (bn == 256) return launch_tc<256, 32>(p, ngroups, stream);
@@ -877,3 +881,9 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
 }  // namespace unav
 
 extern "C" int unav_gemm_last_variant(void) { return unav::g_last_variant; }
+extern "C" int unav_gemm_variant_counts(long long* out, int n) {
+  if (!out || n < 0) return UNAV_ERR_BAD_ARG;
+  for (int i = 0; i < n; ++i)
+    out[i] = i < UNAV_GEMM_VARIANTS ? static_cast<long long>(__atomic_load_n(&unav::g_variant_counts[i], __ATOMIC_RELAXED)) : 0;
+  return 0;
+}

@@ -20,7 +20,7 @@ OP_TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, BF16X2: torch.bfloat
 # kernel names as ncu lists them, by unav_gemm_last_variant()
 GEMM_KERNELS = {0: "gemm_tcgen05_kernel<64, 64>", 1: "gemm_tcgen05_kernel<128, 32>", 2: "gemm_tcgen05_kernel<128, 64>",
                 3: "gemm_tcgen05_pair_kernel<256>", 4: "gemm_tcgen05_kernel<64, 32>", 5: "gemm_tcgen05_pair_kernel<128>",
-                6: "gemm_tcgen05_kernel<256, 32>"}
+                6: "gemm_tcgen05_kernel<256, 32>", 7: "gemm_tcgen05_ppair_kernel<256>"}
 
 
 def with_passes(op_dtype: int, passes: int = 0) -> int:
@@ -405,6 +405,16 @@ def softnms_batched(cand_segs, cand_scores, cand_labels, B: int, cap: int, ncls:
                                      _p(vid_meta), _p(out_segs), _p(out_scores), _p(out_labels),
                                      _p(out_counts), _p(workspace), workspace.numel() * workspace.element_size(),
                                      _stream()), "unav_softnms_batched")
+
+
+def gemm_variant_counts() -> dict:
+    """Cumulative tcgen05 GEMM launches per kernel variant (names as ncu lists them), summed over the loaded libraries."""
+    tot = [0] * 8
+    for lib in A.loaded():
+        buf = (C.c_longlong * 8)()
+        A.check(lib.unav_gemm_variant_counts(buf, 8), "unav_gemm_variant_counts")
+        tot = [a + int(b) for a, b in zip(tot, buf)]
+    return {GEMM_KERNELS.get(i, f"variant{i}"): n for i, n in enumerate(tot)}
 
 
 def launch_count() -> int:
