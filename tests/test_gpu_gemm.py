@@ -163,6 +163,70 @@ def test_tcgen05_cta_pair_kernel_128_wide(cuda, monkeypatch, op, M, N, Kd, group
     assert all(torch.equal(a, b) for a, b in zip(outs[0][0], outs[1][0]))
 
 
+@pytest.mark.parametrize("op", [K.BF16X2, K.BF16, K.F16X2])
+@pytest.mark.parametrize("M,N,Kd,groups", [(256, 256, 64, 1), (3600, 2048, 512, 2), (3584, 512, 512, 6), (1000, 256, 768, 2),
+                                           (7056, 1024, 352, 1), (16384, 1280, 224, 1), (40000, 512, 96, 1)])
+def test_tcgen05_persistent_pair_kernel(cuda, monkeypatch, op, M, N, Kd, groups):
+    """Persistent cta_group::2 kernel (one cluster per SM pair walking a list of 256 x 256 tiles, two TMEM accumulators):
+    tile counts below / equal to / far above the number of clusters (1 .. 790 tiles), ragged M (second CTA of the last pair
+    partly / wholly out of range), ragged K, grouped launches, full epilogue vs the FP32 reference; and the SAME bits as
+    the one-tile-per-CTA kernels (one canonical accumulation order), also with 1 MMA pass."""
+    from unav_yolyolva_b200 import _cabi
+    monkeypatch.setenv("UNAV_TC_PPAIR", "1")
+    _run(cuda, M, N, Kd, op, K.GEMM_TCGEN05, full_epi=True, act=K.ACT_GELU, groups=groups)
+    g = torch.Generator().manual_seed(13)
+    A, W = torch.randn(M, Kd, generator=g), torch.randn(N, Kd, generator=g) / Kd ** 0.5
+    Aop, Wop = K.pack_operand(A.to(cuda), op), K.pack_operand(W.to(cuda), op)
+    for passes in ((0, 1) if op in K.SPLIT_DTYPES else (0,)):
+        outs = []
+        for pp in ("1", "0"):
+            monkeypatch.setenv("UNAV_TC_PPAIR", pp)
+            o = [torch.empty(M, N, device=cuda) for _ in range(groups)]
+            oo = [K.new_operand(M, N, op, cuda) for _ in range(groups)]
+            K.gemm([{"A": Aop, "W": Wop, "out_f32": oi, "out_op": ooi} for oi, ooi in zip(o, oo)], M, N, Kd, op, K.ACT_NONE, False,
+                   K.GEMM_TCGEN05, passes=passes)
+            outs.append((o, oo, _cabi.load(op).unav_gemm_last_variant()))
+        torch.cuda.synchronize()
+        assert outs[0][2] == 7 and outs[1][2] in (0, 1, 2, 3, 4)
+        assert all(torch.equal(a, b) for a, b in zip(outs[0][0], outs[1][0]))
+        assert all(torch.equal(a, b) for a, b in zip(outs[0][1], outs[1][1]))
+
+
+def test_tcgen05_persistent_pair_kernel_two_streams(cuda, monkeypatch):
+    """Persistent pair kernels of two streams, interleaved with one-CTA kernels and the one-tile pair kernel of a third: no
+    CTA of one cluster kernel can co-reside with another's (each owns its SM's shared and tensor memory), so nothing can wait
+    in a cycle; results stay those of the single-stream run."""
+    op = K.BF16X2
+    g = torch.Generator().manual_seed(14)
+    M, N, Kd = 3584, 512, 512
+    A = K.pack_operand(torch.randn(M, Kd, generator=g).to(cuda), op)
+    W = K.pack_operand((torch.randn(N, Kd, generator=g) / Kd ** 0.5).to(cuda), op)
+    M2, N2, K2 = 7056, 1024, 3072
+    A2 = K.pack_operand(torch.randn(M2, K2, generator=g).to(cuda), op)
+    W2 = K.pack_operand((torch.randn(N2, K2, generator=g) / K2 ** 0.5).to(cuda), op)
+    monkeypatch.setenv("UNAV_TC_PPAIR", "1")
+    ref = torch.empty(M, N, device=cuda)
+    K.gemm([{"A": A, "W": W, "out_f32": ref}], M, N, Kd, op, K.ACT_NONE, False, K.GEMM_TCGEN05)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(cuda) for _ in range(3)]
+    outs = [torch.zeros(M, N, device=cuda) for _ in range(2)]
+    o2 = torch.empty(M2, N2, device=cuda)
+    small = torch.empty(448, 256, device=cuda)
+    for it in range(40):
+        for si in range(2):
+            with torch.cuda.stream(streams[si]):
+                monkeypatch.setenv("UNAV_TC_PPAIR", "1")
+                for _ in range(3):
+                    K.gemm([{"A": A, "W": W, "out_f32": outs[si]}], M, N, Kd, op, K.ACT_NONE, False, K.GEMM_TCGEN05)
+                monkeypatch.setenv("UNAV_TC_PPAIR", "0")
+                K.gemm([{"A": A[:448], "W": W[:256], "out_f32": small}], 448, 256, Kd, op, K.ACT_NONE, False, K.GEMM_TCGEN05)
+        with torch.cuda.stream(streams[2]):
+            monkeypatch.setenv("UNAV_TC_PPAIR", "0")          # the one-tile CTA-pair kernel (256 TMEM columns, two CTAs per SM)
+            K.gemm([{"A": A2, "W": W2, "out_f32": o2}], M2, N2, K2, op, K.ACT_NONE, False, K.GEMM_TCGEN05)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], ref) and torch.equal(outs[1], ref)
+
+
 @pytest.mark.skipif(os.environ.get("UNAV_TEST_EXPERIMENTAL") != "1",
                     reason="128 x 256 tiles (UNAV_TC_BN=256) were written after round 1's GPU budget was spent: first validation pending")
 @pytest.mark.parametrize("op", [K.BF16X2, K.F16X2])

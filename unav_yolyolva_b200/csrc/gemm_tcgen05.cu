@@ -44,7 +44,7 @@ struct TcGroup {
 };
 struct TcParams {
   TcGroup g[UNAV_MAX_GROUPS];
-  int M, N, K, op_dtype, act, res_masked, nseg, stages, once;
+  int M, N, K, op_dtype, act, res_masked, nseg, stages, once, ngroups;
   // implicit k=3 convolution (conv_T > 0): A is the PLAIN operand [items*conv_T, Cin] (K = 3*Cin); a tile is 128 time steps
   // of one item and the k-loop fetches tap t from rows t0 + t - 1 through a 4-D map {Cin, T, items, halves}: rows outside
   // [0, T) are zero-filled by the TMA unit = the per-video zero padding of MaskedConv1D (blocks.py:30-31).  No im2col
@@ -164,46 +164,88 @@ struct TcSmem {
 // Phase B of the epilogue for full-width, 16-byte aligned tiles: one instantiation per (activation, operand format) so
 // the row loop carries no dtype / activation dispatch (the generic loop below executed ~170 instructions per float4).
 // Each lane owns 4 consecutive columns of RPP-strided rows; four rows are in flight per lane.
-template <int ACT, bool SPLIT, int PITCH, int RPP>
+template <int ACT, bool SPLIT, int PITCH, int RPP, int U, int RES = -1>
 __device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const float* stg_lane, long long m_base, int rows,
                                                    int rsub, int n, int res_masked, bool f16, const float (&bias)[4],
                                                    const float (&cs)[4]) {
-  const bool has_res = e.res != nullptr, has_gate = e.gate != nullptr, has_mask = e.rowmask != nullptr,
-             has_rs = e.rowscale != nullptr;
+  // The row loop is LATENCY bound, not issue bound (per-CTA phase stamps: ~450 clocks per row with two epilogue warps per
+  // scheduler, against ~80 issued instructions): so every address is a hoisted pointer that is bumped per batch (the group's
+  // parameters live in constant memory behind a run-time index, and re-deriving `base + m * ld + n` per row put an indexed
+  // constant load and a 64-bit multiply chain on every row's critical path), and rows are processed four at a time with all
+  // loads (staging tile, mask, scale, gate, residual) issued before the first use.
+  static_assert((32 / RPP) % U == 0, "a warp's 32 staged rows must be a whole number of U-row batches per lane");
+  // RES: -1 = residual decided at run time, 0 / 1 = compiled out / in (the persistent kernel's lean epilogue)
+  const bool has_res = RES < 0 ? e.res != nullptr : RES != 0;
+  const bool has_gate = e.gate != nullptr, has_mask = e.rowmask != nullptr,
+             has_rs = e.rowscale != nullptr, has_f32 = e.out_f32 != nullptr, has_op = e.out_op != nullptr;
+  const long long m_first = m_base + rsub;
   const long long op_split = e.ld_op / 2;
-  const int ggrp = has_gate ? n / e.gate_width : 0;       // gate_width % 4 == 0 on this path: one group per lane
-#pragma unroll 4
-  for (int r = rsub; r < rows; r += RPP) {
-    const long long m = m_base + r;
-    const float4 a4 = *reinterpret_cast<const float4*>(stg_lane + r * PITCH);
-    float v[4] = {a4.x, a4.y, a4.z, a4.w};
-    float mk = 1.f, mrs = 1.f;
-    if (has_mask) { mk = e.rowmask[m] ? 1.f : 0.f; mrs = mk; }
-    if (has_rs) mrs *= __ldg(e.rowscale + m);
-    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_res) rr = *reinterpret_cast<const float4*>(e.res + m * e.ldres + n);
+  const float* res_p = has_res ? e.res + m_first * e.ldres + n : nullptr;
+  const long long res_step = static_cast<long long>(RPP) * e.ldres;
+  float* f32_p = has_f32 ? e.out_f32 + m_first * e.ld_f32 + n : nullptr;
+  const long long f32_step = static_cast<long long>(RPP) * e.ld_f32;
+  uint16_t* op_p = has_op ? reinterpret_cast<uint16_t*>(e.out_op) + m_first * e.ld_op + n : nullptr;
+  const long long op_step = static_cast<long long>(RPP) * e.ld_op;
+  const uint8_t* mk_p = has_mask ? e.rowmask + m_first : nullptr;
+  const float* rs_p = has_rs ? e.rowscale + m_first : nullptr;
+  // gate_width % 4 == 0 on this path: one gate group per lane
+  const float* gate_p = has_gate ? e.gate + m_first * e.gate_groups + n / e.gate_width : nullptr;
+  const long long gate_step = static_cast<long long>(RPP) * e.gate_groups;
+  (void)f16;
+#pragma unroll 1
+  for (int r0 = rsub; r0 < rows; r0 += U * RPP) {
+    float4 a[U], rr[U];
+    float mk[U], mrs[U], gt[U];
+    bool ok[U];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = (v[i] + bias[i]) * mrs;
-    if (has_gate) {
-      const float gt = __ldg(e.gate + m * e.gate_groups + ggrp);
+    for (int u = 0; u < U; ++u) {
+      ok[u] = r0 + u * RPP < rows;
+      a[u] = *reinterpret_cast<const float4*>(stg_lane + (r0 + u * RPP) * PITCH);      // always inside the warp's 32 staged rows
+      mk[u] = 1.f; mrs[u] = 1.f; gt[u] = 1.f;
+      rr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] *= gt;
+    for (int u = 0; u < U; ++u) {
+      if (ok[u]) {
+        if (has_mask) { mk[u] = mk_p[u * RPP] ? 1.f : 0.f; mrs[u] = mk[u]; }
+        if (has_rs) mrs[u] *= __ldg(rs_p + u * RPP);
+        if (has_gate) gt[u] = __ldg(gate_p + u * gate_step);
+        if (has_res) rr[u] = *reinterpret_cast<const float4*>(res_p + u * res_step);
+      }
     }
-    if (ACT != UNAV_ACT_NONE) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], ACT);
+    for (int u = 0; u < U; ++u) {
+      float v[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (v[i] + bias[i]) * mrs[u];
+      if (has_gate) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] *= gt[u];
+      }
+      if (ACT != UNAV_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = apply_act_tc(v[i], ACT);
+      }
+      if (has_res) {
+        const float rm = res_masked ? mk[u] : 1.f;
+        v[0] = rr[u].x * rm + cs[0] * v[0]; v[1] = rr[u].y * rm + cs[1] * v[1];
+        v[2] = rr[u].z * rm + cs[2] * v[2]; v[3] = rr[u].w * rm + cs[3] * v[3];
+      }
+      a[u] = make_float4(v[0], v[1], v[2], v[3]);
     }
-    if (has_res) {
-      const float rm = res_masked ? mk : 1.f;
-      v[0] = rr.x * rm + cs[0] * v[0]; v[1] = rr.y * rm + cs[1] * v[1];
-      v[2] = rr.z * rm + cs[2] * v[2]; v[3] = rr.w * rm + cs[3] * v[3];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (ok[u]) {
+        if (has_f32) *reinterpret_cast<float4*>(f32_p + u * f32_step) = a[u];
+        if (has_op) store_op4_16<kHalfF16>(op_p + u * op_step, SPLIT, 0, op_split, a[u]);
+      }
     }
-    if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + m * e.ld_f32 + n) = make_float4(v[0], v[1], v[2], v[3]);
-    if (e.out_op) {
-      char* row = reinterpret_cast<char*>(e.out_op) + static_cast<size_t>(m) * e.ld_op * 2;
-      store_op4(row, SPLIT ? (f16 ? UNAV_F16X2 : UNAV_BF16X2) : (f16 ? UNAV_F16 : UNAV_BF16), n, op_split,
-                make_float4(v[0], v[1], v[2], v[3]));
-    }
+    if (has_mask) mk_p += U * RPP;
+    if (has_rs) rs_p += U * RPP;
+    if (has_gate) gate_p += U * gate_step;
+    if (has_res) res_p += U * res_step;
+    if (has_f32) f32_p += U * f32_step;
+    if (has_op) op_p += U * op_step;
   }
 }
 
@@ -212,7 +254,9 @@ __device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const flo
 // Phase A: tcgen05.ld (one accumulator row per thread) -> padded FP32 staging tile in the (now idle) pipeline smem;
 // phase B: each warp walks its 32 rows x BN/2 columns with lanes across columns, so residual loads and all stores are
 // row-contiguous 128-bit accesses.
-template <int BN>
+// U = rows in flight per lane in the row loop: 4 where the register budget allows (the persistent kernel owns its SM), 2 in
+// the kernels that keep two CTAs resident per SM (96 registers per thread)
+template <int BN, int U = 2>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& g, uint32_t tmem_cols, int m0, int n0,
                                               int warp, int lane, float* stg_base, long long m_limit) {
   constexpr int PITCH = BN + 4;              // floats; 16-byte groups of consecutive rows fall in distinct banks
@@ -286,16 +330,16 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& 
     constexpr bool f16 = kHalfF16;
 #define UNAV_EPI_CASE(A)                                                                                          \
     case A:                                                                                                       \
-      if (split) epilogue_rows_fast<A, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);   \
-      else epilogue_rows_fast<A, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);        \
+      if (split) epilogue_rows_fast<A, true, PITCH, RPP, U>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);   \
+      else epilogue_rows_fast<A, false, PITCH, RPP, U>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);        \
       break;
     switch (act) {
       UNAV_EPI_CASE(UNAV_ACT_RELU)
       UNAV_EPI_CASE(UNAV_ACT_GELU)
       UNAV_EPI_CASE(UNAV_ACT_SILU)
       default:
-        if (split) epilogue_rows_fast<UNAV_ACT_NONE, true, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);
-        else epilogue_rows_fast<UNAV_ACT_NONE, false, PITCH, RPP>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);
+        if (split) epilogue_rows_fast<UNAV_ACT_NONE, true, PITCH, RPP, U>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);
+        else epilogue_rows_fast<UNAV_ACT_NONE, false, PITCH, RPP, U>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);
     }
 #undef UNAV_EPI_CASE
   } else if (nvalid > 0 && (e.out_f32 || e.out_op)) {
@@ -327,7 +371,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& 
       }
       if (act != UNAV_ACT_NONE) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], act);
+        for (int i = 0; i < 4; ++i) v[i] = apply_act_tc(v[i], act);
       }
       if (has_res) {
         const float rm = p.res_masked ? mk : 1.f;
@@ -659,6 +703,258 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
+// Lean epilogue pass of the persistent kernel: one 128 x 64 column block of a TMEM accumulator.  The host has already
+// established what epilogue_tile checks per call (full-width tiles, 16-byte aligned outputs / residual / bias / column scale,
+// gate_width % 4 == 0), so there is no generic fallback and the per-pass set-up is a few dozen instructions (ncu source page of
+// the first version: 359 of the 1 053 instructions a warp executed per pass were set-up).  The bias / column-scale loads are
+// issued before the tensor-memory read so their latency overlaps it.
+template <int U>
+__device__ __forceinline__ void pp_epilogue_pass(const TcParams& p, const TcGroup& g, uint32_t tmem_cols, int m0, int n0, int warp,
+                                                 int lane, float* stg_base, long long m_limit) {
+  constexpr int BN = 64, PITCH = BN + 4, HALF = BN / 2, LPR = HALF / 4, RPP = 32 / LPR;
+  const int q = warp & 3, half = (warp - 2) >> 2;
+  const EpiParams& e = g.epi;
+  float* stg = stg_base + q * 32 * PITCH + half * HALF;
+  const int cl = lane % LPR, rsub = lane / LPR;
+  const int n = n0 + half * HALF + cl * 4;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f};
+  if (e.bias) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    bias[0] = b4.x; bias[1] = b4.y; bias[2] = b4.z; bias[3] = b4.w;
+  }
+  if (e.colscale) {
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(e.colscale + n));
+    cs[0] = c4.x; cs[1] = c4.y; cs[2] = c4.z; cs[3] = c4.w;
+  }
+  {
+    uint32_t r[32];
+    tc_ld_32x32b_x32(tmem_cols + (static_cast<uint32_t>(q * 32) << 16) + half * HALF, r);
+    tc_wait_ld();
+    float* dst = stg + lane * PITCH;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+  }
+  __syncwarp();
+  if (e.out_opT) {       // transposed operand output (V^T for the tensor-core attention), as in epilogue_tile
+    const long long mt = static_cast<long long>(m0) + q * 32 + lane;
+    if (mt < m_limit) {
+      const int ncols = e.t_ncols > 0 ? e.t_ncols : p.N;
+      const long long item = mt / e.t_seg, t = mt % e.t_seg;
+      const long long spl = e.ld_opT / 2;
+      for (int j = 0; j < HALF; ++j) {
+        const int nn = n0 + half * HALF + j;
+        const int nc = nn - e.t_col0;
+        if (nc >= 0 && nc < ncols) {
+          float x = stg[lane * PITCH + j];
+          if (e.bias) x += __ldg(e.bias + nn);
+          char* row = reinterpret_cast<char*>(e.out_opT) + static_cast<size_t>(item * ncols + nc) * e.ld_opT * 2;
+          store_op(row, p.op_dtype, t, spl, x);
+        }
+      }
+    }
+  }
+  if (!(e.out_f32 || e.out_op)) return;
+  const long long m_base = static_cast<long long>(m0) + q * 32;
+  const int rows = static_cast<int>(min(32ll, m_limit - m_base));
+  const float* sl = stg + cl * 4;
+  const bool split = op_is_split(p.op_dtype);
+  constexpr bool f16 = kHalfF16;
+#define UNAV_PP_CASE(A)                                                                                                        \
+  case A:                                                                                                                      \
+    if (e.res) {                                                                                                               \
+      if (split) epilogue_rows_fast<A, true, PITCH, RPP, U, 1>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);      \
+      else epilogue_rows_fast<A, false, PITCH, RPP, U, 1>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);           \
+    } else {                                                                                                                   \
+      if (split) epilogue_rows_fast<A, true, PITCH, RPP, U, 0>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);      \
+      else epilogue_rows_fast<A, false, PITCH, RPP, U, 0>(e, sl, m_base, rows, rsub, n, p.res_masked, f16, bias, cs);           \
+    }                                                                                                                          \
+    break;
+  switch (p.act) {
+    UNAV_PP_CASE(UNAV_ACT_RELU)
+    UNAV_PP_CASE(UNAV_ACT_GELU)
+    UNAV_PP_CASE(UNAV_ACT_SILU)
+    UNAV_PP_CASE(UNAV_ACT_NONE)
+    default: break;
+  }
+#undef UNAV_PP_CASE
+}
+
+// =============================================================================================
+// Persistent CTA-pair variant: ONE cluster of two CTAs per SM pair (74 clusters on a B200) walks a static list of 256 x 256
+// output tiles.  Same operand staging, MMA shape (cta_group::2, M = 256, N = 256) and accumulation order as the kernel above,
+// so the results are bit-identical; what changes is everything AROUND the k-loop, which is what bounds the K = 512 shapes of the
+// hot path (a 128 x 256 CTA-tile there spends ~6 us in its k-loop and ~12 us in TMEM allocation, barrier set-up, the first L2
+// round trip and the epilogue, and the 1.1 - 1.6 wave grids of one-tile CTAs leave SMs idle in the last wave):
+//   * TMEM holds TWO 128 x 256 FP32 accumulators per CTA (all 512 columns): the epilogue warps drain tile i (tcgen05.ld ->
+//     private 64-column staging tiles -> fused row epilogue) while the MMA warp already accumulates tile i+1 into the other half;
+//   * the TMA ring never drains between tiles (the producer runs ahead into the next tile's k-blocks), so set-up, allocation
+//     and the first L2 round trip are paid once per CTA, not once per tile;
+//   * 5 x 32 KB stages (160 KB in flight per SM) + a dedicated 34 KB staging tile: the CTA owns the SM (> half of its shared
+//     memory and all of its tensor memory), so two cluster kernels of different streams can never co-reside on an SM and wait
+//     for each other's tensor memory (the hold-and-wait cycle that CTA pairs with partial allocations can form across streams).
+// Barriers: full[s] / empty[s] as above; tfull[a] (accumulator a complete: commit multicast to both CTAs); tempty[a] lives in
+// rank 0's shared memory and collects one arrival per CTA once its eight epilogue warps have read accumulator a.
+// =============================================================================================
+constexpr int PP_STG_BN = 64;                                   // epilogue staging width (columns per pass)
+constexpr int PP_STG_BYTES = 128 * (PP_STG_BN + 4) * 4;         // 34 816
+constexpr int PP_MAX_SMEM = 227 * 1024;
+
+template <int PN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tcgen05_ppair_kernel(const __grid_constant__ TcParams p) {
+  static_assert(PN == 256, "two 128 x PN accumulators must fill the 512 tensor-memory columns");
+  constexpr int W_PART = (PN / 2) * P2_BK * 2;
+  // 1024-byte aligned by declaration (SWIZZLE_64B / 128B stages): no alignment slack, which is what lets a sixth 32 KB stage fit
+  extern __shared__ __align__(1024) uint8_t pp_smem[];
+  uint8_t* const smem_raw = pp_smem;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0) __trap();
+  const int NS = p.stages;
+  const int nparts = p.nseg > 1 ? 2 : 1;
+  const uint32_t stage_bytes = nparts * (P2_PART + W_PART);
+  const uint32_t w_off = nparts * P2_PART;
+  const uint32_t stg_addr = base + stage_bytes * NS;
+  const uint32_t bar_base = stg_addr + PP_STG_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 4);
+
+  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  // diagnostics (unav_set_phase_trace): 32 int64 per CTA = 4 slots of 8: slot 0 {smid, start, setup done, exit}, slots 1..3 = this
+  // CTA's first three tiles {producer: first load issued, MMA: accumulator free, first operands landed, last MMA issued,
+  // epilogue: accumulator ready, first 64-column pass done, all passes done, accumulator released}
+  long long* ph_out = (p.phase && 4 * static_cast<int>(blockIdx.x) + 3 < p.phase_cap) ? p.phase + 32ll * blockIdx.x : nullptr;
+  if (ph_out && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    ph_out[0] = smid;
+    ph_out[1] = clock_stamp();
+  }
+  const int tiles_m = (p.M + 255) / 256, tiles_n = p.N / PN;
+  const int tiles_per_group = tiles_m * tiles_n;
+  const int ntiles = tiles_per_group * p.ngroups;
+  const int nkb = (p.K + P2_BK - 1) / P2_BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int g = 0; g < p.ngroups; ++g) { tma_prefetch_desc(&p.g[g].tmA); tma_prefetch_desc(&p.g[g].tmW); }
+    for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * PN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  pdl_wait();
+  pdl_launch_dependents();
+  if (ph_out && threadIdx.x == 0) ph_out[2] = clock_stamp();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): k-blocks of this pair's tiles, back to back =====
+      uint32_t it = 0, ti = 0;
+      for (int tile = pair_id; tile < ntiles; tile += npairs, ++ti) {
+        const int g = tile / tiles_per_group, r = tile - g * tiles_per_group;
+        const int n_t = r / tiles_m, m_t = r - n_t * tiles_m;
+        const int m0 = m_t * 256 + static_cast<int>(rank) * 128;
+        const int wn0 = n_t * PN + static_cast<int>(rank) * (PN / 2);
+        const TcGroup& grp = p.g[g];
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (ph_out && kb == 0 && ti < 3) ph_out[8 * (ti + 1) + 0] = clock_stamp();
+          if (rank == 0) mbar_expect_tx(full_bar(s), 2u * stage_bytes);
+          else mbar_arrive_remote(full_bar(s), 0);
+          const uint32_t sa = base + s * stage_bytes;
+          tma_load_3d_pair(sa, &grp.tmA, full_bar(s), kb * P2_BK, m0, 0);
+          tma_load_3d_pair(sa + w_off, &grp.tmW, full_bar(s), kb * P2_BK, wn0, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (rank 0 only) =====
+      const uint32_t idesc = make_idesc(256, PN, kHalfF16);
+      uint32_t it = 0, i = 0;
+      for (int tile = pair_id; tile < ntiles; tile += npairs, ++i) {
+        const uint32_t a = i & 1, aph = (i >> 1) & 1;
+        mbar_wait(tempty_bar(a), aph ^ 1);        // both CTAs' epilogues have drained this accumulator (first use: free)
+        tc_fence_after();
+        if (ph_out && i < 3) ph_out[8 * (i + 1) + 1] = clock_stamp();
+        const uint32_t acc = tmem_base + a * PN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          if (ph_out && kb == 0 && i < 3) ph_out[8 * (i + 1) + 2] = clock_stamp();
+          const uint32_t sa = base + s * stage_bytes;
+          // canonical order: per 32-wide k-step hi.hi, lo.hi, hi.lo
+#pragma unroll
+          for (int seg = 0; seg < 3; ++seg) {
+            if (seg >= p.nseg) break;
+            const uint64_t adesc = make_smem_desc<P2_BK>(sa + (seg == 1 ? P2_PART : 0));
+            const uint64_t bdesc = make_smem_desc<P2_BK>(sa + w_off + (seg == 2 ? W_PART : 0));
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              tc_mma_f16_pair(acc, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > 0 || seg > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit_pair(empty_bar(s));
+        }
+        tc_commit_pair(tfull_bar(a));
+        if (ph_out && i < 3) ph_out[8 * (i + 1) + 3] = clock_stamp();
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue (both CTAs): four 64-column passes over this CTA's 128 x PN accumulator =====
+    float* stg = reinterpret_cast<float*>(smem_raw + (stg_addr - smem_u32(smem_raw)));
+    uint32_t i = 0;
+    for (int tile = pair_id; tile < ntiles; tile += npairs, ++i) {
+      const int g = tile / tiles_per_group, r = tile - g * tiles_per_group;
+      const int n_t = r / tiles_m, m_t = r - n_t * tiles_m;
+      const int m0 = m_t * 256 + static_cast<int>(rank) * 128;
+      const int n0 = n_t * PN;
+      const uint32_t a = i & 1, aph = (i >> 1) & 1;
+      mbar_wait(tfull_bar(a), aph);
+      tc_fence_after();
+      const bool stamp = ph_out && threadIdx.x == 64 && i < 3;
+      if (stamp) ph_out[8 * (i + 1) + 4] = clock_stamp();
+#pragma unroll 1
+      for (int c = 0; c < PN / PP_STG_BN; ++c) {
+        pp_epilogue_pass<4>(p, p.g[g], tmem_base + a * PN + c * PP_STG_BN, m0, n0 + c * PP_STG_BN, warp, lane, stg, p.M);
+        __syncwarp();
+        if (stamp && c == 0) ph_out[8 * (i + 1) + 5] = clock_stamp();
+      }
+      if (stamp) ph_out[8 * (i + 1) + 6] = clock_stamp();
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps have read accumulator a
+      if (threadIdx.x == 64) mbar_arrive_remote(tempty_bar(a), 0);
+      if (stamp) ph_out[8 * (i + 1) + 7] = clock_stamp();
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (ph_out && threadIdx.x == 0) ph_out[3] = clock_stamp();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * PN) : "memory");
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -828,6 +1124,66 @@ static int use_pair(int M, int N, int K, int ngroups) {
   return 0;
 }
 
+// Persistent CTA-pair launch: one cluster per SM pair (at most as many as the device can hold at once), 5 x 32 KB stages.
+static int launch_ppair(TcParams& p, int ngroups, cudaStream_t stream) {
+  static SmemAttr attr = {};
+  static int max_clusters[kMaxDevices] = {};
+  if (int rc = ensure_dyn_smem(gemm_tcgen05_ppair_kernel<256>, attr, PP_MAX_SMEM, "gemm_tcgen05_ppair")) return rc;
+  const int nparts = p.nseg > 1 ? 2 : 1;
+  const int per_stage = nparts * (P2_PART + 128 * P2_BK * 2);
+  const int nkb = (p.K + P2_BK - 1) / P2_BK;
+  int stages = (PP_MAX_SMEM - PP_STG_BYTES - 256) / per_stage;
+  if (const char* env = getenv("UNAV_TC_STAGES")) {
+    const int v = atoi(env);
+    if (v >= 2 && v < stages) stages = v;
+  }
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  const long long tiles = static_cast<long long>((p.M + 255) / 256) * (p.N / 256) * ngroups;
+  if (stages > nkb * 2 && nkb * 2 >= 2) stages = nkb * 2;       // never more ring than two tiles' worth of k-blocks
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  p.once = p.nseg > 1 ? 1 : 0;
+  p.ngroups = ngroups;
+  const size_t smem = static_cast<size_t>(stages) * per_stage + PP_STG_BYTES + 256;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int cap = (dev >= 0 && dev < kMaxDevices) ? max_clusters[dev] : 0;
+  if (cap == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = PP_MAX_SMEM;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_ppair_kernel<256>, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = 74;
+    }
+    cap = n;
+    if (dev >= 0 && dev < kMaxDevices) max_clusters[dev] = cap;
+  }
+  if (const char* env = getenv("UNAV_TC_PPAIR_CLUSTERS")) {       // experiment knob
+    const int v = atoi(env);
+    if (v >= 1 && v < cap) cap = v;
+  }
+  const int npairs = static_cast<int>(tiles < cap ? tiles : cap);
+  launch_pdl(gemm_tcgen05_ppair_kernel<256>, dim3(2 * npairs), dim3(TC_THREADS), smem, stream, p);
+  count_launch();
+  return finish_launch("gemm_tcgen05_ppair");
+}
+
+// Persistent CTA pairs (UNAV_TC_PPAIR: 0 never, 1 whenever the shape allows, unset = the measured policy below).
+// scripts/gemm_ab.py on B200, split operands, cold L2 (profiles/r02_gemm_ab.md): the persistent kernel wins where its tile list
+// is at least two rounds of the 74 clusters (1x[7200,1536,512] 59 -> 48 us, 6x[3584,512,512] 57 -> 49, 3x[7168,512,512] 57 -> 48,
+// 1x[16384,1280,224] 70 -> 62) or one well-filled round with a long k-loop (2x[3600,512,2048] 54 -> 48, 2x[3584,512,1536] 45 -> 41),
+// ties with the one-tile pair kernel on the two head GEMMs (K = 1536 / 3072), and loses where a single partial round leaves
+// the un-overlapped epilogue of a 128 x 256 CTA tile exposed (<= 60 tiles with K = 512, everything with <= 30 tiles).
+static bool use_ppair(int M, int N, int K, int ngroups) {
+  int v = -1;
+  if (const char* env = getenv("UNAV_TC_PPAIR")) v = atoi(env);
+  if (v == 0 || M < 256 || N % 256 != 0 || K < 64) return false;
+  if (v == 1) return true;
+  const long long tiles = static_cast<long long>((M + 255) / 256) * (N / 256) * ngroups;
+  return tiles >= 148 || (tiles >= 56 && K >= 1024);
+}
+
 // which kernel the last tcgen05 GEMM call of this thread used (unav_gemm_last_variant): 0 <64,64>, 1 <128,32>, 2 <128,64>,
 // 3 CTA pair 256 wide, 4 <64,32>, 5 CTA pair 128 wide, 6 <256,32> (experiment); -1 before the first call / for the CUDA-core backend
 thread_local int g_last_variant = -1;
@@ -848,7 +1204,19 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
   if (conv_T > 0)
     UNAV_REQUIRE(M % conv_T == 0 && K % 3 == 0 && (K / 3) % 32 == 0, "gemm_tcgen05: implicit conv needs M %% T == 0 and Cin %% 32 == 0");
   p.conv_T = conv_T; p.conv_cin = conv_T > 0 ? K / 3 : 0; p.conv_tiles = conv_T > 0 ? (conv_T + TC_BM - 1) / TC_BM : 0;
-  const int pair = conv_T == 0 ? use_pair(M, N, K, ngroups) : 0;
+  bool ppair = conv_T == 0 && use_ppair(M, N, K, ngroups);
+  if (ppair) {      // the persistent kernel's lean epilogue has no unaligned fallback: every vector access must be 16-byte clean
+    auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    for (int i = 0; i < ngroups && ppair; ++i) {
+      const UnavGemmGroup& g = groups[i];
+      const long long op_split = g.ld_op / 2;
+      ppair = (!g.out_f32 || (al16(g.out_f32) && g.ld_f32 % 4 == 0)) && (!g.res || (al16(g.res) && g.ldres % 4 == 0)) &&
+              (!g.out_op || ((reinterpret_cast<uintptr_t>(g.out_op) & 7) == 0 && g.ld_op % 4 == 0 && op_split % 4 == 0)) &&
+              (!g.bias || al16(g.bias)) && (!g.colscale || al16(g.colscale)) &&
+              (!g.gate || (g.gate_width > 0 && g.gate_width % 4 == 0));
+    }
+  }
+  const int pair = ppair ? 256 : (conv_T == 0 ? use_pair(M, N, K, ngroups) : 0);
   const TcChoice ch = choose_tile(M, N, K, ngroups, p.nseg);
   const int bn = pair ? pair / 2 : ch.bn, bk = pair ? P2_BK : (ch.sched == 2 ? 32 : 64);
   p.once = ch.sched ? 1 : 0;
@@ -869,8 +1237,10 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
     if ((rc = encode_map(&p.g[i].tmW, g.W, N, K, g.ldw, bn, bk, split, halves))) return rc;
     p.g[i].epi = make_epi(g);
   }
-  g_last_variant = pair == 256 ? 3 : pair == 128 ? 5 : bn == 256 ? 6 : (bn == 128 ? (bk == 32 ? 1 : 2) : (bk == 32 ? 4 : 0));
+  p.ngroups = ngroups;
+  g_last_variant = ppair ? 7 : pair == 256 ? 3 : pair == 128 ? 5 : bn == 256 ? 6 : (bn == 128 ? (bk == 32 ? 1 : 2) : (bk == 32 ? 4 : 0));
   __atomic_fetch_add(&g_variant_counts[g_last_variant], 1ull, __ATOMIC_RELAXED);
+  if (ppair) return launch_ppair(p, ngroups, stream);
   if (pair == 256) return launch_pair<256>(p, ngroups, stream);
   if (pair == 128) return launch_pair<128>(p, ngroups, stream);
   if (bn == 256) return launch_tc<256, 32>(p, ngroups, stream);
