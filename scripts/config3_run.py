@@ -15,6 +15,8 @@ import tempfile
 import time
 import zlib
 
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")      # before torch / libgomp initialise (see bench.py)
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -38,19 +40,15 @@ def main():
     model = make_multimodal_meta_arch("LocPointTransformer", **default_model_cfg())
     model.load_state_dict(synth.trained_like_state_dict(), strict=True)
     model = model.to(dev).eval()
+    torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // max(1, world))))
+    BS = int(os.environ.get("UNAV_CONFIG3_BATCH", 16))
+    res = runner.split_benchmark(model, N, BS, dev, rank, world)
     mine = runner.shard_indices(N, rank, world)
     cache = {i: synth.make_items(1, i)[0] for i in mine}
     load = lambda idxs: [cache[i] for i in idxs]
-    runner.run_shard(model, mine[:64], load)                  # warm-up: weights packed, graphs captured
+    dets, valid = runner.evaluate_split(model, N, load, batch_size=BS)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    dets, valid = runner.evaluate_split(model, N, load)
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = torch.tensor([res["pass_s"]], device=dev)
     if rank == 0:
         d = dets.cpu()
         ids = [f"synth_{i:06d}" for i in range(N)]
@@ -67,9 +65,9 @@ def main():
             t1 = time.perf_counter()
             mAPs, avg = ev.evaluate(runner.detections_to_anet(dets, ids), verbose=False)
             t_map = time.perf_counter() - t1
-        print(json.dumps({"workload": "config 3: %d synthetic videos sharded i %% world" % N, "n_gpus": world,
+        print(json.dumps({"workload": "config 3: %d synthetic videos sharded i %% world" % N, "n_gpus": world, "batch_per_step": BS,
                           "videos_per_s": N / float(dt), "pass_s": float(dt), "all_gathered": bool(valid.all()),
-                          "checksum_crc32": zlib.crc32(d.numpy().tobytes()), "map_eval_s": t_map, "avg_mAP": float(avg),
+                          "checksum_crc32": zlib.crc32(d.numpy().tobytes()), "breakdown": res["rank0_breakdown"], "map_eval_s": t_map, "avg_mAP": float(avg),
                           "mAP_at_tiou": [float(x) for x in np.atleast_1d(mAPs)]}))
     if world > 1:
         dist.barrier()

@@ -131,6 +131,33 @@ def test_device_collate_full_size_and_model_parity():
             assert torch.equal(res[k].cpu(), want[j][k]), (j, k)
 
 
+def test_device_collate_pinned_items_upload_direct_and_pack_thread():
+    """Items whose features already live in pinned host memory are uploaded from where they lie (no host repack); pageable
+    items are packed into the staging slot by the prefetcher's background thread.  Both give the host collate's bytes, in
+    order, for more batches than there are slots."""
+    from unav_yolyolva_b200.ingest import DeviceCollator
+    dev = torch.device("cuda", 0)
+    sizes = [3, 4, 2, 4, 4, 1, 3]
+    for pinned in (False, True):
+        lists, first = [], 40
+        for n in sizes:
+            items = synth.make_items(n, first)
+            if pinned:
+                for it in items:
+                    it["feats"] = {k: v.pin_memory() for k, v in it["feats"].items()}
+            lists.append(items)
+            first += n
+        for threaded in (True, False):
+            coll = DeviceCollator(224, dev, direct_pinned=pinned)
+            first = 40
+            for j, got in enumerate(CudaPrefetcher(iter(lists), dev, collate=coll, depth=3, pack_thread=threaded)):
+                ref = synth.make_batch(sizes[j], 224, first_index=first, with_gt=False)
+                first += sizes[j]
+                assert torch.equal(got["visual"].cpu(), ref["visual"]) and torch.equal(got["audio"].cpu(), ref["audio"])
+                assert torch.equal(got["mask"].cpu(), ref["mask"]) and got["video_id"] == ref["video_id"]
+            assert j == len(sizes) - 1
+
+
 def test_device_collate_rejects_cpu_and_mismatched_lengths():
     from unav_yolyolva_b200.ingest import DeviceCollator
     with pytest.raises(RuntimeError):

@@ -136,6 +136,46 @@ def test_dwconv_ln(cuda, stride, C, n_pre):
         assert (od["out_f32"].cpu() - ref).abs().max() < 3e-5
 
 
+@pytest.mark.parametrize("C,stride,n_pre,n_out,nseg,T", [(512, 1, 2, 3, 6, 224), (256, 1, 0, 3, 5, 56), (512, 2, 0, 1, 4, 112),
+                                                      (256, 2, 0, 1, 3, 14), (512, 1, 0, 2, 3, 7), (256, 1, 2, 3, 2, 1)])
+def test_dwconv_ln_streaming_equals_tiled(cuda, monkeypatch, C, stride, n_pre, n_out, nseg, T):
+    """The streaming dwconv_ln kernel (weights staged once per CTA, 3-row register window per warp) keeps the tiled kernel's
+    per-lane channel mapping and operation order: same bits on FP32 and split-operand outputs, for both strides, with and
+    without pre-LayerNorms, plain depthwise conv (no LN) included, short segments and strips that do not divide them."""
+    if T % stride:
+        pytest.skip("odd length")
+    g = torch.Generator().manual_seed(C + stride + T)
+    To = T // stride
+    xb = torch.randn(nseg * T, C + 128, generator=g).to(cuda)
+    mask = (torch.rand(nseg * To, generator=g) > 0.2).to(torch.uint8).to(cuda)
+    pre = [((torch.rand(C, generator=g) + 0.5).to(cuda), (torch.randn(C, generator=g) * 0.2).to(cuda)) for _ in range(n_pre)]
+    wts = [{"dw": torch.randn(3 * C, generator=g).to(cuda), "ln_w": (torch.rand(C, generator=g) + 0.5).to(cuda),
+            "ln_b": (torch.randn(C, generator=g) * 0.1).to(cuda), "src": (j % 2 if n_pre else -1)} for j in range(n_out)]
+    if n_out == 2:
+        wts[1]["ln_w"] = wts[1]["ln_b"] = None            # plain masked depthwise conv
+    res = {}
+    for mode, strip in (("tiled", None), ("stream", None), ("stream", "3")):
+        monkeypatch.delenv("UNAV_DWCONV_TILED", raising=False)
+        monkeypatch.delenv("UNAV_DWCONV_STRIP", raising=False)
+        monkeypatch.setenv("UNAV_DWCONV_STREAM", "1")
+        if mode == "tiled":
+            monkeypatch.setenv("UNAV_DWCONV_TILED", "1")
+        if strip:
+            monkeypatch.setenv("UNAV_DWCONV_STRIP", strip)
+        outs = []
+        for w in wts:
+            d = {k: v for k, v in w.items() if v is not None}
+            d["out_f32"] = torch.zeros(nseg * To, C, device=cuda)
+            d["out_op"] = K.new_operand(nseg * To, C, K.BF16X2, cuda)
+            outs.append(d)
+        K.dwconv_ln([{"x": K.View(xb, 64, C), "mask_out": mask, "pre": pre, "outs": outs}], nseg, T, stride, C, K.BF16X2)
+        torch.cuda.synchronize()
+        res[(mode, strip)] = [(o["out_f32"].clone(), o["out_op"].clone()) for o in outs]
+    for key in (("stream", None), ("stream", "3")):
+        for (a32, aop), (b32, bop) in zip(res[("tiled", None)], res[key]):
+            assert torch.equal(a32, b32) and torch.equal(aop, bop), key
+
+
 def test_rowcopy_upsample_im2col_stride2(cuda):
     g = torch.Generator().manual_seed(2)
     nseg, C = 3, 256

@@ -329,6 +329,169 @@ dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
 }
 
 // =============================================================================================
+// dwconv_ln, streaming version (the default): same math, same per-lane channel mapping and operation order as
+// dwconv_ln_kernel above (bit-identical outputs, tests/test_gpu_rowops.py), different schedule.  The tiled kernel stages a
+// CTA's weights (up to 39 KB: taps + LN affine of three outputs + two pre-LN affines) for FOUR output rows and sends every
+// input row through shared memory; on the [7168, 512] x 3 stem launches that is 70 MB of weight traffic for 59 MB of data and
+// 57 % issue utilisation on 154 registers.  Here a CTA stages the weights ONCE and each of its warps walks a strip of
+// consecutive output rows of one segment with the three input rows of the current window in REGISTERS (normalised once per
+// input row when a pre-LayerNorm is present: n = (x - mean) * rstd; the per-source affine is one FMA per tap), the next
+// input row's loads issued before the current row is computed.
+// =============================================================================================
+template <int NV, int STRIDE>
+__global__ void __launch_bounds__(256, 2)
+dwconv_ln_stream_kernel(const __grid_constant__ DwLnParams p, int strip) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) float dws_smem[];     // [n_out][dw 3C | ln_w C | ln_b C] then [n_pre][pre_w C | pre_b C]
+  const UnavDwLnGroup& g = p.g[blockIdx.y];
+  constexpr int C = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  {
+    constexpr int C4 = C / 4;
+    for (int oo = 0; oo < p.n_out; ++oo) {
+      const UnavDwLnOut& q = g.out[oo];
+      float4* dst = reinterpret_cast<float4*>(dws_smem + oo * 5 * C);
+      for (int i = threadIdx.x; i < 3 * C4; i += blockDim.x) dst[i] = reinterpret_cast<const float4*>(q.dw)[i];
+      if (q.ln_w)
+        for (int i = threadIdx.x; i < C4; i += blockDim.x) {
+          dst[3 * C4 + i] = reinterpret_cast<const float4*>(q.ln_w)[i];
+          dst[4 * C4 + i] = reinterpret_cast<const float4*>(q.ln_b)[i];
+        }
+    }
+    for (int sidx = 0; sidx < p.n_pre; ++sidx) {
+      float4* dst = reinterpret_cast<float4*>(dws_smem + p.n_out * 5 * C + sidx * 2 * C);
+      for (int i = threadIdx.x; i < C4; i += blockDim.x) {
+        dst[i] = reinterpret_cast<const float4*>(g.pre_w[sidx])[i];
+        dst[C4 + i] = reinterpret_cast<const float4*>(g.pre_b[sidx])[i];
+      }
+    }
+  }
+  __syncthreads();
+  const bool pre = p.n_pre > 0;
+  const size_t es = op_elem_size(p.op_dtype);
+  const int strips_per_seg = (p.seg_len_out + strip - 1) / strip;
+  const int total = p.nseg * strips_per_seg;
+
+  // load input row ti of segment seg (zeros outside the segment); with a pre-LayerNorm the row comes back normalised
+  auto load_row = [&](int seg, int ti, float4 (&v)[NV]) {
+    const bool ok = ti >= 0 && ti < p.seg_len_in;
+    const float* xr = g.x + (static_cast<long long>(seg) * p.seg_len_in + (ok ? ti : 0)) * g.ldx;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      v[j] = ok ? *reinterpret_cast<const float4*>(xr + (j * 32 + lane) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto normalise = [&](float4 (&v)[NV]) {           // statistics exactly as the tiled kernel computes them
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    const float mean = warp_sum(sum) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float a = v[j].x - mean, b = v[j].y - mean, cc = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      v[j].x = (v[j].x - mean) * rstd; v[j].y = (v[j].y - mean) * rstd;
+      v[j].z = (v[j].z - mean) * rstd; v[j].w = (v[j].w - mean) * rstd;
+    }
+  };
+
+  for (int sidx = blockIdx.x * nwarps + warp; sidx < total; sidx += gridDim.x * nwarps) {
+    const int seg = sidx / strips_per_seg;
+    const int t0 = (sidx - seg * strips_per_seg) * strip;
+    const int t1 = min(t0 + strip, p.seg_len_out);
+    float4 w0[NV], w1[NV], w2[NV], nx[NV], nx2[NV];     // window rows STRIDE*t - 1, STRIDE*t, STRIDE*t + 1 and the prefetch
+    load_row(seg, STRIDE * t0 - 1, w0);
+    load_row(seg, STRIDE * t0, w1);
+    load_row(seg, STRIDE * t0 + 1, w2);
+    if (pre) { normalise(w0); normalise(w1); normalise(w2); }
+    for (int t = t0; t < t1; ++t) {
+      const bool more = t + 1 < t1;
+      if (more) {                                     // next window's new rows: in flight while this row is computed
+        if (STRIDE == 1) load_row(seg, t + 2, nx);
+        else { load_row(seg, 2 * t + 2, nx); load_row(seg, 2 * t + 3, nx2); }
+      }
+      const long long r = static_cast<long long>(seg) * p.seg_len_out + t;
+      const float mk = g.mask_out ? (g.mask_out[r] ? 1.f : 0.f) : 1.f;
+      bool okt[3];
+#pragma unroll
+      for (int tap = 0; tap < 3; ++tap) {
+        const int ti = STRIDE * t + tap - 1;
+        okt[tap] = ti >= 0 && ti < p.seg_len_in;
+      }
+      for (int o = 0; o < p.n_out; ++o) {
+        const UnavDwLnOut& od = g.out[o];
+        const bool has_pre = od.src >= 0;
+        const bool has_ln = od.ln_w != nullptr;
+        const float* wo = dws_smem + o * 5 * C;
+        const float* wp = dws_smem + p.n_out * 5 * C + (has_pre ? od.src : 0) * 2 * C;
+        float4 z[NV];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int c = (j * 32 + lane) * 4;
+          const float4 d0 = *reinterpret_cast<const float4*>(wo + c * 3);
+          const float4 d1 = *reinterpret_cast<const float4*>(wo + c * 3 + 4);
+          const float4 d2 = *reinterpret_cast<const float4*>(wo + c * 3 + 8);
+          float4 lw = make_float4(1.f, 1.f, 1.f, 1.f), lb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_pre) { lw = *reinterpret_cast<const float4*>(wp + c); lb = *reinterpret_cast<const float4*>(wp + C + c); }
+          const float wt[4][3] = {{d0.x, d0.y, d0.z}, {d0.w, d1.x, d1.y}, {d1.z, d1.w, d2.x}, {d2.y, d2.z, d2.w}};
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap) {
+            if (!okt[tap]) continue;
+            float4 u = tap == 0 ? w0[j] : (tap == 1 ? w1[j] : w2[j]);
+            if (has_pre) {
+              u.x = u.x * lw.x + lb.x; u.y = u.y * lw.y + lb.y; u.z = u.z * lw.z + lb.z; u.w = u.w * lw.w + lb.w;
+            }
+            acc[0] = fmaf(wt[0][tap], u.x, acc[0]); acc[1] = fmaf(wt[1][tap], u.y, acc[1]);
+            acc[2] = fmaf(wt[2][tap], u.z, acc[2]); acc[3] = fmaf(wt[3][tap], u.w, acc[3]);
+          }
+          z[j] = make_float4(acc[0] * mk, acc[1] * mk, acc[2] * mk, acc[3] * mk);
+          sum += (z[j].x + z[j].y) + (z[j].z + z[j].w);
+        }
+        const float mu = warp_sum(sum) / C;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          z[j].x -= mu; z[j].y -= mu; z[j].z -= mu; z[j].w -= mu;
+          q += (z[j].x * z[j].x + z[j].y * z[j].y) + (z[j].z * z[j].z + z[j].w * z[j].w);
+        }
+        const float rs = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
+        char* op_row = od.out_op ? reinterpret_cast<char*>(od.out_op) + static_cast<size_t>(r) * od.ld_op * es : nullptr;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int c = (j * 32 + lane) * 4;
+          float4 y;
+          if (has_ln) {
+            const float4 nw = *reinterpret_cast<const float4*>(wo + 3 * C + c);
+            const float4 nb = *reinterpret_cast<const float4*>(wo + 4 * C + c);
+            y.x = z[j].x * rs * nw.x + nb.x; y.y = z[j].y * rs * nw.y + nb.y;
+            y.z = z[j].z * rs * nw.z + nb.z; y.w = z[j].w * rs * nw.w + nb.w;
+          } else {
+            y = make_float4(z[j].x + mu, z[j].y + mu, z[j].z + mu, z[j].w + mu);
+          }
+          if (od.out_f32) *reinterpret_cast<float4*>(od.out_f32 + r * od.ld_f32 + c) = y;
+          if (op_row) store_op4(op_row, p.op_dtype, c, od.ld_op / 2, y);
+        }
+      }
+      if (more) {                                     // slide the window
+        if (pre) { normalise(nx); if (STRIDE == 2) normalise(nx2); }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          if (STRIDE == 1) { w0[j] = w1[j]; w1[j] = w2[j]; w2[j] = nx[j]; }
+          else { w0[j] = w2[j]; w1[j] = nx[j]; w2[j] = nx2[j]; }
+        }
+      }
+    }
+  }
+}
+
+// =============================================================================================
 // row copy jobs (gather / nearest up-sample / im2col / concat)
 // =============================================================================================
 struct CopyParams {
@@ -666,6 +829,42 @@ extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg
   for (int i = 0; i < ngroups; ++i) p.g[i] = groups[i];
   p.nseg = nseg; p.seg_len_in = seg_len_in; p.seg_len_out = seg_len_in / stride; p.stride = stride; p.C = C;
   p.n_pre = n_pre; p.n_out = n_out; p.op_dtype = op_dtype; p.eps = eps;
+  // Streaming kernel where it wins (scripts/dwconv_probe.py, B200, cold L2): the launches with pre-LayerNorms over >= 4096 rows
+  // (the stem's 2 x [3584, 512] x 3: 55.3 -> 47.3 us); it ties on the other full-grid launches and loses on the short pyramid
+  // levels, where one CTA per four rows spreads a handful of rows over more SMs.  UNAV_DWCONV_STREAM=1 forces it (tests),
+  // UNAV_DWCONV_TILED=1 disables it.  Both kernels are instruction bound (ncu: ~740 warp instructions per row and output at
+  // 39 % issue utilisation with ~10 resident warps per SM), not bandwidth bound.
+  const char* force_stream = getenv("UNAV_DWCONV_STREAM");
+  const bool want_stream = force_stream ? force_stream[0] == '1'
+                                        : (n_pre > 0 && static_cast<long long>(nseg) * p.seg_len_out * ngroups >= 4096);
+  if ((C == 256 || C == 512) && want_stream && !getenv("UNAV_DWCONV_TILED")) {
+    bool aligned = true;
+    for (int i = 0; i < ngroups; ++i) aligned = aligned && groups[i].ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(groups[i].x) & 15) == 0;
+    if (aligned) {
+      const size_t smem = static_cast<size_t>(5 * n_out + 2 * n_pre) * C * sizeof(float);
+      const long long rows = static_cast<long long>(nseg) * p.seg_len_out;
+      // strip length: enough warps in flight to cover the memory latency (about 12 warps per SM) before strips get longer
+      int strip = static_cast<int>((rows * ngroups + 148 * 12 - 1) / (148 * 12));
+      strip = strip < 2 ? 2 : (strip > 16 ? 16 : strip);
+      if (const char* env = getenv("UNAV_DWCONV_STRIP")) { const int v = atoi(env); if (v >= 1) strip = v; }
+      const int nw = 8;
+      const long long strips = static_cast<long long>(nseg) * ((p.seg_len_out + strip - 1) / strip);
+      long long blocks = (strips + nw - 1) / nw;
+      if (blocks > 148 * 4) blocks = 148 * 4;
+      cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+      dim3 grid(static_cast<unsigned>(blocks), ngroups);
+#define UNAV_DWS_CASE(NVV, STR)                                                                         \
+      if (C == 128 * NVV && stride == STR) {                                                            \
+        static SmemAttr attr = {};                                                                      \
+        if (int rc = ensure_dyn_smem(dwconv_ln_stream_kernel<NVV, STR>, attr, smem, "dwconv_ln")) return rc; \
+        launch_pdl(dwconv_ln_stream_kernel<NVV, STR>, dim3(grid), dim3(32 * nw), smem, st, p, strip);   \
+        count_launch();                                                                                 \
+        return finish_launch("dwconv_ln");                                                              \
+      }
+      UNAV_DWS_CASE(2, 1) UNAV_DWS_CASE(2, 2) UNAV_DWS_CASE(4, 1) UNAV_DWS_CASE(4, 2)
+#undef UNAV_DWS_CASE
+    }
+  }
   const bool narrow = C <= 256;
   const int R = narrow ? 8 : 4;
   const int tiles_per_seg = (p.seg_len_out + R - 1) / R;

@@ -250,7 +250,7 @@ def dwconv_ln(groups: Sequence[dict], nseg: int, seg_len_in: int, stride: int, C
         assert len(g["outs"]) == n_out and len(g.get("pre", [])) == n_pre
         for j, o in enumerate(g["outs"]):
             d = s.out[j]
-            d.dw, d.ln_w, d.ln_b = _p(o["dw"]), _p(o["ln_w"]), _p(o["ln_b"])
+            d.dw, d.ln_w, d.ln_b = _p(o["dw"]), _p(o.get("ln_w")), _p(o.get("ln_b"))
             d.src = o.get("src", -1)
             d.out_f32, d.ld_f32 = _vp(o.get("out_f32")), _vld(o.get("out_f32"))
             d.out_op, d.ld_op = _vp(o.get("out_op")), _vld(o.get("out_op"))

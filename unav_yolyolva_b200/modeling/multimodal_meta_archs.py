@@ -194,6 +194,7 @@ class PtTransformer(nn.Module):
         self._engine_key = None
         self._host_ring = {}
         self._submit_n = 0
+        self._profile = None                    # dict: run_shard(stats=...) collects host-side waits here
 
     @property
     def device(self):
@@ -257,7 +258,13 @@ class PtTransformer(nn.Module):
         slot = ring["slots"][ring["next"]]
         ring["next"] = (ring["next"] + 1) % nslots
         if slot["event"] is not None:
-            slot["event"].synchronize()         # its previous user (a full ring ago) must have retired
+            if self._profile is not None:
+                import time
+                t0 = time.perf_counter()
+                slot["event"].synchronize()
+                self._profile["host_slot_wait_s"] = self._profile.get("host_slot_wait_s", 0.0) + time.perf_counter() - t0
+            else:
+                slot["event"].synchronize()     # its previous user (a full ring ago) must have retired
         return slot
 
     @torch.no_grad()

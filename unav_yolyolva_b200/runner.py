@@ -178,12 +178,16 @@ def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluato
     return mAP, last_losses
 
 
-def run_shard(model, indices: List[int], load_items, batch_size: int = 16, device=None) -> torch.Tensor:
+def run_shard(model, indices: List[int], load_items, batch_size: int = 16, device=None, stats: Optional[dict] = None) -> torch.Tensor:
     """Detections of the videos ``indices`` (this rank's shard) as one device tensor [len(indices), K, 4]
     (seg0, seg1, score, label), through the overlapped public pipeline: ``load_items(list_of_indices)`` returns un-collated
     dataset items (/root/reference/libs/datasets/datasets.py:28-46 layout), ``DeviceCollator`` pads them on the device,
     ``CudaPrefetcher`` uploads batch j+1 under the forward of batch j, ``PtTransformer.submit`` keeps ``model.streams``
-    batches in flight.  Videos with fewer than K detections keep zero rows (score 0)."""
+    batches in flight.  Videos with fewer than K detections keep zero rows (score 0).
+    ``stats`` (optional dict) receives the host-side seconds spent per stage (collate + upload enqueue, submit, waiting for the
+    device), the number of batches and the device time from the first submit to the last detection (CUDA events)."""
+    import time
+
     from .ingest import CudaPrefetcher, DeviceCollator
     net = model.module if hasattr(model, "module") else model
     dev = torch.device(device) if device is not None else net.device
@@ -197,11 +201,32 @@ def run_shard(model, indices: List[int], load_items, batch_size: int = 16, devic
     ar = torch.arange(K_, device=dev)[None]
     pending, tails, row = [], {}, 0
     loader = (load_items(c) for c in chunks)
-    coll = DeviceCollator(net.max_seq_len, dev, max_div_factor=net.max_div_factor)
-    for j, batch in enumerate(CudaPrefetcher(loader, dev, collate=coll, depth=depth + 1)):
+    # the collator owns pinned staging + device slots: keep ONE per model and device, so that a warm-up pass really warms
+    # (a fresh collator per call re-allocated ~100 MB of pinned memory inside every pass: tens of milliseconds, which is what
+    # a 17-batch shard on 8 GPUs cannot hide)
+    coll = getattr(net, "_shard_collator", None)
+    if coll is None or coll.device != dev or coll.T != net.max_seq_len:
+        coll = DeviceCollator(net.max_seq_len, dev, max_div_factor=net.max_div_factor)
+        net._shard_collator = coll
+    t_fetch = t_submit = t_wait = t_tail = 0.0
+    if stats is not None:
+        net._profile = {}
+    ev_first = torch.cuda.Event(enable_timing=True) if stats is not None else None
+    it = iter(CudaPrefetcher(loader, dev, collate=coll, depth=depth + 1))
+    j = 0
+    while True:
+        ta = time.perf_counter()
+        try:
+            batch = next(it)                                # returns batch j, enqueues collate + upload of batch j+1
+        except StopIteration:
+            break
+        tb = time.perf_counter()
+        if ev_first is not None and j == 0:
+            ev_first.record(cur)
         n = len(chunks[j])
         with torch.no_grad():
             h = net.submit(batch)
+            tb2 = time.perf_counter()
             P = h.plan
             ns = P["nms_stream"]
             with torch.cuda.stream(ns):                     # device -> device, behind this step's soft-NMS
@@ -213,19 +238,80 @@ def run_shard(model, indices: List[int], load_items, batch_size: int = 16, devic
                 tails[id(ns)] = ev
         pending.append(h)
         row += n
+        tc = time.perf_counter()
         if len(pending) > depth:
             pending.pop(0)._event.synchronize()             # bounds the host's lead over the device
+        td = time.perf_counter()
+        t_fetch += tb - ta; t_submit += tb2 - tb; t_tail += tc - tb2; t_wait += td - tc
+        j += 1
     for ev in tails.values():
         cur.wait_event(ev)
+    if stats is not None:
+        ev_last = torch.cuda.Event(enable_timing=True)
+        ev_last.record(cur)
+        ev_last.synchronize()
+        stats.update(net._profile)
+        net._profile = None
+        stats.update({"batches": len(chunks), "host_collate_upload_s": t_fetch, "host_submit_s": t_submit, "host_pack_out_s": t_tail,
+                      "host_wait_device_s": t_wait,
+                      "device_first_submit_to_last_detection_s": ev_first.elapsed_time(ev_last) / 1e3 if chunks else 0.0})
     return out
 
 
-def evaluate_split(model, n_videos: int, load_items, batch_size: int = 16, device=None):
+def evaluate_split(model, n_videos: int, load_items, batch_size: int = 16, device=None, stats: Optional[dict] = None):
     """BASELINE.json config 3: a whole split sharded by video index over the ranks of the current process group (or one
     process), one all-gather of the detections.  Returns (detections [n_videos, K, 4] ordered by video index, valid [n_videos])
     on every rank; rank 0 hands them to ``ANETdetection.evaluate`` via ``detections_to_anet``."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     idx = shard_indices(n_videos, rank, world)
-    local = run_shard(model, idx, load_items, batch_size, device)
+    local = run_shard(model, idx, load_items, batch_size, device, stats=stats)
     return gather_detections(local, torch.tensor(idx, dtype=torch.int64, device=local.device), n_videos)
+
+
+def split_benchmark(model, n_videos: int, batch_size: int, device, rank: int, world: int, ms_per_step: Optional[float] = None) -> dict:
+    """BASELINE.json configs[2] as a measurement: the test-split-sized synthetic workload sharded by video index over the
+    ``world`` ranks through the public pipeline, one all-gather of the detections — STRONG scaling (total work fixed).
+    Window: CUDA events on each rank's stream from before the first batch's collate to after the all-gather, max over ranks;
+    weights packed, graphs captured, staging buffers allocated and NCCL warmed before it; the synthetic features are generated
+    in host memory outside the window.  Every rank must call it; the dict is meaningful on every rank (checksum on rank 0's copy)."""
+    import time
+    import zlib
+
+    from . import synth
+    dev = torch.device(device)
+    net = model.module if hasattr(model, "module") else model
+    mine = shard_indices(n_videos, rank, world)
+    items = [synth.make_items(1, i)[0] for i in mine]          # this rank's shard of the synthetic dataset, in host memory
+    cache = dict(zip(mine, items))
+    load = lambda idxs: [cache[i] for i in idxs]
+    K_ = net.test_max_seg_num
+    warm = mine[:(max(1, getattr(net, "streams", 1)) + 2) * batch_size]
+    for _ in range(2):                                        # plans, host rings, every collate slot, allocator
+        run_shard(model, warm, load, batch_size=batch_size, device=dev)
+    gather_detections(torch.zeros(1, K_, 4, device=dev), torch.tensor([rank], device=dev), world)      # NCCL warm-up
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    st: dict = {}
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    c0.record()
+    dets, valid = evaluate_split(model, n_videos, load, batch_size=batch_size, device=dev, stats=st)
+    c1.record()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    tt = torch.tensor([c0.elapsed_time(c1) / 1e3, wall], device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    sec = float(tt[0])
+    out = {"workload": f"configs[2]: {n_videos} synthetic videos sharded i % {world} over {world} GPU(s), detections all-gathered",
+           "scaling": "strong", "videos": n_videos, "n_gpus": world, "videos_per_s": n_videos / sec, "pass_s": sec,
+           "wall_s_max": float(tt[1]), "all_gathered": bool(valid.all().item()),
+           "detections_crc32": zlib.crc32(dets.cpu().numpy().tobytes()),
+           "rank0_breakdown": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in st.items()},
+           "window": "CUDA events from before the first collate to after the all-gather, max over ranks; init / capture / "
+                     "staging allocation / NCCL warm-up excluded"}
+    if ms_per_step is not None:
+        out["ideal_pass_s_at_device_rate"] = (len(mine) / batch_size) * ms_per_step / 1e3
+    return out
