@@ -229,6 +229,17 @@ typedef struct UnavAttnTcGroup {
 int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int nb, int Tq, int Tk,
                       int nh, int hs, float scale, int op_dtype, void* stream);
 
+/* Same contract for ANY key length (BASELINE.json config 4: max_seq_len = 2304; blocks.py:218-240 with T = 2304,
+ * multimodal_backbones.py:845-924 with 2305 tokens): for Tk > 256 the keys are processed in 256-key chunks by separate CTAs
+ * of the same tcgen05 kernel (S and P in tensor memory, chunks beyond a video's valid length skipped), each writing an
+ * un-normalised FP32 partial output and the row's (max, sum) into `workspace`; a second kernel merges the chunks and the
+ * optional extra key.  workspace: at least unav_attention_tc_workspace_bytes(...) bytes (0 for Tk <= 256, where the call is
+ * identical to unav_attention_tc). */
+size_t unav_attention_tc_workspace_bytes(int ngroups, int nb, int Tq, int Tk, int nh, int hs);
+int unav_attention_tc_long(const UnavAttnTcGroup* groups, int ngroups, int nb, int Tq, int Tk,
+                           int nh, int hs, float scale, int op_dtype, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ---- MaxSigmoid gate ----------------------------------------------------------------------- */
 /* gate[r, h] = sigmoid( max_{n<nwords} <x[r, h*hc:(h+1)*hc], G[(r/T)*nwords + n, h*hc:...]> / sqrt(hc)
  *                       + head_bias[h] ),   r < nb*T, h < H.  x, G FP32. */

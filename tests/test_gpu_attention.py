@@ -141,3 +141,65 @@ def test_tc_alignment_attention_with_cross_key(cuda, op, tol):
         ref = _ref(_rt(q, op), _rt(k, op), _rt(v, op), kmask, nh, hs, 0.125, xk, xv, 1)
         err = (_read(out[m * hm:(m + 1) * hm], C, op).view(nb, N, C) - ref).abs().max().item()
         assert err < tol * 4, err
+
+
+@pytest.mark.parametrize("nb,T,nh,hs", [(2, 300, 4, 64), (2, 576, 4, 128), (1, 1152, 4, 64), (1, 2304, 4, 128), (3, 257, 2, 64)])
+@pytest.mark.parametrize("op,tol", [(K.BF16X2, 6e-5), (K.BF16, 2e-2)])
+def test_tc_attention_long_keys_chunked(cuda, nb, T, nh, hs, op, tol):
+    """Key lengths above 256 (BASELINE.json config 4: T = 2304 and the pyramid levels 1152 / 576 / 288): the same tcgen05
+    kernel on 256-key chunks + the merge kernel, vs the FP64 reference; valid lengths that end inside a chunk, exactly at a
+    chunk boundary and before the first chunk's end (trailing chunks skipped), ragged last chunk (T % 256 != 0)."""
+    g = torch.Generator().manual_seed(T + hs)
+    C = nh * hs
+    q, k, v = (torch.randn(nb, T, C, generator=g) for _ in range(3))
+    lens = torch.randint(1, T + 1, (nb,), generator=g)
+    lens[0] = min(T, 256)                                    # boundary case
+    if nb > 1:
+        lens[1] = 70                                         # everything beyond the first chunk is skipped
+    kmask = (torch.arange(T)[None] < lens[:, None]).to(torch.uint8)
+    qo, ko, vt = _tc_inputs(cuda, q, k, v, op)
+    out = K.new_operand(nb * T, C, op, cuda)
+    ws = torch.empty(K.attention_tc_workspace_bytes(1, nb, T, T, nh, hs), dtype=torch.uint8, device=cuda)
+    assert ws.numel() > 0
+    K.attention_tc([{"q": qo, "k": ko, "vt": vt, "kmask": kmask.to(cuda), "out": out}], nb, T, T, nh, hs, 1 / math.sqrt(hs), op,
+                   workspace=ws)
+    torch.cuda.synchronize()
+    ref = _ref(_rt(q, op), _rt(k, op), _rt(v, op), kmask, nh, hs, 1 / math.sqrt(hs))
+    err = (_read(out, C, op).view(nb, T, C) - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), err
+
+
+def test_tc_alignment_attention_long_with_cross_key(cuda):
+    """The Alignment layers at T = 2304 (2305 tokens per modality, 8 heads, the time-aligned token of the other modality as a
+    per-query extra key): chunked tcgen05 kernel + merge with the extra key, two groups in one launch."""
+    op, tol = K.BF16X2, 6e-5
+    g = torch.Generator().manual_seed(5)
+    nb, N, nh, hs = 1, 577, 8, 64
+    C = nh * hs
+    qkv = torch.randn(2, nb, N, 3 * C, generator=g)
+    lens = torch.tensor([400])
+    kmask = torch.cat([torch.ones(nb, 1), (torch.arange(N - 1)[None] < lens[:, None]).float()], 1).to(torch.uint8)
+    d32 = qkv.reshape(2 * nb * N, 3 * C).to(cuda)
+    dop = K.pack_operand(d32, op)
+    hm = nb * N
+    out = K.new_operand(2 * hm, C, op, cuda)
+    vts = []
+    for m in range(2):
+        vt = K.new_operand(nb * C, N, op, cuda)
+        K.transpose_cast(K.View(d32[m * hm:(m + 1) * hm], 2 * C, C), 3 * C, vt, nb, N, C, op)
+        vts.append(vt)
+    groups = []
+    for m in range(2):
+        own, oth = dop[m * hm:(m + 1) * hm], d32[(1 - m) * hm:(2 - m) * hm]
+        groups.append({"q": K.View(own, 0, C), "k": K.View(own, C, C), "vt": vts[m], "kmask": kmask.to(cuda),
+                       "q32": K.View(d32[m * hm:(m + 1) * hm], 0, C), "xk": K.View(oth, C, C), "xv": K.View(oth, 2 * C, C),
+                       "x_first": 1, "out": out[m * hm:(m + 1) * hm]})
+    ws = torch.empty(K.attention_tc_workspace_bytes(2, nb, N, N, nh, hs), dtype=torch.uint8, device=cuda)
+    K.attention_tc(groups, nb, N, N, nh, hs, 0.125, op, workspace=ws)
+    torch.cuda.synchronize()
+    for m in range(2):
+        q, k, v = qkv[m, ..., :C], qkv[m, ..., C:2 * C], qkv[m, ..., 2 * C:]
+        xk, xv = qkv[1 - m, ..., C:2 * C], qkv[1 - m, ..., 2 * C:]
+        ref = _ref(_rt(q, op), _rt(k, op), _rt(v, op), kmask, nh, hs, 0.125, xk, xv, 1)
+        err = (_read(out[m * hm:(m + 1) * hm], C, op).view(nb, N, C) - ref).abs().max().item()
+        assert err < tol * 4, err

@@ -83,6 +83,8 @@ _PROTOS = {
     "unav_dwconv_ln": (c_i, [C.POINTER(DwLnGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp]),
     "unav_attention": (c_i, [C.POINTER(AttnGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp]),
     "unav_attention_tc": (c_i, [C.POINTER(AttnTcGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp]),
+    "unav_attention_tc_workspace_bytes": (C.c_size_t, [c_i, c_i, c_i, c_i, c_i, c_i]),
+    "unav_attention_tc_long": (c_i, [C.POINTER(AttnTcGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp, C.c_size_t, c_vp]),
     "unav_maxsig_gate": (c_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "unav_maxsig_gate_tc": (c_i, [c_vp, c_ll, c_i, c_vp, c_ll, c_i, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "unav_pool_match": (c_i, [c_vp, c_vp, c_vp, c_i, c_i, c_i, c_ll, c_vp, c_vp, c_vp, c_ll, c_i, c_i, c_i, c_i, c_vp]),

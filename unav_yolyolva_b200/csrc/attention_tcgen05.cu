@@ -136,6 +136,12 @@ struct AttnTcParams {
   int q_bytes, kv_bytes;      // smem region sizes
   long long* phase; int phase_cap;   // diagnostics (unav_set_phase_trace)
   float scale;
+  // Key-chunked mode for Tk > 256 (nchunks > 0; BASELINE.json config 4, T = 2304): blockIdx.z also enumerates 256-key
+  // chunks; a CTA attends its 128 queries to ONE chunk and writes the un-normalised partial output (FP32) and the row's
+  // (max, sum) instead of the final rows; attention_merge_kernel combines the chunks (and the optional extra key).
+  int nchunks, ng;
+  float* part_o;              // [nchunks][ng][nb*Tq][nh*hs]
+  float* part_ml;             // [nchunks][ng][nb*Tq][nh][2]
 };
 
 constexpr int ATC_THREADS = 320;     // TMA warp, MMA warp, 8 softmax / epilogue warps (two per TMEM lane quarter)
@@ -192,7 +198,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
   using namespace atc;
   extern __shared__ uint8_t smem_raw[];
-  const int gi = blockIdx.z / p.nb, b = blockIdx.z % p.nb;
+  const bool chunked = p.nchunks > 0;
+  const int zz = chunked ? blockIdx.z % (p.ng * p.nb) : blockIdx.z;
+  const int chunk = chunked ? blockIdx.z / (p.ng * p.nb) : 0;
+  const int k0 = chunk * 256;                    // first key of this CTA's chunk (0 in the single-tile mode)
+  const int gi = zz / p.nb, b = zz % p.nb;
   const AttnTcGroup& g = p.g[gi];
   const int h = blockIdx.y, q0 = blockIdx.x * 128;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -228,8 +238,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
   pdl_wait();                 // PDL: the preceding grid has completed; nothing above touched global memory
   pdl_launch_dependents();    // let the next kernel's CTAs start their prologue
   if (warp < 9) {      // key validity as 8 x 32 bits (+ a zero word for the funnel shift of the last chunk)
-    const int j = warp * 32 + lane;
-    const bool valid = j < p.Tk && (!g.kmask || g.kmask[static_cast<long long>(b) * p.Tk + j]);
+    const int j = k0 + warp * 32 + lane;
+    const bool valid = warp < 8 && j < p.Tk && (!g.kmask || g.kmask[static_cast<long long>(b) * p.Tk + j]);
     const uint32_t w = __ballot_sync(0xffffffffu, valid);
     if (lane == 0) maskw[warp] = w;
   }
@@ -240,22 +250,39 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
   const uint32_t tm_s = tmem_base, tm_p = tmem_base + p.ncols / 2, tm_o = tmem_base;
   if (ph_out && threadIdx.x == 0) ph_out[2] = clock_stamp();
+  // a chunk with no valid key (beyond the video's length) contributes nothing: record sum = 0 and skip the tensor work
+  bool live = true;
+  if (chunked) {
+    uint32_t any = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) any |= maskw[w];
+    live = any != 0;
+  }
 
-  if (warp == 0) {
+  if (!live) {
+    if (warp >= 2 && ((warp - 2) >> 2) == 0) {
+      const int qi = q0 + (warp & 3) * 32 + lane;
+      if (qi < p.Tq) {
+        const long long rowi = static_cast<long long>(b) * p.Tq + qi;
+        float* ml = p.part_ml + (((static_cast<long long>(chunk) * p.ng + gi) * p.nb * p.Tq + rowi) * p.nh + h) * 2;
+        ml[0] = -CUDART_INF_F; ml[1] = 0.f;
+      }
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       // ---- Q tile + K of this (item, head)
       mbar_expect_tx(bar_qk, nparts * kq * (q_box + k_box));
       for (int pt = 0; pt < nparts; ++pt)
         for (int kb = 0; kb < kq; ++kb) {
           tma_load_2d(q_smem + (pt * kq + kb) * q_box, &g.tmQ[pt], bar_qk, h * hs + kb * 64, b * p.Tq + q0);
-          tma_load_2d(kv_smem + (pt * kq + kb) * k_box, &g.tmK[pt], bar_qk, h * hs + kb * 64, b * p.Tk);
+          tma_load_2d(kv_smem + (pt * kq + kb) * k_box, &g.tmK[pt], bar_qk, h * hs + kb * 64, b * p.Tk + k0);
         }
       // ---- V^T once the QK^T MMAs have finished reading K
       mbar_wait(bar_s, 0);
       mbar_expect_tx(bar_v, nparts * nkv * v_box);
       for (int pt = 0; pt < nparts; ++pt)
         for (int kb = 0; kb < nkv; ++kb)
-          tma_load_2d(kv_smem + (pt * nkv + kb) * v_box, &g.tmV[pt], bar_v, kb * 64, b * p.nh * hs + h * hs);
+          tma_load_2d(kv_smem + (pt * nkv + kb) * v_box, &g.tmV[pt], bar_v, k0 + kb * 64, b * p.nh * hs + h * hs);
     }
     __syncwarp();     // lanes 1..31 wait for the elected lane: the block barrier at the end must see whole warps
   } else if (warp == 1) {
@@ -306,7 +333,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
     const int csplit = ((Tkp / 16 + 1) / 2) * 16;
     const int c_lo = half ? csplit : 0, c_hi = half ? Tkp : csplit;
     // optional extra key: s_x = scale * <q_i, xk_i>
-    const bool has_x = g.xk != nullptr && row_ok && qi >= g.x_first;
+    const bool has_x = !chunked && g.xk != nullptr && row_ok && qi >= g.x_first;     // chunked: the merge kernel adds it
     float s_x = -CUDART_INF_F;
     if (has_x) {
       const float* qr = g.q32 + (static_cast<long long>(b) * p.Tq + qi) * g.ldq32 + h * hs;
@@ -388,6 +415,27 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
     mbar_wait(bar_o, 0);
     tc_fence_after();
     if (ph_out && threadIdx.x == 64) ph_out[5] = clock_stamp();
+    if (chunked) {
+      // un-normalised partial output + (max, sum) of this chunk
+      const long long rowi = static_cast<long long>(b) * p.Tq + (row_ok ? qi : 0);
+      const long long slab = (static_cast<long long>(chunk) * p.ng + gi) * p.nb * p.Tq + rowi;
+      if (row_ok && half == 0) {
+        float* ml = p.part_ml + (slab * p.nh + h) * 2;
+        ml[0] = l > 0.f ? mx : -CUDART_INF_F; ml[1] = l;
+      }
+      float* po = p.part_o + slab * (static_cast<long long>(p.nh) * hs) + h * hs;
+#pragma unroll 1
+      for (int c = half * (hs / 2); c < (half + 1) * (hs / 2); c += 16) {
+        uint32_t r[16];
+        ld16(tm_o + lane_addr + c, r);
+        wait_ld();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(po + c + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
+    } else {
     const float inv = 1.0f / l;
     const size_t es = op_elem_size(p.op_dtype);
     char* orow = reinterpret_cast<char*>(g.out) + (static_cast<size_t>(b) * p.Tq + (row_ok ? qi : 0)) * g.ldo * es;
@@ -409,6 +457,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
         store_op4(orow, p.op_dtype, h * hs + c + j, g.ldo / 2, o);
       }
     }
+    }
     if (ph_out && threadIdx.x == 64) ph_out[6] = clock_stamp();
   }
   tc_fence_before();
@@ -418,6 +467,70 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.ncols) : "memory");
   }
+}
+
+// Combine the key chunks of one query row and head (chunked mode): with M = max_c m_c,
+//   out = ( sum_c e^(m_c - M) O_c  +  p_x xv ) / ( sum_c e^(m_c - M) l_c  +  p_x ),   p_x = e^(s_x - M) for the optional extra key
+// (Alignment's time-aligned token of the other modality: s_x = scale <q_i, xk_i>, FP32 rows).  One warp per (row, head).
+struct AttnMergeParams {
+  const float* part_o; const float* part_ml;
+  const float* q32[4]; const float* xk[4]; const float* xv[4];
+  long long ldq32[4], ldx[4];
+  void* out[4]; long long ldo[4];
+  int x_first[4];
+  int nchunks, ng, nb, Tq, nh, hs, op_dtype;
+  float scale;
+};
+
+__global__ void __launch_bounds__(256)
+attention_merge_kernel(const __grid_constant__ AttnMergeParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long rows = static_cast<long long>(p.nb) * p.Tq;
+  const long long rowi = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (rowi >= rows) return;
+  const int h = blockIdx.y, gi = blockIdx.z;
+  const int hs = p.hs, C = p.nh * hs;
+  const int qi = static_cast<int>(rowi % p.Tq);
+  const int per = hs / 32;                                 // 2 | 4 consecutive head columns per lane
+  float s_x = -CUDART_INF_F;
+  const bool has_x = p.xk[gi] != nullptr && qi >= p.x_first[gi];
+  if (has_x) {
+    const float* qr = p.q32[gi] + rowi * p.ldq32[gi] + h * hs;
+    const float* kr = p.xk[gi] + rowi * p.ldx[gi] + h * hs;
+    float a = 0.f;
+    for (int d = lane; d < hs; d += 32) a = fmaf(qr[d], kr[d], a);
+    s_x = warp_sum(a) * p.scale;
+  }
+  float M = s_x;
+  for (int c = 0; c < p.nchunks; ++c)
+    M = fmaxf(M, p.part_ml[((((static_cast<long long>(c) * p.ng + gi) * rows + rowi) * p.nh) + h) * 2]);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float den = 0.f;
+  if (M > -CUDART_INF_F) {
+    for (int c = 0; c < p.nchunks; ++c) {
+      const long long slab = (static_cast<long long>(c) * p.ng + gi) * rows + rowi;
+      const float* ml = p.part_ml + (slab * p.nh + h) * 2;
+      const float l = ml[1];
+      if (l > 0.f) {
+        const float w = __expf(ml[0] - M);
+        den = fmaf(w, l, den);
+        const float* po = p.part_o + slab * C + h * hs + lane * per;
+        for (int i = 0; i < per; ++i) acc[i] = fmaf(w, po[i], acc[i]);
+      }
+    }
+    if (has_x) {
+      const float px = __expf(s_x - M);
+      den += px;
+      const float* xr = p.xv[gi] + rowi * p.ldx[gi] + h * hs + lane * per;
+      for (int i = 0; i < per; ++i) acc[i] = fmaf(px, xr[i], acc[i]);
+    }
+  }
+  const float inv = 1.0f / den;                            // fully masked row: 0 / 0 = NaN, as in the reference's softmax
+  const size_t es = op_elem_size(p.op_dtype);
+  char* orow = reinterpret_cast<char*>(p.out[gi]) + static_cast<size_t>(rowi) * p.ldo[gi] * es;
+  for (int i = 0; i < per; ++i) store_op(orow, p.op_dtype, h * hs + lane * per + i, p.ldo[gi] / 2, acc[i] * inv);
 }
 
 // ---- host ---------------------------------------------------------------------------------------
@@ -554,28 +667,48 @@ maxsig_tcgen05_kernel(const __grid_constant__ MaxsigTcParams p) {
 
 }  // namespace unav
 
-extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int nb, int Tq, int Tk, int nh, int hs,
-                                 float scale, int op_arg, void* stream) {
+static size_t attn_long_ws_bytes(int ngroups, int nb, int Tq, int Tk, int nh, int hs) {
+  const size_t nchunks = static_cast<size_t>((Tk + 255) / 256);
+  const size_t rows = static_cast<size_t>(ngroups) * nb * Tq;
+  return nchunks * rows * (static_cast<size_t>(nh) * hs + 2 * nh) * sizeof(float) + 256;
+}
+
+extern "C" size_t unav_attention_tc_workspace_bytes(int ngroups, int nb, int Tq, int Tk, int nh, int hs) {
+  return Tk > 256 ? attn_long_ws_bytes(ngroups, nb, Tq, Tk, nh, hs) : 0;
+}
+
+static int attention_tc_impl(const UnavAttnTcGroup* groups, int ngroups, int nb, int Tq, int Tk, int nh, int hs,
+                             float scale, int op_arg, void* workspace, size_t ws_bytes, void* stream) {
   using namespace unav;
   const int op_dtype = op_base(op_arg);
   UNAV_REQUIRE(groups && ngroups >= 1 && ngroups <= 4, "attention_tc: bad group count %d", ngroups);
   UNAV_REQUIRE(op_is_16bit(op_dtype), "attention_tc: operands must be BF16 / F16");
   UNAV_REQUIRE_OP(op_dtype, "attention_tc");
   UNAV_REQUIRE(hs == 64 || hs == 128, "attention_tc: head size %d not in {64,128}", hs);
-  UNAV_REQUIRE(nb > 0 && Tq > 0 && Tk > 0 && Tk <= 256 && nh > 0, "attention_tc: bad shape (Tk must be <= 256)");
+  UNAV_REQUIRE(nb > 0 && Tq > 0 && Tk > 0 && nh > 0, "attention_tc: bad shape");
+  const bool chunked = Tk > 256;
+  UNAV_REQUIRE(!chunked || (workspace && ws_bytes >= attn_long_ws_bytes(ngroups, nb, Tq, Tk, nh, hs)),
+               "attention_tc: Tk = %d > 256 needs unav_attention_tc_long with a workspace of unav_attention_tc_workspace_bytes()", Tk);
   AttnTcParams p;
   p.nb = nb; p.Tq = Tq; p.Tk = Tk; p.nh = nh; p.hs = hs; p.op_dtype = op_dtype; p.scale = scale;
-  p.Tkp = (Tk + 15) / 16 * 16;
+  p.Tkp = chunked ? 256 : (Tk + 15) / 16 * 16;
   if (p.Tkp < 64) p.Tkp = 64;          // keys beyond Tk are masked; keeps every MMA / TMA box at least 64 wide
   p.nseg = op_passes(op_arg) == 2 ? 3 : op_passes(op_arg);     // 1 = hi halves only, else the full split
   p.ncols = p.Tkp > 128 ? 512 : 256;
   p.phase = g_phase_buf; p.phase_cap = g_phase_cap;
+  p.nchunks = chunked ? (Tk + 255) / 256 : 0;
+  p.ng = ngroups;
+  p.part_o = nullptr; p.part_ml = nullptr;
+  const long long C = static_cast<long long>(nh) * hs;
+  if (chunked) {
+    p.part_o = reinterpret_cast<float*>(workspace);
+    p.part_ml = p.part_o + static_cast<size_t>(p.nchunks) * ngroups * nb * Tq * C;
+  }
   const int nparts = p.nseg > 1 ? 2 : 1;
   const int kq = hs / 64, nkv = (p.Tkp + 63) / 64;
   p.q_bytes = nparts * kq * 128 * 128;
   const int kbytes = nparts * kq * p.Tkp * 128, vbytes = nparts * nkv * hs * 128;
   p.kv_bytes = ((kbytes > vbytes ? kbytes : vbytes) + 1023) / 1024 * 1024;
-  const long long C = static_cast<long long>(nh) * hs;
   for (int i = 0; i < ngroups; ++i) {
     const UnavAttnTcGroup& s = groups[i];
     UNAV_REQUIRE(s.q && s.k && s.vt && s.out, "attention_tc: null pointer in group %d", i);
@@ -599,10 +732,35 @@ extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int
   const int smem = p.q_bytes + p.kv_bytes + 128 + 4 * 128 * 4 + 1024;     // + barriers, mask words, max/sum exchange, slack
   static SmemAttr attr = {};
   if (int rc = ensure_dyn_smem(attention_tcgen05_kernel, attr, smem, "attention_tc")) return rc;
-  dim3 grid((Tq + 127) / 128, nh, nb * ngroups);
-  launch_pdl(attention_tcgen05_kernel, dim3(grid), dim3(ATC_THREADS), smem, reinterpret_cast<cudaStream_t>(stream), p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((Tq + 127) / 128, nh, nb * ngroups * (chunked ? p.nchunks : 1));
+  launch_pdl(attention_tcgen05_kernel, dim3(grid), dim3(ATC_THREADS), smem, st, p);
   count_launch();
-  return finish_launch("attention_tc");
+  int rc = finish_launch("attention_tc");
+  if (rc || !chunked) return rc;
+  AttnMergeParams m;
+  m.part_o = p.part_o; m.part_ml = p.part_ml;
+  for (int i = 0; i < 4; ++i) {
+    const bool on = i < ngroups;
+    m.q32[i] = on ? groups[i].q32 : nullptr; m.xk[i] = on ? groups[i].xk : nullptr; m.xv[i] = on ? groups[i].xv : nullptr;
+    m.ldq32[i] = on ? groups[i].ldq32 : 0; m.ldx[i] = on ? groups[i].ldx : 0;
+    m.out[i] = on ? groups[i].out : nullptr; m.ldo[i] = on ? groups[i].ldo : 0; m.x_first[i] = on ? groups[i].x_first : 0;
+  }
+  m.nchunks = p.nchunks; m.ng = ngroups; m.nb = nb; m.Tq = Tq; m.nh = nh; m.hs = hs; m.op_dtype = op_dtype; m.scale = scale;
+  dim3 mg(static_cast<unsigned>((static_cast<long long>(nb) * Tq + 7) / 8), nh, ngroups);
+  launch_pdl(attention_merge_kernel, dim3(mg), dim3(256), 0, st, m);
+  count_launch();
+  return finish_launch("attention_merge");
+}
+
+extern "C" int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int nb, int Tq, int Tk, int nh, int hs,
+                                 float scale, int op_arg, void* stream) {
+  return attention_tc_impl(groups, ngroups, nb, Tq, Tk, nh, hs, scale, op_arg, nullptr, 0, stream);
+}
+
+extern "C" int unav_attention_tc_long(const UnavAttnTcGroup* groups, int ngroups, int nb, int Tq, int Tk, int nh, int hs,
+                                      float scale, int op_arg, void* workspace, size_t workspace_bytes, void* stream) {
+  return attention_tc_impl(groups, ngroups, nb, Tq, Tk, nh, hs, scale, op_arg, workspace, workspace_bytes, stream);
 }
 
 

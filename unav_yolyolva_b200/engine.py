@@ -95,8 +95,9 @@ class HotPathEngine:
         self.level_off = [0]
         for t in self.Tl:
             self.level_off.append(self.level_off[-1] + t)
-        # fused tcgen05/TMEM attention for the tensor-core modes (key length <= 256); CUDA-core kernel otherwise
-        self.tc_attn = self.backend == GEMM_TCGEN05 and self.T + 1 <= 256
+        # fused tcgen05/TMEM attention for the tensor-core modes: one tile of keys up to 256 (every level of the T = 224 path),
+        # key-chunked + merge above that (config 4, T = 2304); the CUDA-core kernel serves the fp32 / *_simt modes
+        self.tc_attn = self.backend == GEMM_TCGEN05 and not (self.T + 1 > 256 and os.environ.get("UNAV_ATTN_LONG_SIMT") == "1")   # A/B knob
         self.stage_passes = STAGE_PASSES.get(mode, {})
         self._stage = "alignment"
         self.w: Dict[str, torch.Tensor] = {}
@@ -333,6 +334,9 @@ class HotPathEngine:
         P["F"] = f32(M_al, C); P["F1"] = f32(M_al, C)
         P["Fn"] = opb(M_al, C)
         P["QKV"] = f32(M_al, 3 * C)
+        if self.tc_attn and T + 1 > 256:      # partial outputs + (max, sum) of the key chunks, largest call
+            calls = [(2, B, T + 1, 8, C // 8), (1, NB, T, self.n_head, C // self.n_head), (1, NB, T, 4, C // 4), (1, NB, T, 4, C // 8)]
+            P["att_ws"] = u8(max(K.attention_tc_workspace_bytes(ng, nb_, t_, t_, nh_, hs_) for ng, nb_, t_, nh_, hs_ in calls))
         if self.tc_attn:
             P["QKVop"] = opb(M_al, 3 * C)
             P["VTa"] = opb(NB * C, T + 1)          # values of both modalities transposed per item: [2B*C, T+1]
@@ -420,13 +424,13 @@ class HotPathEngine:
             return {"out_op": sl(qop)}, {"out_op": sl(kop)}, {"out_opT": vtv, "t_seg": T}
         return {"out_f32": sl(q32)}, {"out_f32": sl(k32)}, {"out_f32": sl(v32)}
 
-    def _attend(self, q32, k32, v32, qop, kop, vt, kmask, out, nb, T, nh, hs):
+    def _attend(self, q32, k32, v32, qop, kop, vt, kmask, out, nb, T, nh, hs, ws=None):
         """MaskedMHCA core (blocks.py:218-240): tcgen05 kernel on operand q/k + transposed values, or the CUDA-core one."""
         scale = 1.0 / math.sqrt(hs)
         if self.tc_attn:
             Cc = nh * hs
             K.attention_tc([{"q": qop, "k": kop, "vt": vt[:nb * Cc], "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op,
-                           passes=self.stage_passes.get(self._stage, 0))
+                           passes=self.stage_passes.get(self._stage, 0), workspace=ws)
         else:
             K.attention([{"q": q32, "k": k32, "v": v32, "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op)
 
@@ -515,7 +519,8 @@ class HotPathEngine:
                                    "kmask": P["m_cls"], "xk": View(oth, C, C), "xv": View(oth, 2 * C, C), "x_first": 1,
                                    "out": P["AOa"][g * hm:(g + 1) * hm]})
             if self.tc_attn:
-                K.attention_tc(groups, B, N1, N1, 8, C // 8, 1.0 / math.sqrt(C // 8), op, passes=self.stage_passes.get(self._stage, 0))
+                K.attention_tc(groups, B, N1, N1, 8, C // 8, 1.0 / math.sqrt(C // 8), op, passes=self.stage_passes.get(self._stage, 0),
+                               workspace=P.get("att_ws"))
             else:
                 K.attention(groups, B, N1, N1, 8, C // 8, 1.0 / math.sqrt(C // 8), op)
             self._gemm([{"A": P["AOa"], "W": w["al.m"], "bias": w["al.m.b"], "res": F, "out_f32": F1}], Ma, C, C)
@@ -575,7 +580,8 @@ class HotPathEngine:
                     grp.append(dict({"A": xin[g * half:(g + 1) * half], "W": w[f"{nm}.attn.{key}"], "bias": w[f"{nm}.attn.{key}.b"]}, **o))
             self._gemm(grp, half, C, C)
             hs = C // self.n_head
-            self._attend(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"), P.get("VT"), m0, P["AO"], NB, T, self.n_head, hs)
+            self._attend(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"), P.get("VT"), m0, P["AO"], NB, T, self.n_head, hs,
+                         ws=P.get("att_ws"))
             # out = x*mask + scale_attn * (proj(att)*mask)   (blocks.py:243, :316)
             self._gemm([{"A": P["AO"][g * half:(g + 1) * half], "W": w[nm + ".attn.proj"], "bias": w[nm + ".attn.proj.b"],
                          "rowmask": m0[g * half:(g + 1) * half], "res": X[g * half:(g + 1) * half], "colscale": w[nm + ".sa"],
@@ -631,7 +637,7 @@ class HotPathEngine:
                     for xin, o, key in ((P["Qin"], outs[0], "query"), (P["Kin"], outs[1], "key"), (P["Vin"], outs[2], "value"))],
                    M0, C, C)
         hs = C // 4
-        self._attend(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"), P.get("VT"), m0, P["AO"], NB, T, 4, hs)
+        self._attend(P["Qp"], P["Kp"], P["Vp"], P.get("Qop"), P.get("Kop"), P.get("VT"), m0, P["AO"], NB, T, 4, hs, ws=P.get("att_ws"))
         self._gemm([{"A": P["AO"], "W": w[f"{te}.proj"], "bias": w[f"{te}.proj.b"], "rowmask": m0, "out_f32": P["g2"]}], M0, C, C)
         K.transpose_cast(P["g2"], C, P["gT"], NB, T, C, op)
         self._gemm([dict({"A": P["gT"], "W": w["fu.bu.gfc"], "bias": w["fu.bu.gfc.b"]},
@@ -724,7 +730,7 @@ class HotPathEngine:
             outs = self._qkv_outs(qp, kp, vp, q2op, k2op, P.get("VT2"), Tl, Ch)
             self._gemm([dict({"A": a, "W": w[f"{nm}.{key}"], "bias": w[f"{nm}.{key}.b"]}, **o)
                         for a, o, key in ((q2, outs[0], "query"), (k2, outs[1], "key"), (v2, outs[2], "value"))], M, Ch, Ch)
-            self._attend(qp, kp, vp, q2op, k2op, P.get("VT2"), mask, ao, NB, Tl, 4, Ch // 4)
+            self._attend(qp, kp, vp, q2op, k2op, P.get("VT2"), mask, ao, NB, Tl, 4, Ch // 4, ws=P.get("att_ws"))
             cj = P["c"][j][:M]
             self._gemm([{"A": ao, "W": w[f"{nm}.proj"], "bias": w[f"{nm}.proj.b"], "rowmask": mask, "out_f32": cj,
                          "out_op": View(CAT, C + j * Ch, Ch)}], M, Ch, Ch)

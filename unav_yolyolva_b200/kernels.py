@@ -281,10 +281,15 @@ def attention(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs: in
         A.check(lib.unav_attention(arr, n, nb, Tq, Tk, nh, hs, scale, op_dtype, _stream()), "unav_attention")
 
 
+def attention_tc_workspace_bytes(ngroups: int, nb: int, Tq: int, Tk: int, nh: int, hs: int) -> int:
+    return int(A.load().unav_attention_tc_workspace_bytes(ngroups, nb, Tq, Tk, nh, hs))
+
+
 def attention_tc(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs: int, scale: float, op_dtype: int,
-                 passes: int = 0) -> None:
-    """tcgen05 attention (Tk <= 256): groups carry q, k (operand rows), vt (operand, transposed values), kmask, out and
-    optionally q32 / xk / xv (FP32 rows) + x_first for the per-query extra key."""
+                 passes: int = 0, workspace=None) -> None:
+    """tcgen05 attention: groups carry q, k (operand rows), vt (operand, transposed values), kmask, out and optionally
+    q32 / xk / xv (FP32 rows) + x_first for the per-query extra key.  Tk > 256 (config 4) runs key-chunked and needs
+    ``workspace`` (uint8 tensor of ``attention_tc_workspace_bytes``)."""
     n = len(groups)
     arr = (A.AttnTcGroup * n)()
     for i, g in enumerate(groups):
@@ -299,8 +304,13 @@ def attention_tc(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs:
         s.out, s.ldo = _vp(g["out"]), _vld(g["out"])
     lib = A.load(op_dtype)
     with _Span("attention_tc", 4.0 * n * nb * nh * Tq * Tk * hs, n * nb * nh * hs * (Tq * 8 + Tk * 8), f"{n}x[{nb},{nh},{Tq},{Tk},{hs}]"):
-        A.check(lib.unav_attention_tc(arr, n, nb, Tq, Tk, nh, hs, scale, with_passes(op_dtype, passes), _stream()),
-                "unav_attention_tc")
+        if Tk > 256:
+            assert workspace is not None, "attention_tc: Tk > 256 needs a workspace"
+            A.check(lib.unav_attention_tc_long(arr, n, nb, Tq, Tk, nh, hs, scale, with_passes(op_dtype, passes), _p(workspace),
+                                               workspace.numel() * workspace.element_size(), _stream()), "unav_attention_tc_long")
+        else:
+            A.check(lib.unav_attention_tc(arr, n, nb, Tq, Tk, nh, hs, scale, with_passes(op_dtype, passes), _stream()),
+                    "unav_attention_tc")
 
 
 def maxsig_gate(x, G, head_bias, gate, nb: int, T: int, nwords: int, H: int, hc: int) -> None:
