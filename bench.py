@@ -194,6 +194,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace-out", default=None, help="write the per-launch CUDA-event trace of one eager pass (JSON)")
+    ap.add_argument("--profile-run", action="store_true",
+                    help="profiling aid (ncu): only the timed loop, the e2e loop and the traced pass; skips the >= 1 s window, config 1 / 3 and the CPU legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -326,7 +328,7 @@ def main():
     # a second, >= 1 s window of the same streamed loop (the K-step window above is ~50-70 ms): it also keeps the GPU busy
     # until nvidia-smi has had time to sample clocks under load.  Rank 0 only, no collective inside.
     long_window = None
-    if rank == 0:
+    if rank == 0 and not args.profile_run:
         n_long = int(min(3000, max(Kst, math.ceil(1100.0 / (loop_ms / Kst)))))
         la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         la.record()
@@ -417,7 +419,7 @@ def main():
         return runner.split_benchmark(model, int(os.environ.get("UNAV_CONFIG3_VIDEOS", "2158")), b3, dev, rank, world,
                                       ms_per_step=dev_ms / Kst * b3 / B)
 
-    cfg3 = config3_run()
+    cfg3 = None if args.profile_run else config3_run()
 
     if rank != 0:
         if world > 1:
@@ -539,10 +541,10 @@ def main():
                 "gpu_ms_per_video_streamed": thr, "gpu_videos_per_s_streamed": 1e3 / thr, "steps": n1,
                 "timing": "CUDA events around 30 steps incl. the 256 MiB L2 flush per step, device-resident input"}
 
-    cfg1 = batch1_figures()
+    cfg1 = None if args.profile_run else batch1_figures()
 
     cpu, parity = None, None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not args.profile_run:
         r = run_cpu_arm(B, 6, 1, want_results=True)     # ~10-15 s of CPU work on the box's host cores
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "nms": r["nms"]}
         r1 = run_cpu_arm(1, 8, 2)

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.skipif(not ref_runner.reference_available(), reason="reference tree not shipped (oracle/_ref/reference missing)")
 def test_unmodified_eval_py_on_gpu_matches_reference_cpu_map(cuda, tmp_path):
-    n, first = 24, 200
+    n, first = 64, 200
     tmp = str(tmp_path)
     feat_dir, anno, ckpt, cfg = (os.path.join(tmp, x) for x in ("feats", "anno.json", "ckpt/model.pth.tar", "cfg.yaml"))
     items = ED.write_features(feat_dir, n, first_index=first)
