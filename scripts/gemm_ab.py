@@ -21,7 +21,9 @@ op = K.BF16X2 if (len(sys.argv) < 2 or sys.argv[1] == "x3") else K.BF16
 passes = int(os.environ.get("AB_PASSES", "0"))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-tot = {"default": 0.0, "ppair": 0.0, "best": 0.0}
+# default = the library's policy; ppair = persistent CTA pairs forced (16 epilogue warps); pp8 column = the same with 16 epilogue warps (UNAV_PP_EW=16)
+VARIANTS = (("default", {}), ("ppair", {"UNAV_TC_PPAIR": "1"}), ("pp8", {"UNAV_TC_PPAIR": "1", "UNAV_PP_EW": "16"}))
+tot = {"default": 0.0, "ppair": 0.0, "pp8": 0.0, "best": 0.0}
 for (G, M, N, Kd, act) in SHAPES:
     groups = []
     for g in range(G):
@@ -30,11 +32,10 @@ for (G, M, N, Kd, act) in SHAPES:
         groups.append({"A": A, "W": W, "bias": torch.zeros(N, device=dev), "out_f32": torch.empty(M, N, device=dev),
                        "out_op": K.new_operand(M, N, op, dev)})
     res, outs = {}, {}
-    for name, env in (("default", None), ("ppair", "1")):
-        if env is None:
-            os.environ.pop("UNAV_TC_PPAIR", None)
-        else:
-            os.environ["UNAV_TC_PPAIR"] = env
+    for name, env in VARIANTS:
+        for k in ("UNAV_TC_PPAIR", "UNAV_PP_EW"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
         for _ in range(2):
             K.gemm(groups, M, N, Kd, op, act, False, K.GEMM_TCGEN05, passes=passes)
         var = K.GEMM_KERNELS[_cabi.load(op).unav_gemm_last_variant()]
@@ -55,10 +56,10 @@ for (G, M, N, Kd, act) in SHAPES:
         for _ in range(5):
             flush.zero_(); a.record(); g1.replay(); b.record(); torch.cuda.synchronize(); cold.append(a.elapsed_time(b) * 1e3)
         res[name] = (var, warm, min(cold))
-    same = all(torch.equal(x, y) for x, y in zip(outs["default"], outs["ppair"]))
+    same = all(torch.equal(x, y) for x, y in zip(outs["default"], outs["ppair"])) and all(torch.equal(x, y) for x, y in zip(outs["default"], outs["pp8"]))
     fl = 2.0 * G * M * N * Kd
     d, p_ = res["default"], res["ppair"]
-    tot["default"] += d[2]; tot["ppair"] += p_[2]; tot["best"] += min(d[2], p_[2])
+    tot["default"] += d[2]; tot["ppair"] += p_[2]; tot["pp8"] += res["pp8"][2]; tot["best"] += min(d[2], p_[2])
     print(f"{G}x[{M},{N},{Kd}] act={act} | {d[0][13:]:18s} warm {d[1]:6.1f} cold {d[2]:6.1f} us {fl/d[2]/1e6:6.1f} TF | "
-          f"{p_[0][13:]:18s} warm {p_[1]:6.1f} cold {p_[2]:6.1f} us {fl/p_[2]/1e6:6.1f} TF | x{d[2]/p_[2]:.2f} same_bits={same}", flush=True)
+          f"{p_[0][13:]:18s} warm {p_[1]:6.1f} cold {p_[2]:6.1f} us {fl/p_[2]/1e6:6.1f} TF | pp8 cold {res['pp8'][2]:6.1f} | x{d[2]/p_[2]:.2f} same_bits={same}", flush=True)
 print("sum of cold times (us):", {k: round(v, 1) for k, v in tot.items()})

@@ -102,25 +102,41 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
-// GELU for the tensor-core GEMM epilogues: erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7: one MUFU.RCP, one MUFU.EX2
-// and a degree-5 polynomial, ~16 instructions against ~40 plus a divergent branch for erff).  Measured against float64 over
-// [-8, 8]: GELU max abs error 4.7e-7 — torch's own FP32 CPU GELU, which the reference computes, is at 1.2e-6.  The epilogue of
-// the FFN fc1 GEMMs (N = 2048, the heaviest launches of the step) is issue bound on this function.
+// Single-instruction special functions (MUFU.RCP / MUFU.EX2, flush-to-zero): no range check, no slow-path call.  The IEEE
+// variants (__frcp_rn, division, expf with its denormal rescale) each compile to a reconvergence region (BSSY / BRA / CALL /
+// BSYNC) per ELEMENT, which the compiler cannot interleave across elements — the ncu source page of the fc1 + GELU launch
+// (profiles/r02_ncu_full_ppair.csv) showed ~60 thread instructions per output element executed as one serial chain.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// GELU for the tensor-core GEMM epilogues: erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7): one MUFU.RCP, one MUFU.EX2
+// and a degree-5 polynomial, branch-free (~16 instructions that interleave freely across the elements a lane holds, against
+// ~40 plus a divergent branch for erff).  GELU max abs error vs float64 over [-8, 8]: < 1e-6 (torch's own FP32 CPU GELU, which
+// the reference computes, is at 1.2e-6).  The epilogue of the FFN fc1 GEMMs (N = 2048) is issue bound on this function.
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = x * 0.70710678118654752440f;
   const float a = fabsf(z);
-  const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, a, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float e = __expf(-a * a);
+  const float e = ex2_approx(a * a * -1.4426950408889634f);
   const float erf_abs = fmaf(-poly, e, 1.0f);
   return 0.5f * x * (1.0f + copysignf(erf_abs, z));
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float silu_(float x) { return x / (1.0f + expf(-x)); }
+// SiLU of the tensor-core GEMM epilogues, branch-free: x * rcp(1 + 2^(-x log2 e)); x -> -inf gives -0 like x / (1 + inf)
+__device__ __forceinline__ float silu_fast(float x) { return x * rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -136,7 +152,7 @@ __device__ __forceinline__ float apply_act_tc(float v, int act) {
   switch (act) {
     case UNAV_ACT_RELU: return fmaxf(v, 0.0f);
     case UNAV_ACT_GELU: return gelu_fast(v);
-    case UNAV_ACT_SILU: return silu_(v);
+    case UNAV_ACT_SILU: return silu_fast(v);
     default: return v;
   }
 }

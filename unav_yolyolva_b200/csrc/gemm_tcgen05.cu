@@ -128,6 +128,14 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -164,20 +172,24 @@ struct TcSmem {
 // Phase B of the epilogue for full-width, 16-byte aligned tiles: one instantiation per (activation, operand format) so
 // the row loop carries no dtype / activation dispatch (the generic loop below executed ~170 instructions per float4).
 // Each lane owns 4 consecutive columns of RPP-strided rows; four rows are in flight per lane.
-template <int ACT, bool SPLIT, int PITCH, int RPP, int U, int RES = -1>
-__device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const float* stg_lane, long long m_base, int rows,
-                                                   int rsub, int n, int res_masked, bool f16, const float (&bias)[4],
+template <int ACT, bool SPLIT, int PITCH, int RPP, int U, int RES, bool FULL>
+__device__ __forceinline__ void epilogue_rows_body(const EpiParams& e, const float* stg_lane, long long m_base, int rows,
+                                                   int rsub, int n, int res_masked, const float (&bias)[4],
                                                    const float (&cs)[4]) {
   // The row loop is LATENCY bound, not issue bound (per-CTA phase stamps: ~450 clocks per row with two epilogue warps per
   // scheduler, against ~80 issued instructions): so every address is a hoisted pointer that is bumped per batch (the group's
   // parameters live in constant memory behind a run-time index, and re-deriving `base + m * ld + n` per row put an indexed
-  // constant load and a 64-bit multiply chain on every row's critical path), and rows are processed four at a time with all
+  // constant load and a 64-bit multiply chain on every row's critical path), and rows are processed U at a time with all
   // loads (staging tile, mask, scale, gate, residual) issued before the first use.
+  // FULL: all 32 staged rows of the warp are inside M — no per-row predicate at all (a predicated row is a reconvergence
+  // region per row in SASS, which serialises the U rows that are meant to be in flight together); only the last row tile of a
+  // ragged M takes the predicated instantiation.
   static_assert((32 / RPP) % U == 0, "a warp's 32 staged rows must be a whole number of U-row batches per lane");
   // RES: -1 = residual decided at run time, 0 / 1 = compiled out / in (the persistent kernel's lean epilogue)
   const bool has_res = RES < 0 ? e.res != nullptr : RES != 0;
   const bool has_gate = e.gate != nullptr, has_mask = e.rowmask != nullptr,
              has_rs = e.rowscale != nullptr, has_f32 = e.out_f32 != nullptr, has_op = e.out_op != nullptr;
+  const bool has_rowq = has_gate || has_mask || has_rs;
   const long long m_first = m_base + rsub;
   const long long op_split = e.ld_op / 2;
   const float* res_p = has_res ? e.res + m_first * e.ldres + n : nullptr;
@@ -191,26 +203,31 @@ __device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const flo
   // gate_width % 4 == 0 on this path: one gate group per lane
   const float* gate_p = has_gate ? e.gate + m_first * e.gate_groups + n / e.gate_width : nullptr;
   const long long gate_step = static_cast<long long>(RPP) * e.gate_groups;
-  (void)f16;
 #pragma unroll 1
-  for (int r0 = rsub; r0 < rows; r0 += U * RPP) {
+  for (int r0 = rsub; r0 < (FULL ? 32 : rows); r0 += U * RPP) {
     float4 a[U], rr[U];
     float mk[U], mrs[U], gt[U];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      ok[u] = r0 + u * RPP < rows;
+      ok[u] = FULL || (r0 + u * RPP < rows);
       a[u] = *reinterpret_cast<const float4*>(stg_lane + (r0 + u * RPP) * PITCH);      // always inside the warp's 32 staged rows
       mk[u] = 1.f; mrs[u] = 1.f; gt[u] = 1.f;
       rr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (has_res) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (ok[u]) {
-        if (has_mask) { mk[u] = mk_p[u * RPP] ? 1.f : 0.f; mrs[u] = mk[u]; }
-        if (has_rs) mrs[u] *= __ldg(rs_p + u * RPP);
-        if (has_gate) gt[u] = __ldg(gate_p + u * gate_step);
-        if (has_res) rr[u] = *reinterpret_cast<const float4*>(res_p + u * res_step);
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) rr[u] = *reinterpret_cast<const float4*>(res_p + u * res_step);
+    }
+    if (has_rowq) {       // warp-uniform: one branch around all row-quantity loads of the batch
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (ok[u]) {
+          if (has_mask) { mk[u] = mk_p[u * RPP] ? 1.f : 0.f; mrs[u] = mk[u]; }
+          if (has_rs) mrs[u] *= __ldg(rs_p + u * RPP);
+          if (has_gate) gt[u] = __ldg(gate_p + u * gate_step);
+        }
       }
     }
 #pragma unroll
@@ -247,6 +264,15 @@ __device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const flo
     if (has_f32) f32_p += U * f32_step;
     if (has_op) op_p += U * op_step;
   }
+}
+
+template <int ACT, bool SPLIT, int PITCH, int RPP, int U, int RES = -1>
+__device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const float* stg_lane, long long m_base, int rows,
+                                                   int rsub, int n, int res_masked, bool f16, const float (&bias)[4],
+                                                   const float (&cs)[4]) {
+  (void)f16;
+  if (rows >= 32) epilogue_rows_body<ACT, SPLIT, PITCH, RPP, U, RES, true>(e, stg_lane, m_base, rows, rsub, n, res_masked, bias, cs);
+  else epilogue_rows_body<ACT, SPLIT, PITCH, RPP, U, RES, false>(e, stg_lane, m_base, rows, rsub, n, res_masked, bias, cs);
 }
 
 // Epilogue of one 128 x BN accumulator tile (TMEM columns [tmem_cols, tmem_cols + BN) of this CTA), executed by the 8
@@ -708,15 +734,19 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
 // gate_width % 4 == 0), so there is no generic fallback and the per-pass set-up is a few dozen instructions (ncu source page of
 // the first version: 359 of the 1 053 instructions a warp executed per pass were set-up).  The bias / column-scale loads are
 // issued before the tensor-memory read so their latency overlaps it.
-template <int U>
+template <int U, int EW>
 __device__ __forceinline__ void pp_epilogue_pass(const TcParams& p, const TcGroup& g, uint32_t tmem_cols, int m0, int n0, int warp,
                                                  int lane, float* stg_base, long long m_limit) {
-  constexpr int BN = 64, PITCH = BN + 4, HALF = BN / 2, LPR = HALF / 4, RPP = 32 / LPR;
-  const int q = warp & 3, half = (warp - 2) >> 2;
+  // EW epilogue warps share a 64-column pass: TMEM lane quarter = warp % 4 (a warp can only read its own quarter), column
+  // block = (warp - 2) / 4 of CW = 32 (EW = 8) or 16 (EW = 16) columns.  Sixteen warps: the pass is latency bound (tensor-memory
+  // read -> staging -> residual load -> stores is one dependent chain per warp), so twice the warps is twice the chains in flight.
+  constexpr int BN = 64, PITCH = BN + 4, CW = BN / (EW / 4), LPR = CW / 4, RPP = 32 / LPR;
+  static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
+  const int q = warp & 3, cb = (warp - 2) >> 2;
   const EpiParams& e = g.epi;
-  float* stg = stg_base + q * 32 * PITCH + half * HALF;
+  float* stg = stg_base + q * 32 * PITCH + cb * CW;
   const int cl = lane % LPR, rsub = lane / LPR;
-  const int n = n0 + half * HALF + cl * 4;
+  const int n = n0 + cb * CW + cl * 4;
   float bias[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f};
   if (e.bias) {
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
@@ -727,31 +757,39 @@ __device__ __forceinline__ void pp_epilogue_pass(const TcParams& p, const TcGrou
     cs[0] = c4.x; cs[1] = c4.y; cs[2] = c4.z; cs[3] = c4.w;
   }
   {
-    uint32_t r[32];
-    tc_ld_32x32b_x32(tmem_cols + (static_cast<uint32_t>(q * 32) << 16) + half * HALF, r);
+    uint32_t r[CW];
+    const uint32_t taddr = tmem_cols + (static_cast<uint32_t>(q * 32) << 16) + cb * CW;
+    if constexpr (CW == 32) tc_ld_32x32b_x32(taddr, r);
+    else tc_ld_32x32b_x16(taddr, r);
     tc_wait_ld();
     float* dst = stg + lane * PITCH;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
+    for (int j = 0; j < CW; j += 4)
       *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                                                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
   }
   __syncwarp();
-  if (e.out_opT) {       // transposed operand output (V^T for the tensor-core attention), as in epilogue_tile
+  if (e.out_opT) {       // transposed operand output (V^T for the tensor-core attention): lanes run along the token axis, so
+    // each store instruction writes 32 consecutive keys of one channel row.  Addresses are one hoisted row pointer bumped per
+    // channel (the first version re-derived item * ncols * ld per element with 64-bit multiplies).
     const long long mt = static_cast<long long>(m0) + q * 32 + lane;
-    if (mt < m_limit) {
-      const int ncols = e.t_ncols > 0 ? e.t_ncols : p.N;
-      const long long item = mt / e.t_seg, t = mt % e.t_seg;
+    const int ncols = e.t_ncols > 0 ? e.t_ncols : p.N;
+    const int nc0 = n0 + cb * CW - e.t_col0;               // first transposed row of this warp's column block
+    if (mt < m_limit && nc0 + CW > 0 && nc0 < ncols) {
+      const long long item = mt / e.t_seg, t = mt - item * e.t_seg;
       const long long spl = e.ld_opT / 2;
-      for (int j = 0; j < HALF; ++j) {
-        const int nn = n0 + half * HALF + j;
-        const int nc = nn - e.t_col0;
-        if (nc >= 0 && nc < ncols) {
-          float x = stg[lane * PITCH + j];
-          if (e.bias) x += __ldg(e.bias + nn);
-          char* row = reinterpret_cast<char*>(e.out_opT) + static_cast<size_t>(item * ncols + nc) * e.ld_opT * 2;
-          store_op(row, p.op_dtype, t, spl, x);
-        }
+      uint16_t* row = reinterpret_cast<uint16_t*>(e.out_opT) + (item * ncols + nc0) * e.ld_opT + t;
+      const float* bp = e.bias ? e.bias + n0 + cb * CW : nullptr;
+      const float* sp = stg + lane * PITCH;
+      const bool split_t = op_is_split(p.op_dtype);
+#pragma unroll 4
+      for (int j = 0; j < CW; ++j, row += e.ld_opT) {
+        if (nc0 + j < 0 || nc0 + j >= ncols) continue;
+        float x = sp[j];
+        if (bp) x += __ldg(bp + j);
+        const uint16_t hi = f2h16(x, kHalfF16);
+        row[0] = hi;
+        if (split_t) row[spl] = f2h16(x - h162f(hi, kHalfF16), kHalfF16);
       }
     }
   }
@@ -801,8 +839,8 @@ constexpr int PP_STG_BN = 64;                                   // epilogue stag
 constexpr int PP_STG_BYTES = 128 * (PP_STG_BN + 4) * 4;         // 34 816
 constexpr int PP_MAX_SMEM = 227 * 1024;
 
-template <int PN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+template <int PN, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_ppair_kernel(const __grid_constant__ TcParams p) {
   static_assert(PN == 256, "two 128 x PN accumulators must fill the 512 tensor-memory columns");
   constexpr int W_PART = (PN / 2) * P2_BK * 2;
@@ -935,13 +973,13 @@ gemm_tcgen05_ppair_kernel(const __grid_constant__ TcParams p) {
       if (stamp) ph_out[8 * (i + 1) + 4] = clock_stamp();
 #pragma unroll 1
       for (int c = 0; c < PN / PP_STG_BN; ++c) {
-        pp_epilogue_pass<4>(p, p.g[g], tmem_base + a * PN + c * PP_STG_BN, m0, n0 + c * PP_STG_BN, warp, lane, stg, p.M);
+        pp_epilogue_pass<4, EW>(p, p.g[g], tmem_base + a * PN + c * PP_STG_BN, m0, n0 + c * PP_STG_BN, warp, lane, stg, p.M);
         __syncwarp();
         if (stamp && c == 0) ph_out[8 * (i + 1) + 5] = clock_stamp();
       }
       if (stamp) ph_out[8 * (i + 1) + 6] = clock_stamp();
       tc_fence_before();
-      asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps have read accumulator a
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");      // all epilogue warps have read accumulator a
       if (threadIdx.x == 64) mbar_arrive_remote(tempty_bar(a), 0);
       if (stamp) ph_out[8 * (i + 1) + 7] = clock_stamp();
     }
@@ -1073,7 +1111,12 @@ static int launch_tc(TcParams& p, int ngroups, cudaStream_t stream) {
   const int nparts = (p.once && p.nseg > 1) ? 2 : 1;
   const int nkb = (p.K + BK - 1) / BK;
   const int per_stage = Sm::STAGE_BYTES * nparts;
-  int stages = (ctas <= 148 ? 192 * 1024 : 100 * 1024) / per_stage;
+  int small_ring = 192 * 1024;
+  if (const char* env = getenv("UNAV_TC_SMALL_RING_KB")) {     // experiment knob: ring bytes of sub-wave grids (co-residency vs depth)
+    const int v = atoi(env);
+    if (v >= 32 && v <= 192) small_ring = v * 1024;
+  }
+  int stages = (ctas <= 148 ? small_ring : 100 * 1024) / per_stage;
   if (const char* env = getenv("UNAV_TC_STAGES")) {            // experiment knob (scripts/gemm_probe.py)
     const int v = atoi(env);
     if (v >= 2) stages = v;
@@ -1124,11 +1167,16 @@ static int use_pair(int M, int N, int K, int ngroups) {
   return 0;
 }
 
-// Persistent CTA-pair launch: one cluster per SM pair (at most as many as the device can hold at once), 5 x 32 KB stages.
-static int launch_ppair(TcParams& p, int ngroups, cudaStream_t stream) {
+// Persistent CTA-pair launch: one cluster per SM pair (at most as many as the device can hold at once), 6 x 32 KB stages.
+// EW = epilogue warps per CTA: 8 (UNAV_PP_EW=16 selects sixteen for A/B runs: measured SLOWER on every shape of the path, e.g.
+// fc1 + GELU 2x[3600,2048,512] 59.4 -> 71.7 us, 1x[7200,1536,512] 47.0 -> 57.3 us — the epilogue competes with the TMA fill and the
+// MMA operand reads for shared-memory bandwidth, not for latency-hiding warps).
+template <int EW>
+static int launch_ppair_ew(TcParams& p, int ngroups, cudaStream_t stream) {
   static SmemAttr attr = {};
   static int max_clusters[kMaxDevices] = {};
-  if (int rc = ensure_dyn_smem(gemm_tcgen05_ppair_kernel<256>, attr, PP_MAX_SMEM, "gemm_tcgen05_ppair")) return rc;
+  constexpr int THREADS = 64 + 32 * EW;
+  if (int rc = ensure_dyn_smem(gemm_tcgen05_ppair_kernel<256, EW>, attr, PP_MAX_SMEM, "gemm_tcgen05_ppair")) return rc;
   const int nparts = p.nseg > 1 ? 2 : 1;
   const int per_stage = nparts * (P2_PART + 128 * P2_BK * 2);
   const int nkb = (p.K + P2_BK - 1) / P2_BK;
@@ -1150,9 +1198,9 @@ static int launch_ppair(TcParams& p, int ngroups, cudaStream_t stream) {
   int cap = (dev >= 0 && dev < kMaxDevices) ? max_clusters[dev] : 0;
   if (cap == 0) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = PP_MAX_SMEM;
+    cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = PP_MAX_SMEM;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_ppair_kernel<256>, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_ppair_kernel<256, EW>, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
       n = 74;
     }
@@ -1164,9 +1212,14 @@ static int launch_ppair(TcParams& p, int ngroups, cudaStream_t stream) {
     if (v >= 1 && v < cap) cap = v;
   }
   const int npairs = static_cast<int>(tiles < cap ? tiles : cap);
-  launch_pdl(gemm_tcgen05_ppair_kernel<256>, dim3(2 * npairs), dim3(TC_THREADS), smem, stream, p);
+  launch_pdl(gemm_tcgen05_ppair_kernel<256, EW>, dim3(2 * npairs), dim3(THREADS), smem, stream, p);
   count_launch();
   return finish_launch("gemm_tcgen05_ppair");
+}
+static int launch_ppair(TcParams& p, int ngroups, cudaStream_t stream) {
+  const char* env = getenv("UNAV_PP_EW");          // read per call: scripts/gemm_ab.py switches it inside one process
+  const int ew = (env && atoi(env) == 16) ? 16 : 8;
+  return ew == 8 ? launch_ppair_ew<8>(p, ngroups, stream) : launch_ppair_ew<16>(p, ngroups, stream);
 }
 
 // Persistent CTA pairs (UNAV_TC_PPAIR: 0 never, 1 whenever the shape allows, unset = the measured policy below).

@@ -98,6 +98,7 @@ class HotPathEngine:
         # fused tcgen05/TMEM attention for the tensor-core modes: one tile of keys up to 256 (every level of the T = 224 path),
         # key-chunked + merge above that (config 4, T = 2304); the CUDA-core kernel serves the fp32 / *_simt modes
         self.tc_attn = self.backend == GEMM_TCGEN05 and not (self.T + 1 > 256 and os.environ.get("UNAV_ATTN_LONG_SIMT") == "1")   # A/B knob
+        self.attn_simt_max_t = int(os.environ.get("UNAV_ATTN_SIMT_MAX_T", "0"))      # A/B knob, see _tc_attn_for
         self.stage_passes = STAGE_PASSES.get(mode, {})
         self._stage = "alignment"
         self.w: Dict[str, torch.Tensor] = {}
@@ -415,11 +416,17 @@ class HotPathEngine:
     def _gemm(self, groups, M, N, Kd, act=ACT_NONE, res_masked=False):
         K.gemm(groups, M, N, Kd, self.op, act, res_masked, self.backend, passes=self.stage_passes.get(self._stage, 0))
 
+    def _tc_attn_for(self, T):
+        """Tensor-core attention for this key length?  Short pyramid levels (T <= attn_simt_max_t) take the FP32 CUDA-core
+        kernel: a (item, head) there is a <= 28 x 28 score matrix — one 128-query tcgen05 tile would be >= 78 % padding and
+        hold a whole SM (168 registers x 320 threads, TMEM) for ~13 us, while the CUDA-core CTA is 128 threads / 53 KB."""
+        return self.tc_attn and T > self.attn_simt_max_t
+
     def _qkv_outs(self, q32, k32, v32, qop, kop, vt, T, Cc, rows=None, items=None):
         """Output routing of the q / k / v projection GEMMs.  Tensor-core attention: q, k as operand rows and the
         values written TRANSPOSED per item ([item*Cc + channel, key]) straight from the GEMM epilogue."""
         sl = (lambda t: t) if rows is None else (lambda t: t[rows[0]:rows[1]])
-        if self.tc_attn:
+        if self._tc_attn_for(T):
             vtv = vt if items is None else vt[items[0] * Cc:items[1] * Cc]
             return {"out_op": sl(qop)}, {"out_op": sl(kop)}, {"out_opT": vtv, "t_seg": T}
         return {"out_f32": sl(q32)}, {"out_f32": sl(k32)}, {"out_f32": sl(v32)}
@@ -427,7 +434,7 @@ class HotPathEngine:
     def _attend(self, q32, k32, v32, qop, kop, vt, kmask, out, nb, T, nh, hs, ws=None):
         """MaskedMHCA core (blocks.py:218-240): tcgen05 kernel on operand q/k + transposed values, or the CUDA-core one."""
         scale = 1.0 / math.sqrt(hs)
-        if self.tc_attn:
+        if self._tc_attn_for(T):
             Cc = nh * hs
             K.attention_tc([{"q": qop, "k": kop, "vt": vt[:nb * Cc], "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op,
                            passes=self.stage_passes.get(self._stage, 0), workspace=ws)
