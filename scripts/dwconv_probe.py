@@ -27,10 +27,8 @@ for (G, nseg, T, stride, C, n_pre, n_out, f32) in SHAPES:
                        "pre": [(torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev)) for _ in range(n_pre)], "outs": outs})
     line = f"{G}x[{nseg}x{T},{C}] s{stride} pre{n_pre} out{n_out}:"
     for name in ("tiled", "stream"):
-        if name == "tiled":
-            os.environ["UNAV_DWCONV_TILED"] = "1"
-        else:
-            os.environ.pop("UNAV_DWCONV_TILED", None)
+        os.environ.pop("UNAV_DWCONV_TILED", None); os.environ.pop("UNAV_DWCONV_STREAM", None)
+        os.environ["UNAV_DWCONV_TILED" if name == "tiled" else "UNAV_DWCONV_STREAM"] = "1"
         for _ in range(2):
             K.dwconv_ln(groups, nseg, T, stride, C, op)
         torch.cuda.synchronize()

@@ -338,6 +338,70 @@ dwconv_ln_kernel(const __grid_constant__ DwLnParams p) {
 // input row when a pre-LayerNorm is present: n = (x - mean) * rstd; the per-source affine is one FMA per tap), the next
 // input row's loads issued before the current row is computed.
 // =============================================================================================
+// One (output row, output) pair of the streaming kernel: taps over the three window rows held in registers, mask, LayerNorm,
+// stores.  PRE / EDGE are compile-time so that the interior rows (all but the first and last row of a segment) carry no per-tap
+// test at all: the ncu source page of the first version showed 30 reconvergence regions (BSSY / BSYNC) and 52 branches per
+// pair, most of them the `skip this tap` test repeated per float4 chunk.  Without a pre-LayerNorm a window row outside the
+// segment is all zeros and fmaf(w, 0, acc) == acc, so the test is not needed there either (same bits as skipping the tap).
+template <int NV, bool PRE, bool EDGE>
+__device__ __forceinline__ void dws_pair(const float4 (&w0)[NV], const float4 (&w1)[NV], const float4 (&w2)[NV], const float* wo,
+                                         const float* wp, bool ok0, bool ok2, float mk, float eps, const UnavDwLnOut& od,
+                                         long long r, int lane, int op_dtype) {
+  constexpr int C = NV * 128;
+  const bool has_ln = od.ln_w != nullptr;
+  float4 z[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    const float4 d0 = *reinterpret_cast<const float4*>(wo + c * 3);
+    const float4 d1 = *reinterpret_cast<const float4*>(wo + c * 3 + 4);
+    const float4 d2 = *reinterpret_cast<const float4*>(wo + c * 3 + 8);
+    float4 lw = make_float4(1.f, 1.f, 1.f, 1.f), lb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (PRE) { lw = *reinterpret_cast<const float4*>(wp + c); lb = *reinterpret_cast<const float4*>(wp + C + c); }
+    const float wt[4][3] = {{d0.x, d0.y, d0.z}, {d0.w, d1.x, d1.y}, {d1.z, d1.w, d2.x}, {d2.y, d2.z, d2.w}};
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+      if (PRE && EDGE && ((tap == 0 && !ok0) || (tap == 2 && !ok2))) continue;      // warp-uniform, edge rows only
+      float4 u = tap == 0 ? w0[j] : (tap == 1 ? w1[j] : w2[j]);
+      if (PRE) {
+        u.x = u.x * lw.x + lb.x; u.y = u.y * lw.y + lb.y; u.z = u.z * lw.z + lb.z; u.w = u.w * lw.w + lb.w;
+      }
+      acc[0] = fmaf(wt[0][tap], u.x, acc[0]); acc[1] = fmaf(wt[1][tap], u.y, acc[1]);
+      acc[2] = fmaf(wt[2][tap], u.z, acc[2]); acc[3] = fmaf(wt[3][tap], u.w, acc[3]);
+    }
+    z[j] = make_float4(acc[0] * mk, acc[1] * mk, acc[2] * mk, acc[3] * mk);
+    sum += (z[j].x + z[j].y) + (z[j].z + z[j].w);
+  }
+  const float mu = warp_sum(sum) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    z[j].x -= mu; z[j].y -= mu; z[j].z -= mu; z[j].w -= mu;
+    q += (z[j].x * z[j].x + z[j].y * z[j].y) + (z[j].z * z[j].z + z[j].w * z[j].w);
+  }
+  const float rs = 1.0f / sqrtf(warp_sum(q) / C + eps);
+  const size_t es = op_elem_size(op_dtype);
+  char* op_row = od.out_op ? reinterpret_cast<char*>(od.out_op) + static_cast<size_t>(r) * od.ld_op * es : nullptr;
+  float* f32_row = od.out_f32 ? od.out_f32 + r * od.ld_f32 : nullptr;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    float4 y;
+    if (has_ln) {
+      const float4 nw = *reinterpret_cast<const float4*>(wo + 3 * C + c);
+      const float4 nb = *reinterpret_cast<const float4*>(wo + 4 * C + c);
+      y.x = z[j].x * rs * nw.x + nb.x; y.y = z[j].y * rs * nw.y + nb.y;
+      y.z = z[j].z * rs * nw.z + nb.z; y.w = z[j].w * rs * nw.w + nb.w;
+    } else {
+      y = make_float4(z[j].x + mu, z[j].y + mu, z[j].z + mu, z[j].w + mu);
+    }
+    if (f32_row) *reinterpret_cast<float4*>(f32_row + c) = y;
+    if (op_row) store_op4(op_row, op_dtype, c, od.ld_op / 2, y);
+  }
+}
+
 template <int NV, int STRIDE>
 __global__ void __launch_bounds__(256, 2)
 dwconv_ln_stream_kernel(const __grid_constant__ DwLnParams p, int strip) {
@@ -369,7 +433,6 @@ dwconv_ln_stream_kernel(const __grid_constant__ DwLnParams p, int strip) {
   }
   __syncthreads();
   const bool pre = p.n_pre > 0;
-  const size_t es = op_elem_size(p.op_dtype);
   const int strips_per_seg = (p.seg_len_out + strip - 1) / strip;
   const int total = p.nseg * strips_per_seg;
 
@@ -417,66 +480,16 @@ dwconv_ln_stream_kernel(const __grid_constant__ DwLnParams p, int strip) {
       }
       const long long r = static_cast<long long>(seg) * p.seg_len_out + t;
       const float mk = g.mask_out ? (g.mask_out[r] ? 1.f : 0.f) : 1.f;
-      bool okt[3];
-#pragma unroll
-      for (int tap = 0; tap < 3; ++tap) {
-        const int ti = STRIDE * t + tap - 1;
-        okt[tap] = ti >= 0 && ti < p.seg_len_in;
-      }
+      const bool ok0 = STRIDE * t - 1 >= 0, ok2 = STRIDE * t + 1 < p.seg_len_in;      // tap 1 is always inside the segment
       for (int o = 0; o < p.n_out; ++o) {
         const UnavDwLnOut& od = g.out[o];
-        const bool has_pre = od.src >= 0;
-        const bool has_ln = od.ln_w != nullptr;
         const float* wo = dws_smem + o * 5 * C;
-        const float* wp = dws_smem + p.n_out * 5 * C + (has_pre ? od.src : 0) * 2 * C;
-        float4 z[NV];
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const int c = (j * 32 + lane) * 4;
-          const float4 d0 = *reinterpret_cast<const float4*>(wo + c * 3);
-          const float4 d1 = *reinterpret_cast<const float4*>(wo + c * 3 + 4);
-          const float4 d2 = *reinterpret_cast<const float4*>(wo + c * 3 + 8);
-          float4 lw = make_float4(1.f, 1.f, 1.f, 1.f), lb = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_pre) { lw = *reinterpret_cast<const float4*>(wp + c); lb = *reinterpret_cast<const float4*>(wp + C + c); }
-          const float wt[4][3] = {{d0.x, d0.y, d0.z}, {d0.w, d1.x, d1.y}, {d1.z, d1.w, d2.x}, {d2.y, d2.z, d2.w}};
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int tap = 0; tap < 3; ++tap) {
-            if (!okt[tap]) continue;
-            float4 u = tap == 0 ? w0[j] : (tap == 1 ? w1[j] : w2[j]);
-            if (has_pre) {
-              u.x = u.x * lw.x + lb.x; u.y = u.y * lw.y + lb.y; u.z = u.z * lw.z + lb.z; u.w = u.w * lw.w + lb.w;
-            }
-            acc[0] = fmaf(wt[0][tap], u.x, acc[0]); acc[1] = fmaf(wt[1][tap], u.y, acc[1]);
-            acc[2] = fmaf(wt[2][tap], u.z, acc[2]); acc[3] = fmaf(wt[3][tap], u.w, acc[3]);
-          }
-          z[j] = make_float4(acc[0] * mk, acc[1] * mk, acc[2] * mk, acc[3] * mk);
-          sum += (z[j].x + z[j].y) + (z[j].z + z[j].w);
-        }
-        const float mu = warp_sum(sum) / C;
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          z[j].x -= mu; z[j].y -= mu; z[j].z -= mu; z[j].w -= mu;
-          q += (z[j].x * z[j].x + z[j].y * z[j].y) + (z[j].z * z[j].z + z[j].w * z[j].w);
-        }
-        const float rs = 1.0f / sqrtf(warp_sum(q) / C + p.eps);
-        char* op_row = od.out_op ? reinterpret_cast<char*>(od.out_op) + static_cast<size_t>(r) * od.ld_op * es : nullptr;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const int c = (j * 32 + lane) * 4;
-          float4 y;
-          if (has_ln) {
-            const float4 nw = *reinterpret_cast<const float4*>(wo + 3 * C + c);
-            const float4 nb = *reinterpret_cast<const float4*>(wo + 4 * C + c);
-            y.x = z[j].x * rs * nw.x + nb.x; y.y = z[j].y * rs * nw.y + nb.y;
-            y.z = z[j].z * rs * nw.z + nb.z; y.w = z[j].w * rs * nw.w + nb.w;
-          } else {
-            y = make_float4(z[j].x + mu, z[j].y + mu, z[j].z + mu, z[j].w + mu);
-          }
-          if (od.out_f32) *reinterpret_cast<float4*>(od.out_f32 + r * od.ld_f32 + c) = y;
-          if (op_row) store_op4(op_row, p.op_dtype, c, od.ld_op / 2, y);
+        if (od.src >= 0) {
+          const float* wp = dws_smem + p.n_out * 5 * C + od.src * 2 * C;
+          if (ok0 && ok2) dws_pair<NV, true, false>(w0, w1, w2, wo, wp, true, true, mk, p.eps, od, r, lane, p.op_dtype);
+          else dws_pair<NV, true, true>(w0, w1, w2, wo, wp, ok0, ok2, mk, p.eps, od, r, lane, p.op_dtype);
+        } else {
+          dws_pair<NV, false, false>(w0, w1, w2, wo, nullptr, true, true, mk, p.eps, od, r, lane, p.op_dtype);
         }
       }
       if (more) {                                     // slide the window
@@ -533,6 +546,59 @@ rowcopy_kernel(const __grid_constant__ CopyParams p) {
   const long long total = static_cast<long long>(jb.nseg) * jb.seg_len_out * jb.ntaps * (jb.C / 4);
   if (total + static_cast<long long>(gridDim.x) * blockDim.x < (1LL << 31)) rowcopy_body<unsigned int>(jb, p.op_dtype, total);
   else rowcopy_body<long long>(jb, p.op_dtype, total);
+}
+
+// k = 3 im2col of same-length segments as a SCATTER (every job of the launch has ntaps == 3, num == den, C / 4 a power of two
+// and a 16-bit operand type): one thread per SOURCE float4 — loaded once, converted to its hi / lo halves once, stored to the
+// three (output row, tap) positions that read it (row t+1 tap 0, row t tap 1, row t-1 tap 2), zeros for the taps that fall
+// outside the segment.  The gather form above loads and converts every source element three times and pays three integer
+// divisions per element (ncu: 68 % issue utilisation, math-pipe throttle, 2.1 TB/s of writes on the head's 87 MB operand).
+// grid: (ceil(max seg_len * C/4 / 256), max nseg, njobs)
+__global__ void __launch_bounds__(256)
+rowcopy_im2col_kernel(const __grid_constant__ CopyParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const UnavCopyJob& jb = p.j[blockIdx.z];
+  const int seg = blockIdx.y;
+  if (seg >= jb.nseg) return;
+  const int cv = jb.C / 4;
+  const int shift = 31 - __clz(cv);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int t = i >> shift, c = (i & (cv - 1)) * 4;
+  const int T = jb.seg_len_in;
+  if (t >= T) return;
+  const float4 v = *reinterpret_cast<const float4*>(jb.src + (static_cast<long long>(seg) * T + t) * jb.ld_src + c);
+  const bool split = op_is_split(p.op_dtype);
+  const long long sp = jb.ld_dst / 2;
+  uint2 pk, pl = make_uint2(0u, 0u);
+  if (kHalfF16) {
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+    if (split) {
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+      pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+    }
+  } else {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+    if (split) {
+      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+      pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+    }
+  }
+  uint16_t* d0 = reinterpret_cast<uint16_t*>(jb.dst) + (static_cast<long long>(seg) * jb.dst_seg_stride + jb.dst_row_off + t) * jb.ld_dst + c;
+  const uint2 zero = make_uint2(0u, 0u);
+  auto put = [&](uint16_t* q, uint2 hi, uint2 lo) {
+    *reinterpret_cast<uint2*>(q) = hi;
+    if (split) *reinterpret_cast<uint2*>(q + sp) = lo;
+  };
+  put(d0 + jb.tap_stride, pk, pl);                                         // row t, tap 1
+  if (t + 1 < T) put(d0 + jb.ld_dst, pk, pl);                              // row t + 1, tap 0
+  else put(d0 + 2 * jb.tap_stride, zero, zero);                            // last row: its tap 2 reads past the segment
+  if (t > 0) put(d0 - jb.ld_dst + 2 * jb.tap_stride, pk, pl);              // row t - 1, tap 2
+  else put(d0, zero, zero);                                                // first row: its tap 0 reads before the segment
 }
 
 // =============================================================================================
@@ -829,14 +895,16 @@ extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg
   for (int i = 0; i < ngroups; ++i) p.g[i] = groups[i];
   p.nseg = nseg; p.seg_len_in = seg_len_in; p.seg_len_out = seg_len_in / stride; p.stride = stride; p.C = C;
   p.n_pre = n_pre; p.n_out = n_out; p.op_dtype = op_dtype; p.eps = eps;
-  // Streaming kernel where it wins (scripts/dwconv_probe.py, B200, cold L2): the launches with pre-LayerNorms over >= 4096 rows
-  // (the stem's 2 x [3584, 512] x 3: 55.3 -> 47.3 us); it ties on the other full-grid launches and loses on the short pyramid
-  // levels, where one CTA per four rows spreads a handful of rows over more SMs.  UNAV_DWCONV_STREAM=1 forces it (tests),
-  // UNAV_DWCONV_TILED=1 disables it.  Both kernels are instruction bound (ncu: ~740 warp instructions per row and output at
-  // 39 % issue utilisation with ~10 resident warps per SM), not bandwidth bound.
+  // Streaming kernel where it wins (scripts/dwconv_probe.py, B200, cold L2, round 2 after the per-tap branches were compiled
+  // out): every launch over >= 3584 input rows — the stem's 2 x [3584, 512] x 3 with pre-LayerNorms 55.3 -> 44.9 us, the CSP
+  // blocks' [7168, 256] x 3 30.6 -> 26.6, [7168, 512] stride 2 22.5 -> 18.4, [3584, 512] stride 2 14.3 -> 13.1, a tie at
+  // [3584, 256] x 3 — and the tiled kernel on the short pyramid levels (<= 1792 rows: 13.2 vs 15.2 us at T = 56, 9 vs 14 below),
+  // where one CTA per eight rows spreads a handful of rows over more SMs.  UNAV_DWCONV_STREAM=1 forces it (tests),
+  // UNAV_DWCONV_TILED=1 disables it.  Both kernels are latency / issue bound (a warp owns a strip of 4 - 16 rows and a CTA
+  // first stages 15 - 39 KB of weights for 32 - 128 rows of data), not bandwidth bound: 1.1 - 1.6 TB/s of algorithmic bytes.
   const char* force_stream = getenv("UNAV_DWCONV_STREAM");
   const bool want_stream = force_stream ? force_stream[0] == '1'
-                                        : (n_pre > 0 && static_cast<long long>(nseg) * p.seg_len_out * ngroups >= 4096);
+                                        : (static_cast<long long>(nseg) * seg_len_in * ngroups >= 3584);
   if ((C == 256 || C == 512) && want_stream && !getenv("UNAV_DWCONV_TILED")) {
     bool aligned = true;
     for (int i = 0; i < ngroups; ++i) aligned = aligned && groups[i].ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(groups[i].x) & 15) == 0;
@@ -896,6 +964,25 @@ extern "C" int unav_rowcopy(const UnavCopyJob* jobs, int njobs, int op_dtype, vo
     maxtotal = tot > maxtotal ? tot : maxtotal;
   }
   p.op_dtype = op_dtype;
+  {   // scatter form for k = 3 im2col jobs of same-length segments (see rowcopy_im2col_kernel)
+    bool scatter = op_is_16bit(op_dtype) && !getenv("UNAV_ROWCOPY_GATHER");
+    int max_seg = 0, max_work = 0;
+    for (int i = 0; i < njobs && scatter; ++i) {
+      const UnavCopyJob& j = jobs[i];
+      const int cv = j.C / 4;
+      scatter = j.ntaps == 3 && j.num == j.den && j.seg_len_in == j.seg_len_out && cv > 0 && (cv & (cv - 1)) == 0 &&
+                j.ld_src % 4 == 0 && j.ld_dst % 8 == 0 && j.tap_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(j.src) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(j.dst) & 7) == 0 && static_cast<long long>(j.seg_len_in) * cv < (1LL << 30);
+      max_seg = j.nseg > max_seg ? j.nseg : max_seg;
+      max_work = j.seg_len_in * cv > max_work ? j.seg_len_in * cv : max_work;
+    }
+    if (scatter && max_seg > 0 && max_seg <= 65535 && max_work > 0) {
+      dim3 grid(static_cast<unsigned>((max_work + 255) / 256), static_cast<unsigned>(max_seg), njobs);
+      launch_pdl(rowcopy_im2col_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p);
+      count_launch();
+      return finish_launch("rowcopy");
+    }
+  }
   long long blocks = (maxtotal + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
