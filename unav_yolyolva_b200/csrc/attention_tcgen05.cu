@@ -645,14 +645,26 @@ maxsig_tcgen05_kernel(const __grid_constant__ MaxsigTcParams p) {
     const int t = t0 + qd * 32 + lane;
     mbar_wait(bar_s, 0);
     tc_fence_after();
+    // 64 scores per round trip to tensor memory (two x32 loads in flight, four independent max chains); a warp whose 32 rows
+    // all lie beyond T (short pyramid levels: T = 7 .. 56 of a 128-row tile) skips the read.  The first version waited on a
+    // 16-column load 32 times in a row: a ~4 k-clock dependent chain per CTA whatever T was.
     float mx = -CUDART_INF_F;
+    if (t0 + qd * 32 < p.T) {
+      float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < p.nwords; c += 16) {
-      uint32_t r[16];
-      ld16(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + c, r);
-      wait_ld();
+      for (int c = 0; c < p.nwords; c += 64) {
+        uint32_t ra[32], rb[32];
+        ld32(taddr + c, ra);
+        ld32(taddr + c + 32, rb);
+        wait_ld();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        for (int j = 0; j < 32; j += 2) {
+          m0 = fmaxf(m0, __uint_as_float(ra[j])); m1 = fmaxf(m1, __uint_as_float(ra[j + 1]));
+          m2 = fmaxf(m2, __uint_as_float(rb[j])); m3 = fmaxf(m3, __uint_as_float(rb[j + 1]));
+        }
+      }
+      mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     }
     if (t < p.T)
       p.gate[(static_cast<long long>(b) * p.T + t) * p.H + h] = sigmoidf_(mx * (1.0f / sqrtf(static_cast<float>(p.hc))) + p.head_bias[h]);

@@ -325,21 +325,26 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& 
                       (e.ld_op % 4 == 0) && (op_split % 4 == 0);
   if (e.out_opT) {
     // transposed operand output (V^T for the tensor-core attention): lanes run along the token axis, so each
-    // store instruction writes 32 consecutive keys of one channel row
+    // store instruction writes 32 consecutive keys of one channel row; one hoisted row pointer bumped per channel
     const long long mt = static_cast<long long>(m0) + q * 32 + lane;
-    if (mt < m_limit) {
-      const int ncols = e.t_ncols > 0 ? e.t_ncols : p.N;
-      const long long item = mt / e.t_seg, t = mt % e.t_seg;
+    const int ncols = e.t_ncols > 0 ? e.t_ncols : p.N;
+    const int nc0 = n0 + half * HALF - e.t_col0;           // first transposed row of this warp's column block
+    const int jend = min(HALF, p.N - (n0 + half * HALF));  // columns of the block inside N
+    if (mt < m_limit && nc0 + HALF > 0 && nc0 < ncols) {
+      const long long item = mt / e.t_seg, t = mt - item * e.t_seg;
       const long long spl = e.ld_opT / 2;
-      for (int j = 0; j < HALF; ++j) {
-        const int nn = n0 + half * HALF + j;
-        const int nc = nn - e.t_col0;
-        if (nn < p.N && nc >= 0 && nc < ncols) {
-          float x = stg[lane * PITCH + j];
-          if (e.bias) x += __ldg(e.bias + nn);
-          char* row = reinterpret_cast<char*>(e.out_opT) + static_cast<size_t>(item * ncols + nc) * e.ld_opT * 2;
-          store_op(row, p.op_dtype, t, spl, x);
-        }
+      uint16_t* row = reinterpret_cast<uint16_t*>(e.out_opT) + (item * ncols + nc0) * e.ld_opT + t;
+      const float* bp = e.bias ? e.bias + n0 + half * HALF : nullptr;
+      const float* sp = stg + lane * PITCH;
+      const bool split_t = op_is_split(p.op_dtype);
+#pragma unroll 4
+      for (int j = 0; j < jend; ++j, row += e.ld_opT) {
+        if (nc0 + j < 0 || nc0 + j >= ncols) continue;
+        float x = sp[j];
+        if (bp) x += __ldg(bp + j);
+        const uint16_t hi = f2h16(x, kHalfF16);
+        row[0] = hi;
+        if (split_t) row[spl] = f2h16(x - h162f(hi, kHalfF16), kHalfF16);
       }
     }
   }
