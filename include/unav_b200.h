@@ -214,7 +214,10 @@ int unav_attention(const UnavAttnGroup* groups, int ngroups, int nb, int Tq, int
  * head h at columns [h*hs, (h+1)*hs); vt: the values TRANSPOSED per batch item, operand dtype [nb*nh*hs, ldvt >= Tk]
  * (row = item*C + channel, column = key), e.g. unav_transpose_cast(v, nb, R = Tk, Cc = C).  The optional extra key uses FP32 rows q32 / xk / xv
  * (token-major, ld = ldq32 / ldx).  out has operand dtype.  S = Q.K^T and O = P.V run as tcgen05.mma with the
- * accumulators and P in tensor memory; BF16X2 operands use the 3-pass split for FP32-level accuracy. */
+ * accumulators and P in tensor memory; BF16X2 operands use the 3-pass split for FP32-level accuracy.
+ * Masked work is not executed: keys beyond an item's last valid key (kmask) are neither loaded nor multiplied nor
+ * exponentiated — they contribute exactly 0 in the reference's softmax (blocks.py:233-236) — so the cost of an item follows
+ * its valid length, not the padded one. */
 typedef struct UnavAttnTcGroup {
   const void* q;  long long ldq;
   const void* k;  long long ldk;
@@ -224,6 +227,10 @@ typedef struct UnavAttnTcGroup {
   const float* xk; const float* xv; long long ldx;
   void* out; long long ldo;
   int x_first; int pad_;
+  /* optional [nb, Tq] query validity (NULL = all valid): a 128-query tile whose queries are all invalid is skipped and its
+   * output rows are written as zeros (the reference computes them and multiplies them by the mask afterwards,
+   * blocks.py:243).  Ignored for Tk > 256. */
+  const uint8_t* qmask;
 } UnavAttnTcGroup;
 
 int unav_attention_tc(const UnavAttnTcGroup* groups, int ngroups, int nb, int Tq, int Tk,

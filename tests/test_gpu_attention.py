@@ -110,6 +110,38 @@ def test_tc_attention(cuda, nb, T, nh, hs, op, tol):
     assert err < tol * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("nb,T,nh,hs", [(4, 224, 4, 64), (3, 224, 4, 128), (3, 112, 4, 64), (4, 225, 8, 64)])
+def test_tc_attention_skips_masked_work(cuda, nb, T, nh, hs):
+    """Keys beyond an item's last valid key are neither loaded nor multiplied (cost follows the valid length), and with a
+    query mask the 128-query tiles without a valid query are skipped: valid rows equal the reference (and the un-masked
+    call to rounding), rows of skipped tiles are exactly zero (finite, so the masked projection that follows stays finite)."""
+    op = K.BF16X2
+    g = torch.Generator().manual_seed(11 * T + hs)
+    C = nh * hs
+    q, k, v = (torch.randn(nb, T, C, generator=g) for _ in range(3))
+    lens = torch.tensor([1, 70, 128, 129, T][:nb] if nb > 3 else [17, 128, T - 5])
+    kmask = (torch.arange(T)[None] < lens[:, None]).to(torch.uint8)
+    qo, ko, vt = _tc_inputs(cuda, q, k, v, op)
+    out_a = K.new_operand(nb * T, C, op, cuda); out_a.fill_(7.0)
+    out_b = K.new_operand(nb * T, C, op, cuda)
+    scale = 1 / math.sqrt(hs)
+    K.attention_tc([{"q": qo, "k": ko, "vt": vt, "kmask": kmask.to(cuda), "qmask": kmask.to(cuda), "out": out_a}], nb, T, T, nh, hs, scale, op)
+    K.attention_tc([{"q": qo, "k": ko, "vt": vt, "kmask": kmask.to(cuda), "out": out_b}], nb, T, T, nh, hs, scale, op)
+    torch.cuda.synchronize()
+    ref = _ref(_rt(q, op), _rt(k, op), _rt(v, op), kmask, nh, hs, scale)
+    a, b_ = _read(out_a, C, op).view(nb, T, C), _read(out_b, C, op).view(nb, T, C)
+    tol = 4e-5 * max(1.0, ref.abs().max().item())
+    assert (b_ - ref).abs().max().item() < tol
+    for i in range(nb):
+        L = int(lens[i])
+        assert (a[i, :L] - ref[i, :L]).abs().max().item() < tol                  # valid queries
+        assert torch.equal(a[i, :L], b_[i, :L])                                   # same bits with and without the query mask
+        first_skipped = ((L + 127) // 128) * 128                                  # tiles that hold no valid query
+        if first_skipped < T:
+            assert torch.count_nonzero(a[i, first_skipped:]) == 0
+        assert torch.isfinite(a[i]).all()
+
+
 @pytest.mark.parametrize("op,tol", [(K.BF16X2, 4e-5), (K.BF16, 2e-2)])
 def test_tc_alignment_attention_with_cross_key(cuda, op, tol):
     g = torch.Generator().manual_seed(3)

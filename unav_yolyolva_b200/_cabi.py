@@ -61,7 +61,7 @@ class AttnGroup(C.Structure):
 class AttnTcGroup(C.Structure):
     _fields_ = [("q", c_vp), ("ldq", c_ll), ("k", c_vp), ("ldk", c_ll), ("vt", c_vp), ("ldvt", c_ll), ("kmask", c_vp),
                 ("q32", c_vp), ("ldq32", c_ll), ("xk", c_vp), ("xv", c_vp), ("ldx", c_ll), ("out", c_vp), ("ldo", c_ll),
-                ("x_first", c_i), ("pad_", c_i)]
+                ("x_first", c_i), ("pad_", c_i), ("qmask", c_vp)]
 
 
 class CopyJob(C.Structure):

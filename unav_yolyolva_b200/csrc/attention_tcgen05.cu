@@ -129,6 +129,7 @@ struct AttnTcGroup {
   long long ldq32, ldx;
   void* out; long long ldo;
   int x_first;
+  const uint8_t* qmask;
 };
 struct AttnTcParams {
   AttnTcGroup g[4];
@@ -217,7 +218,9 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
   const int nparts = p.nseg > 1 ? 2 : 1;
   const int kq = hs / 64;                       // 64-column boxes along the head dim
   const int nkv = (Tkp + 63) / 64;              // 64-key boxes of V^T
-  const int q_box = 128 * 128, k_box = Tkp * 128, v_box = hs * 128;
+  // K is fetched in 64-key boxes into a region of ceil(Tkp / 64) * 64 rows per (part, 64-channel block), so that only the boxes
+  // up to the item's last valid key are loaded
+  const int q_box = 128 * 128, k_box = ((Tkp + 63) / 64) * 64 * 128, v_box = hs * 128;
   const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   long long* ph_out = (p.phase && cta_lin < p.phase_cap) ? p.phase + 8ll * cta_lin : nullptr;
   if (ph_out && threadIdx.x == 0) {
@@ -243,23 +246,44 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
     const uint32_t w = __ballot_sync(0xffffffffu, valid);
     if (lane == 0) maskw[warp] = w;
   }
+  // query validity of this tile (optional): a tile without a valid query does no tensor work at all
+  int q_valid = 1;
+  if (g.qmask && !chunked) {
+    const int qr = q0 + static_cast<int>(threadIdx.x);
+    q_valid = threadIdx.x < 128 && qr < p.Tq && g.qmask[static_cast<long long>(b) * p.Tq + qr];
+  }
   tc_fence_before();
-  __syncthreads();
+  const bool any_q = __syncthreads_or(q_valid) != 0;
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
   const uint32_t tm_s = tmem_base, tm_p = tmem_base + p.ncols / 2, tm_o = tmem_base;
   if (ph_out && threadIdx.x == 0) ph_out[2] = clock_stamp();
-  // a chunk with no valid key (beyond the video's length) contributes nothing: record sum = 0 and skip the tensor work
-  bool live = true;
-  if (chunked) {
-    uint32_t any = 0;
+  // Keys beyond the last valid one contribute exactly 0 to every row (masked to -inf before the softmax in the reference):
+  // they are not loaded, not multiplied and not exponentiated.  Tke = this CTA's key count, a multiple of 16 (>= 16: a fully
+  // masked item still runs one masked block and yields the reference's 0/0 rows).
+  int kmax = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) any |= maskw[w];
-    live = any != 0;
-  }
+  for (int w = 7; w >= 0; --w)
+    if (kmax == 0 && maskw[w] != 0) kmax = w * 32 + 32 - __clz(maskw[w]);
+  const int Tke = min(Tkp, max(16, (kmax + 15) & ~15));
+  const int nkb_k = (Tke + 63) / 64;            // 64-key boxes of K and of V^T that are needed
+  // a chunk with no valid key (beyond the video's length) contributes nothing: record sum = 0 and skip the tensor work
+  const bool live = !chunked || kmax != 0;
 
-  if (!live) {
+  if (!any_q) {
+    // no valid query in this tile: zero rows (finite, so that the masked projection that follows stays finite)
+    if (warp >= 2) {
+      const int qd = warp & 3, half = (warp - 2) >> 2;
+      const int qi = q0 + qd * 32 + lane;
+      if (qi < p.Tq) {
+        const size_t es = op_elem_size(p.op_dtype);
+        char* orow = reinterpret_cast<char*>(g.out) + (static_cast<size_t>(b) * p.Tq + qi) * g.ldo * es;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = half * (hs / 2); c < (half + 1) * (hs / 2); c += 4) store_op4(orow, p.op_dtype, h * hs + c, g.ldo / 2, z);
+      }
+    }
+  } else if (!live) {
     if (warp >= 2 && ((warp - 2) >> 2) == 0) {
       const int qi = q0 + (warp & 3) * 32 + lane;
       if (qi < p.Tq) {
@@ -271,17 +295,18 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
   } else if (warp == 0) {
     if (lane == 0) {
       // ---- Q tile + K of this (item, head)
-      mbar_expect_tx(bar_qk, nparts * kq * (q_box + k_box));
+      mbar_expect_tx(bar_qk, nparts * kq * (q_box + nkb_k * 64 * 128));
       for (int pt = 0; pt < nparts; ++pt)
         for (int kb = 0; kb < kq; ++kb) {
           tma_load_2d(q_smem + (pt * kq + kb) * q_box, &g.tmQ[pt], bar_qk, h * hs + kb * 64, b * p.Tq + q0);
-          tma_load_2d(kv_smem + (pt * kq + kb) * k_box, &g.tmK[pt], bar_qk, h * hs + kb * 64, b * p.Tk + k0);
+          for (int i = 0; i < nkb_k; ++i)
+            tma_load_2d(kv_smem + (pt * kq + kb) * k_box + i * (64 * 128), &g.tmK[pt], bar_qk, h * hs + kb * 64, b * p.Tk + k0 + i * 64);
         }
       // ---- V^T once the QK^T MMAs have finished reading K
       mbar_wait(bar_s, 0);
-      mbar_expect_tx(bar_v, nparts * nkv * v_box);
+      mbar_expect_tx(bar_v, nparts * nkb_k * v_box);
       for (int pt = 0; pt < nparts; ++pt)
-        for (int kb = 0; kb < nkv; ++kb)
+        for (int kb = 0; kb < nkb_k; ++kb)
           tma_load_2d(kv_smem + (pt * nkv + kb) * v_box, &g.tmV[pt], bar_v, k0 + kb * 64, b * p.nh * hs + h * hs);
     }
     __syncwarp();     // lanes 1..31 wait for the elected lane: the block barrier at the end must see whole warps
@@ -290,7 +315,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
       // ---- S = Q.K^T : segments (Qhi,Khi), (Qlo,Khi), (Qhi,Klo)
       mbar_wait(bar_qk, 0);
       tc_fence_after();
-      const uint32_t id_s = idesc_16(128, Tkp, op_is_f16(p.op_dtype));
+      const uint32_t id_s = idesc_16(128, Tke, op_is_f16(p.op_dtype));
       uint32_t acc = 0;
       for (int seg = 0; seg < p.nseg; ++seg) {
         const int pa = seg == 1 ? 1 : 0, pb = seg == 2 ? 1 : 0;
@@ -310,7 +335,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
       acc = 0;
       for (int seg = 0; seg < p.nseg; ++seg) {
         const int pa = seg == 1 ? 1 : 0, pb = seg == 2 ? 1 : 0;
-        for (int ks = 0; ks < Tkp / 16; ++ks) {
+        for (int ks = 0; ks < Tke / 16; ++ks) {
           const uint32_t a_t = tm_p + pa * (Tkp / 2) + ks * 8;        // 16 bf16 = 8 packed 32-bit columns
           const uint64_t bd = smem_desc(kv_smem + (pb * nkv + ks / 4) * v_box) + 2u * (ks % 4);
           mma_ts(tm_o, a_t, bd, id_o, acc);
@@ -330,8 +355,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnTcParams p) {
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const float sc = p.scale;
     const bool split = p.nseg > 1, f16 = op_is_f16(p.op_dtype);
-    const int csplit = ((Tkp / 16 + 1) / 2) * 16;
-    const int c_lo = half ? csplit : 0, c_hi = half ? Tkp : csplit;
+    const int csplit = ((Tke / 16 + 1) / 2) * 16;
+    const int c_lo = half ? csplit : 0, c_hi = half ? Tke : csplit;
     // optional extra key: s_x = scale * <q_i, xk_i>
     const bool has_x = !chunked && g.xk != nullptr && row_ok && qi >= g.x_first;     // chunked: the merge kernel adds it
     float s_x = -CUDART_INF_F;
@@ -719,7 +744,7 @@ static int attention_tc_impl(const UnavAttnTcGroup* groups, int ngroups, int nb,
   const int nparts = p.nseg > 1 ? 2 : 1;
   const int kq = hs / 64, nkv = (p.Tkp + 63) / 64;
   p.q_bytes = nparts * kq * 128 * 128;
-  const int kbytes = nparts * kq * p.Tkp * 128, vbytes = nparts * nkv * hs * 128;
+  const int kbytes = nparts * kq * nkv * 64 * 128, vbytes = nparts * nkv * hs * 128;      // K: whole 64-key boxes
   p.kv_bytes = ((kbytes > vbytes ? kbytes : vbytes) + 1023) / 1024 * 1024;
   for (int i = 0; i < ngroups; ++i) {
     const UnavAttnTcGroup& s = groups[i];
@@ -734,12 +759,12 @@ static int attention_tc_impl(const UnavAttnTcGroup* groups, int ngroups, int nb,
       const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(s.k) + (pt ? s.ldk / 2 : 0);
       const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(s.vt) + (pt ? s.ldvt / 2 : 0);
       if ((rc = encode2d(&d.tmQ[pt], q, mq, C, s.ldq, 128))) return rc;
-      if ((rc = encode2d(&d.tmK[pt], k, mk, C, s.ldk, p.Tkp))) return rc;
+      if ((rc = encode2d(&d.tmK[pt], k, mk, C, s.ldk, 64))) return rc;
       if ((rc = encode2d(&d.tmV[pt], v, static_cast<long long>(nb) * C, Tk, s.ldvt, hs))) return rc;
     }
     if (nparts == 1) { d.tmQ[1] = d.tmQ[0]; d.tmK[1] = d.tmK[0]; d.tmV[1] = d.tmV[0]; }
     d.kmask = s.kmask; d.q32 = s.q32; d.xk = s.xk; d.xv = s.xv; d.ldq32 = s.ldq32; d.ldx = s.ldx;
-    d.out = s.out; d.ldo = s.ldo; d.x_first = s.x_first;
+    d.out = s.out; d.ldo = s.ldo; d.x_first = s.x_first; d.qmask = s.qmask;
   }
   const int smem = p.q_bytes + p.kv_bytes + 128 + 4 * 128 * 4 + 1024;     // + barriers, mask words, max/sum exchange, slack
   static SmemAttr attr = {};

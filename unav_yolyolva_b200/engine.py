@@ -436,7 +436,9 @@ class HotPathEngine:
         scale = 1.0 / math.sqrt(hs)
         if self._tc_attn_for(T):
             Cc = nh * hs
-            K.attention_tc([{"q": qop, "k": kop, "vt": vt[:nb * Cc], "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op,
+            # qmask = kmask: self-attention over one masked sequence — the projection that follows multiplies the rows of invalid
+            # queries by the same mask (blocks.py:243), so tiles without a valid query are skipped (zero rows)
+            K.attention_tc([{"q": qop, "k": kop, "vt": vt[:nb * Cc], "kmask": kmask, "qmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op,
                            passes=self.stage_passes.get(self._stage, 0), workspace=ws)
         else:
             K.attention([{"q": q32, "k": k32, "v": v32, "kmask": kmask, "out": out}], nb, T, T, nh, hs, scale, self.op)
@@ -518,7 +520,7 @@ class HotPathEngine:
                 if self.tc_attn:
                     oop = P["QKVop"][g * hm:(g + 1) * hm]
                     groups.append({"q": View(oop, 0, C), "k": View(oop, C, C), "vt": P["VTa"][g * B * C:(g + 1) * B * C],
-                                   "kmask": P["m_cls"],
+                                   "kmask": P["m_cls"], "qmask": P["m_cls"],
                                    "q32": View(own, 0, C), "xk": View(oth, C, C), "xv": View(oth, 2 * C, C), "x_first": 1,
                                    "out": P["AOa"][g * hm:(g + 1) * hm]})
                 else:

@@ -302,6 +302,7 @@ def attention_tc(groups: Sequence[dict], nb: int, Tq: int, Tk: int, nh: int, hs:
         s.xk, s.xv, s.ldx = _vp(g.get("xk")), _vp(g.get("xv")), _vld(g.get("xk"))
         s.x_first = g.get("x_first", 0)
         s.out, s.ldo = _vp(g["out"]), _vld(g["out"])
+        s.qmask = _p(g.get("qmask"))
     lib = A.load(op_dtype)
     with _Span("attention_tc", 4.0 * n * nb * nh * Tq * Tk * hs, n * nb * nh * hs * (Tq * 8 + Tk * 8), f"{n}x[{nb},{nh},{Tq},{Tk},{hs}]"):
         if Tk > 256:
