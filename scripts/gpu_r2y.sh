@@ -1,6 +1,7 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_attention.py tests/test_gpu_modules.py tests/test_gpu_model.py tests/test_gpu_configs.py -q -m gpu -x --tb=short -k "not config3" > gpurun_out/t_quick.log 2>&1; echo "attention/modules/model/configs tests exit $?"
-tail -15 gpurun_out/t_quick.log
+timeout 900 python -m pytest tests/test_gpu_rowops.py tests/test_gpu_modules.py tests/test_gpu_model.py tests/test_gpu_configs.py -q -m gpu -x --tb=short -k "not config3" > gpurun_out/t_quick.log 2>&1; echo "rowops/modules/model/configs tests exit $?"
+tail -5 gpurun_out/t_quick.log
+timeout 300 python scripts/dwconv_probe.py > gpurun_out/dwconv_probe.log 2>&1; head -4 gpurun_out/dwconv_probe.log
 run() {  # tag, env...
   tag=$1; shift
   env "$@" timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err || tail -5 gpurun_out/bench_$tag.err

@@ -463,34 +463,65 @@ dwconv_ln_stream_kernel(const __grid_constant__ DwLnParams p, int strip) {
     }
   };
 
+  // A masked output row (mask_out == 0) is exactly its LayerNorm bias: z = conv * 0 = 0, so mean = 0, variance = 0 and
+  // y = 0 * rstd * w + b = b (plain zero without a LayerNorm), whatever the input holds — the reference computes the same
+  // thing the long way (blocks.py:56-61 then :99-103).  Such rows are written without loading or convolving anything; with
+  // the padded batches of the path (valid length 60 .. 187 of 224 frames) that is ~45 % of the rows.
+  auto masked_row = [&](long long r) {
+    const size_t es = op_elem_size(p.op_dtype);
+    for (int o = 0; o < p.n_out; ++o) {
+      const UnavDwLnOut& od = g.out[o];
+      const float* wo = dws_smem + o * 5 * C;
+      char* op_row = od.out_op ? reinterpret_cast<char*>(od.out_op) + static_cast<size_t>(r) * od.ld_op * es : nullptr;
+      float* f32_row = od.out_f32 ? od.out_f32 + r * od.ld_f32 : nullptr;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        const float4 y = od.ln_w ? *reinterpret_cast<const float4*>(wo + 4 * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f32_row) *reinterpret_cast<float4*>(f32_row + c) = y;
+        if (op_row) store_op4(op_row, p.op_dtype, c, od.ld_op / 2, y);
+      }
+    }
+  };
+
   for (int sidx = blockIdx.x * nwarps + warp; sidx < total; sidx += gridDim.x * nwarps) {
     const int seg = sidx / strips_per_seg;
     const int t0 = (sidx - seg * strips_per_seg) * strip;
     const int t1 = min(t0 + strip, p.seg_len_out);
+    const long long r0 = static_cast<long long>(seg) * p.seg_len_out + t0;
+    // validity bits of the strip's rows (strip <= 32): rows after the last valid one need no input at all
+    const bool lane_valid = lane < t1 - t0 && (!g.mask_out || g.mask_out[r0 + lane] != 0);
+    const uint32_t vbits = __ballot_sync(0xffffffffu, lane_valid);
+    const int t_last = vbits ? t0 + 31 - __clz(vbits) : t0 - 1;          // last valid row of the strip
+    for (int t = t_last + 1; t < t1; ++t) masked_row(r0 + (t - t0));
+    if (t_last < t0) continue;
     float4 w0[NV], w1[NV], w2[NV], nx[NV], nx2[NV];     // window rows STRIDE*t - 1, STRIDE*t, STRIDE*t + 1 and the prefetch
     load_row(seg, STRIDE * t0 - 1, w0);
     load_row(seg, STRIDE * t0, w1);
     load_row(seg, STRIDE * t0 + 1, w2);
     if (pre) { normalise(w0); normalise(w1); normalise(w2); }
-    for (int t = t0; t < t1; ++t) {
-      const bool more = t + 1 < t1;
+    for (int t = t0; t <= t_last; ++t) {
+      const bool more = t < t_last;
       if (more) {                                     // next window's new rows: in flight while this row is computed
         if (STRIDE == 1) load_row(seg, t + 2, nx);
         else { load_row(seg, 2 * t + 2, nx); load_row(seg, 2 * t + 3, nx2); }
       }
-      const long long r = static_cast<long long>(seg) * p.seg_len_out + t;
-      const float mk = g.mask_out ? (g.mask_out[r] ? 1.f : 0.f) : 1.f;
-      const bool ok0 = STRIDE * t - 1 >= 0, ok2 = STRIDE * t + 1 < p.seg_len_in;      // tap 1 is always inside the segment
-      for (int o = 0; o < p.n_out; ++o) {
-        const UnavDwLnOut& od = g.out[o];
-        const float* wo = dws_smem + o * 5 * C;
-        if (od.src >= 0) {
-          const float* wp = dws_smem + p.n_out * 5 * C + od.src * 2 * C;
-          if (ok0 && ok2) dws_pair<NV, true, false>(w0, w1, w2, wo, wp, true, true, mk, p.eps, od, r, lane, p.op_dtype);
-          else dws_pair<NV, true, true>(w0, w1, w2, wo, wp, ok0, ok2, mk, p.eps, od, r, lane, p.op_dtype);
-        } else {
-          dws_pair<NV, false, false>(w0, w1, w2, wo, nullptr, true, true, mk, p.eps, od, r, lane, p.op_dtype);
+      const long long r = r0 + (t - t0);
+      if ((vbits >> (t - t0)) & 1u) {
+        const bool ok0 = STRIDE * t - 1 >= 0, ok2 = STRIDE * t + 1 < p.seg_len_in;      // tap 1 is always inside the segment
+        for (int o = 0; o < p.n_out; ++o) {
+          const UnavDwLnOut& od = g.out[o];
+          const float* wo = dws_smem + o * 5 * C;
+          if (od.src >= 0) {
+            const float* wp = dws_smem + p.n_out * 5 * C + od.src * 2 * C;
+            if (ok0 && ok2) dws_pair<NV, true, false>(w0, w1, w2, wo, wp, true, true, 1.f, p.eps, od, r, lane, p.op_dtype);
+            else dws_pair<NV, true, true>(w0, w1, w2, wo, wp, ok0, ok2, 1.f, p.eps, od, r, lane, p.op_dtype);
+          } else {
+            dws_pair<NV, false, false>(w0, w1, w2, wo, nullptr, true, true, 1.f, p.eps, od, r, lane, p.op_dtype);
+          }
         }
+      } else {
+        masked_row(r);                                // a masked row between valid ones (not a prefix mask): same shortcut
       }
       if (more) {                                     // slide the window
         if (pre) { normalise(nx); if (STRIDE == 2) normalise(nx2); }
@@ -914,7 +945,7 @@ extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg
       // strip length: enough warps in flight to cover the memory latency (about 12 warps per SM) before strips get longer
       int strip = static_cast<int>((rows * ngroups + 148 * 12 - 1) / (148 * 12));
       strip = strip < 2 ? 2 : (strip > 16 ? 16 : strip);
-      if (const char* env = getenv("UNAV_DWCONV_STRIP")) { const int v = atoi(env); if (v >= 1) strip = v; }
+      if (const char* env = getenv("UNAV_DWCONV_STRIP")) { const int v = atoi(env); if (v >= 1 && v <= 32) strip = v; }
       const int nw = 8;
       const long long strips = static_cast<long long>(nseg) * ((p.seg_len_out + strip - 1) / strip);
       long long blocks = (strips + nw - 1) / nw;
