@@ -58,3 +58,11 @@ for i in range(3):
     print("    first 64-column pass                       ", st(r[:, o + 5] - r[:, o + 4]))
     print("    all four passes                            ", st(r[:, o + 6] - r[:, o + 4]))
     print("    release (bar.sync + arrive)                ", st(r[:, o + 7] - r[:, o + 6]))
+
+if os.environ.get("UNAV_PP_FINE"):
+    f = t[t[:, 28] != 0]
+    if f.shape[0]:
+        print("  fine trace, second pass of the second tile (warp 2):")
+        print("    bias loads + tcgen05.ld + wait             ", st(f[:, 29] - f[:, 28]))
+        print("    staging stores + syncwarp                  ", st(f[:, 30] - f[:, 29]))
+        print("    transposed store (if any) + row loop       ", st(f[:, 31] - f[:, 30]))

@@ -5,9 +5,10 @@ run() {  # tag, env...
   python - "$tag" <<PY
 import json,sys
 b=json.loads(open(f'gpurun_out/bench_{sys.argv[1]}.json').read().strip().splitlines()[-1])
-print(sys.argv[1], 'value', round(b['value'],1), 'ms/step', round(b['ms_per_step'],3), 'e2e', round(b['e2e']['value'],1), 'long', round(b['long_window']['ms_per_step'],3), 'det', b['detections_check']['match'], 'traced', round(b['roofline']['traced_step_us']), 'dwconv', round(b['roofline']['per_kernel']['dwconv_ln']['us_per_step']))
+print(sys.argv[1], 'value', round(b['value'],1), 'long', round(b['long_window']['ms_per_step'],3), 'det', b['detections_check']['match'], 'softnms us', round(b['roofline']['per_kernel']['softnms']['us_per_step']), 'b1 sync ms', round(b['config1_batch1']['gpu_ms_per_video_sync'],3))
 PY
 }
-run strip2 UNAV_DWCONV_STRIP=2
-run strip3 UNAV_DWCONV_STRIP=3
-run strip8 UNAV_DWCONV_STRIP=8
+run w0 UNAV_NMS_WARP_MAX=0
+run w32 UNAV_NMS_WARP_MAX=32
+run w64 UNAV_NMS_WARP_MAX=64
+run w128 UNAV_NMS_WARP_MAX=128

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-( for s in "32 224 4 128" "32 224 4 64" "16 225 8 64" "32 112 4 64" "32 56 4 64"; do timeout 120 python scripts/attn_phases.py $s; done ) > gpurun_out/attn_phases.log 2>&1
-cat gpurun_out/attn_phases.log
+( UNAV_PP_FINE=1 timeout 100 python scripts/gemm_phases_pp.py 2 3584 512 512 0 f32; UNAV_PP_FINE=1 timeout 100 python scripts/gemm_phases_pp.py 6 3584 512 512 0 f32; UNAV_PP_FINE=1 timeout 100 python scripts/gemm_phases_pp.py 6 3584 512 512 0 both;  UNAV_PP_FINE=1 timeout 100 python scripts/gemm_phases_pp.py 2 3600 2048 512 2 op ) > gpurun_out/phases_fine.log 2>&1
+cat gpurun_out/phases_fine.log

@@ -51,11 +51,15 @@ body = seq[n_pack:]
 nsteps = len(body) // per_step
 step = body[(nsteps - 1) * per_step: nsteps * per_step]
 with open(f"profiles/{tag}_launches_b16_bf16x3.csv", "w") as f:
-    f.write("id,kernel,gpu__time_duration_us,dram_read_bytes,dram_write_bytes\n")
+    f.write("id,kernel,gpu__time_duration_us,dram_read_bytes,dram_write_bytes,grid,block,sm_active_frac\n")
     for i, x in enumerate(step):
-        f.write(f"{i},{x['kernel']},{x.get('gpu__time_duration.sum', 0):.3f},{x.get('dram__bytes_read.sum', 0):.0f},{x.get('dram__bytes_write.sum', 0):.0f}\n")
+        x["act"] = x.get("sm__cycles_active.avg", 0.0) / max(1.0, x.get("sm__cycles_elapsed.avg", 1.0))
+        f.write(f"{i},\"{x['kernel']}\",{x.get('gpu__time_duration.sum', 0):.3f},{x.get('dram__bytes_read.sum', 0):.0f},{x.get('dram__bytes_write.sum', 0):.0f},"
+                f"{x.get('launch__grid_size', 0):.0f},{x.get('launch__block_size', 0):.0f},{x['act']:.3f}\n")
 agg = collections.OrderedDict()
+smw = collections.defaultdict(float)          # SM-time per kernel: duration x fraction of SM cycles with a resident CTA
 for x in step:
+    smw[x["kernel"]] += x.get("gpu__time_duration.sum", 0.0) * x["act"]
     a = agg.setdefault(x["kernel"], [0, 0.0, 0.0])
     a[0] += 1
     a[1] += x.get("gpu__time_duration.sum", 0.0)
@@ -63,11 +67,11 @@ for x in step:
 tot = sum(a[1] for a in agg.values())
 bench = json.loads(open("gpurun_out/plain.json").read().strip().splitlines()[-1])
 ev = bench["roofline"]["kernel_time_shares"]
-CLS = [("gemm_tcgen05_ppair_kernel", "gemm_tcgen05_ppair_kernel<256>"), ("gemm_tcgen05_pair_kernel", "gemm_tcgen05_pair_kernel<256>"),
+CLS = [("gemm_tcgen05_ppair_kernel", "gemm_tcgen05_ppair_kernel<256, 8>"), ("gemm_tcgen05_pair_kernel", "gemm_tcgen05_pair_kernel<256>"),
        ("gemm_tcgen05_kernel<64, 64>", "gemm_tcgen05_kernel<64, 64>"), ("gemm_tcgen05_kernel<128, 32>", "gemm_tcgen05_kernel<128, 32>"),
        ("gemm_tcgen05_kernel<128, 64>", "gemm_tcgen05_kernel<128, 64>"), ("gemm_tcgen05_kernel<64, 32>", "gemm_tcgen05_kernel<64, 32>"),
        ("attention_tcgen05_kernel", "attention_tc"), ("attention_merge_kernel", "attention_tc"), ("dwconv_ln", "dwconv_ln"),
-       ("ln_rows", "layernorm_rows"), ("rowcopy_kernel", "rowcopy"), ("maxsig_tcgen05_kernel", "maxsig_gate_tc"), ("softnms", "softnms"),
+       ("ln_rows", "layernorm_rows"), ("rowcopy", "rowcopy"), ("maxsig_tcgen05_kernel", "maxsig_gate_tc"), ("softnms", "softnms"),
        ("merge_kernel", "softnms"), ("decode_kernel", "decode"), ("transpose_cast_kernel", "transpose_cast"), ("pool_match_kernel", "pool_match"),
        ("align_embed_kernel", "align_embed"), ("build_masks_kernel", "build_masks")]
 
@@ -80,19 +84,25 @@ def cls(k):
 
 
 cagg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+csmw = collections.defaultdict(float)
 for k, (n, us, by) in agg.items():
     c = cagg[cls(k)]
     c[0] += n; c[1] += us; c[2] += by
+    csmw[cls(k)] += smw[k]
+tot_smw = sum(csmw.values())
 out = [f"# Round 2 — ncu launch list of one forward + decode + soft-NMS (batch 16, T=224, mode bf16x3) [{tag}]", "",
        "Command (B200, `gpurun`, `scripts/gpu_profile_r2.sh`): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
        "--clock-control none -k regex:^(gemm_|attention_|...) -c 1400 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --profile-run`, "
        f"run after the same command exited 0 without ncu.  One step = {per_step} launches (the last complete step of the capture; "
        f"{n_pack} `pack_operand_kernel` launches of the weight packing precede the first step).  ncu times are cold-cache and serialised, so "
        "the SHARE of the step is what is compared with the CUDA-event shares of `bench.py` (graph replay, `roofline.kernel_time_shares`).", "",
-       "| kernel class | launches | us (ncu) | share (ncu) | share (bench.py events) | DRAM MB / launch |", "|---|---:|---:|---:|---:|---:|"]
+       "SM-time = duration x (`sm__cycles_active.avg / sm__cycles_elapsed.avg`): what a launch takes away from the other batches in flight "
+       "(a kernel that fills every SM costs its whole duration, a 16-CTA kernel a tenth of it) — the sum over the step is what the streamed "
+       "ms/step follows (DESIGN.md section 8).", "",
+       "| kernel class | launches | us (ncu) | share (ncu) | share (bench.py events) | SM-time us | SM-time share | DRAM MB / launch |", "|---|---:|---:|---:|---:|---:|---:|---:|"]
 for c, (n, us, by) in sorted(cagg.items(), key=lambda kv: -kv[1][1]):
-    out.append(f"| `{c}` | {n} | {us:.1f} | {us / tot:.3f} | {ev.get(c, float('nan')):.3f} | {by / n / 1e6:.2f} |")
-out += ["", f"Sum of the {per_step} launches under ncu: {tot:.0f} us; the 2-step profiling run itself reports {bench['ms_per_step']:.3f} ms/step (pipeline fill dominates two steps; the "
+    out.append(f"| `{c}` | {n} | {us:.1f} | {us / tot:.3f} | {ev.get(c, float('nan')):.3f} | {csmw[c]:.1f} | {csmw[c] / max(tot_smw, 1e-9):.3f} | {by / n / 1e6:.2f} |")
+out += ["", f"Sum of the {per_step} launches under ncu: {tot:.0f} us, SM-time {tot_smw:.0f} us; the 2-step profiling run itself reports {bench['ms_per_step']:.3f} ms/step (pipeline fill dominates two steps; the "
         "20-step bench of this build: see the bench line in DESIGN.md section 8)."]
 open(f"profiles/{tag}_launch_summary.md", "w").write("\n".join(out) + "\n")
 json.dump({"source": f"profiles/{tag}_launches_b16_bf16x3.csv (ncu, batch 16, bf16x3)",

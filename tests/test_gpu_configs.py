@@ -54,7 +54,7 @@ def test_config2_batch16_vs_oracle(cuda):
     with torch.no_grad():
         logits, offsets, masks = R.forward_logits(sd, batch["visual"], batch["audio"], batch["mask"])
     ref_l, ref_o = torch.cat(logits, 1), torch.cat(offsets, 1)
-    big = ("gemm_tcgen05_kernel<128, 32>", "gemm_tcgen05_pair_kernel<256>", "gemm_tcgen05_ppair_kernel<256>")
+    big = ("gemm_tcgen05_kernel<128, 32>", "gemm_tcgen05_pair_kernel<256>", "gemm_tcgen05_ppair_kernel<256, 8>")
     for mode, tol_l, tol_o in (("bf16x3", 5e-5, 1e-4), ("fp32", 1e-5, 1e-5)):
         model.precision, model.use_cuda_graph = mode, True
         before = K.gemm_variant_counts()
@@ -65,7 +65,7 @@ def test_config2_batch16_vs_oracle(cuda):
         print(f"[config 2, {mode}] GEMM variants launched: {used}")
         if mode == "bf16x3":
             assert any(used.get(k, 0) > 0 for k in big), f"batch 16 did not reach the full-grid tile variants: {used}"
-            assert used.get("gemm_tcgen05_pair_kernel<256>", 0) + used.get("gemm_tcgen05_ppair_kernel<256>", 0) > 0, used
+            assert used.get("gemm_tcgen05_pair_kernel<256>", 0) + used.get("gemm_tcgen05_ppair_kernel<256, 8>", 0) > 0, used
         lg = plan["logits"].cpu().view(B, 441, 100)
         of = plan["offsets"].cpu().view(B, 441, 100, 2)
         e1 = float((lg - ref_l).abs().max() / ref_l.abs().max())

@@ -216,12 +216,14 @@ def test_tcgen05_persistent_pair_kernel_two_streams(cuda, monkeypatch):
         for si in range(2):
             with torch.cuda.stream(streams[si]):
                 monkeypatch.setenv("UNAV_TC_PPAIR", "1")
+                monkeypatch.setenv("UNAV_TC_PAIR", "0")
                 for _ in range(3):
                     K.gemm([{"A": A, "W": W, "out_f32": outs[si]}], M, N, Kd, op, K.ACT_NONE, False, K.GEMM_TCGEN05)
                 monkeypatch.setenv("UNAV_TC_PPAIR", "0")
                 K.gemm([{"A": A[:448], "W": W[:256], "out_f32": small}], 448, 256, Kd, op, K.ACT_NONE, False, K.GEMM_TCGEN05)
         with torch.cuda.stream(streams[2]):
             monkeypatch.setenv("UNAV_TC_PPAIR", "0")          # the one-tile CTA-pair kernel (256 TMEM columns, two CTAs per SM)
+            monkeypatch.setenv("UNAV_TC_PAIR", "1")           # (no policy selects it any more: forced for this stream)
             K.gemm([{"A": A2, "W": W2, "out_f32": o2}], M2, N2, K2, op, K.ACT_NONE, False, K.GEMM_TCGEN05)
     torch.cuda.synchronize()
     assert torch.equal(outs[0], ref) and torch.equal(outs[1], ref)

@@ -51,7 +51,7 @@ struct TcParams {
   // operand is materialised; the accumulation order (K = tap*Cin + c ascending) is that of the im2col GEMM, bit for bit.
   int conv_T, conv_cin, conv_tiles;
   long long* phase;    // diagnostics (unav_gemm_set_phase_trace): 8 clock64 stamps per CTA, or nullptr
-  int phase_cap;
+  int phase_cap, fine;
 };
 
 
@@ -741,7 +741,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
 // issued before the tensor-memory read so their latency overlaps it.
 template <int U, int EW>
 __device__ __forceinline__ void pp_epilogue_pass(const TcParams& p, const TcGroup& g, uint32_t tmem_cols, int m0, int n0, int warp,
-                                                 int lane, float* stg_base, long long m_limit) {
+                                                 int lane, float* stg_base, long long m_limit, long long* fine = nullptr) {
+  if (fine) fine[0] = clock_stamp();            // diagnostics (UNAV_PP_FINE=1 + unav_set_phase_trace): inside one pass
   // EW epilogue warps share a 64-column pass: TMEM lane quarter = warp % 4 (a warp can only read its own quarter), column
   // block = (warp - 2) / 4 of CW = 32 (EW = 8) or 16 (EW = 16) columns.  Sixteen warps: the pass is latency bound (tensor-memory
   // read -> staging -> residual load -> stores is one dependent chain per warp), so twice the warps is twice the chains in flight.
@@ -767,6 +768,7 @@ __device__ __forceinline__ void pp_epilogue_pass(const TcParams& p, const TcGrou
     if constexpr (CW == 32) tc_ld_32x32b_x32(taddr, r);
     else tc_ld_32x32b_x16(taddr, r);
     tc_wait_ld();
+    if (fine) fine[1] = clock_stamp();
     float* dst = stg + lane * PITCH;
 #pragma unroll
     for (int j = 0; j < CW; j += 4)
@@ -774,6 +776,7 @@ __device__ __forceinline__ void pp_epilogue_pass(const TcParams& p, const TcGrou
                                                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
   }
   __syncwarp();
+  if (fine) fine[2] = clock_stamp();
   if (e.out_opT) {       // transposed operand output (V^T for the tensor-core attention): lanes run along the token axis, so
     // each store instruction writes 32 consecutive keys of one channel row.  Addresses are one hoisted row pointer bumped per
     // channel (the first version re-derived item * ncols * ld per element with 64-bit multiplies).
@@ -822,6 +825,7 @@ __device__ __forceinline__ void pp_epilogue_pass(const TcParams& p, const TcGrou
     default: break;
   }
 #undef UNAV_PP_CASE
+  if (fine) fine[3] = clock_stamp();
 }
 
 // =============================================================================================
@@ -974,11 +978,13 @@ gemm_tcgen05_ppair_kernel(const __grid_constant__ TcParams p) {
       const uint32_t a = i & 1, aph = (i >> 1) & 1;
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
-      const bool stamp = ph_out && threadIdx.x == 64 && i < 3;
+      const bool stamp = ph_out && threadIdx.x == 64 && i < (p.fine ? 2 : 3);
       if (stamp) ph_out[8 * (i + 1) + 4] = clock_stamp();
 #pragma unroll 1
       for (int c = 0; c < PN / PP_STG_BN; ++c) {
-        pp_epilogue_pass<4, EW>(p, p.g[g], tmem_base + a * PN + c * PP_STG_BN, m0, n0 + c * PP_STG_BN, warp, lane, stg, p.M);
+        // fine trace: the second pass of the CTA's second tile, in the (otherwise unused) epilogue slots of the third tile's row
+        long long* fine = (p.fine && ph_out && threadIdx.x == 64 && i == 1 && c == 1) ? ph_out + 24 + 4 : nullptr;
+        pp_epilogue_pass<4, EW>(p, p.g[g], tmem_base + a * PN + c * PP_STG_BN, m0, n0 + c * PP_STG_BN, warp, lane, stg, p.M, fine);
         __syncwarp();
         if (stamp && c == 0) ph_out[8 * (i + 1) + 5] = clock_stamp();
       }
@@ -1165,7 +1171,9 @@ static int launch_pair(TcParams& p, int ngroups, cudaStream_t stream) {
 static int use_pair(int M, int N, int K, int ngroups) {
   int v = -1;
   if (const char* env = getenv("UNAV_TC_PAIR")) v = atoi(env);       // experiment knob: 0 never, 1 256-wide whenever possible,
-  if (M < 256 || v == 0) return 0;                                   // 2 also 128-wide pairs for the other full grids
+  if (M < 256 || v <= 0) return 0;                                   // 2 also 128-wide pairs for the other full grids; unset = NEVER:
+  // round 2: no policy selects a one-tile pair kernel (the persistent pair kernel serves every shape they served, and a pair
+  // CTA with a partial tensor-memory allocation next to other streams' kernels is the hazard of DESIGN.md section 11)
   const long long tiles128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128) * ngroups;
   if (N % 256 == 0 && (v == 1 || (tiles128 >= 296 && K >= 1024))) return 256;
   if (v == 2 && N % 128 == 0 && tiles128 >= 148) return 128;
@@ -1257,6 +1265,7 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
   p.M = M; p.N = N; p.K = K; p.op_dtype = op_dtype; p.act = act; p.res_masked = res_masked;
   p.nseg = op_passes(op_arg);       // 1 pass on split operands reads the hi halves only
   p.phase = g_phase_buf; p.phase_cap = g_phase_cap;
+  p.fine = (g_phase_buf && getenv("UNAV_PP_FINE")) ? 1 : 0;
   const int conv_T = groups[0].conv_T;
   for (int i = 0; i < ngroups; ++i) UNAV_REQUIRE(groups[i].conv_T == conv_T, "gemm_tcgen05: groups must share conv_T");
   if (conv_T > 0)

@@ -20,7 +20,7 @@ OP_TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, BF16X2: torch.bfloat
 # kernel names as ncu lists them, by unav_gemm_last_variant()
 GEMM_KERNELS = {0: "gemm_tcgen05_kernel<64, 64>", 1: "gemm_tcgen05_kernel<128, 32>", 2: "gemm_tcgen05_kernel<128, 64>",
                 3: "gemm_tcgen05_pair_kernel<256>", 4: "gemm_tcgen05_kernel<64, 32>", 5: "gemm_tcgen05_pair_kernel<128>",
-                6: "gemm_tcgen05_kernel<256, 32>", 7: "gemm_tcgen05_ppair_kernel<256>"}
+                6: "gemm_tcgen05_kernel<256, 32>", 7: "gemm_tcgen05_ppair_kernel<256, 8>"}
 
 
 def with_passes(op_dtype: int, passes: int = 0) -> int:
