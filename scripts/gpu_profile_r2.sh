@@ -12,8 +12,8 @@ cap() {  # name regex skip
 }
 # skip counts: the weight packing and the eager warm-up pass precede the replays; any launch of the class is representative
 cap ppair 'gemm_tcgen05_ppair_kernel' 30
-cap gemm6464 'gemm_tcgen05_kernel<64, 64>' 100
-cap gemm12832 'gemm_tcgen05_kernel<128, 32>' 20
+cap gemm6464 'gemm_tcgen05_kernel<\(int\)64, \(int\)64>' 100
+cap gemm12832 'gemm_tcgen05_kernel<\(int\)128, \(int\)32>' 20
 cap attention 'attention_tcgen05_kernel' 40
 cap maxsig 'maxsig_tcgen05_kernel' 12
 cap softnms 'softnms_lazy_kernel' 3
