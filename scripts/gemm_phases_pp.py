@@ -60,9 +60,10 @@ for i in range(3):
     print("    release (bar.sync + arrive)                ", st(r[:, o + 7] - r[:, o + 6]))
 
 if os.environ.get("UNAV_PP_FINE"):
-    f = t[t[:, 28] != 0]
-    if f.shape[0]:
-        print("  fine trace, second pass of the second tile (warp 2):")
-        print("    bias loads + tcgen05.ld + wait             ", st(f[:, 29] - f[:, 28]))
-        print("    staging stores + syncwarp                  ", st(f[:, 30] - f[:, 29]))
-        print("    transposed store (if any) + row loop       ", st(f[:, 31] - f[:, 30]))
+    for o, what in ((24, "first pass of the first tile"), (28, "second pass of the second tile")):
+        f = t[t[:, o] != 0]
+        if f.shape[0]:
+            print(f"  fine trace, {what} (warp 2):")
+            print("    bias loads + tcgen05.ld + wait             ", st(f[:, o + 1] - f[:, o]))
+            print("    staging stores + syncwarp                  ", st(f[:, o + 2] - f[:, o + 1]))
+            print("    transposed store (if any) + row loop       ", st(f[:, o + 3] - f[:, o + 2]))

@@ -51,7 +51,7 @@ struct TcParams {
   // operand is materialised; the accumulation order (K = tap*Cin + c ascending) is that of the im2col GEMM, bit for bit.
   int conv_T, conv_cin, conv_tiles;
   long long* phase;    // diagnostics (unav_gemm_set_phase_trace): 8 clock64 stamps per CTA, or nullptr
-  int phase_cap, fine;
+  int phase_cap, fine, no_dry;
 };
 
 
@@ -275,6 +275,24 @@ __device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const flo
   else epilogue_rows_body<ACT, SPLIT, PITCH, RPP, U, RES, false>(e, stg_lane, m_base, rows, rsub, n, res_masked, bias, cs);
 }
 
+// 1 KB that the DRY epilogue pass reads and writes (see pp_epilogue_pass / epilogue_tile): contents are never used.  Row-indexed vectors (mask,
+// row scale) are read at offsets below 128 + 16, column-indexed ones below 32 floats.
+__device__ __align__(256) float g_epi_scratch[256];
+
+// Redirect every pointer of an epilogue to the scratch block, with zero strides (dry pass: same instructions, harmless addresses)
+__device__ __forceinline__ void epi_make_dry(EpiParams& e) {
+  float* sc = g_epi_scratch;
+  if (e.bias) e.bias = sc;
+  if (e.colscale) e.colscale = sc;
+  if (e.rowmask) e.rowmask = reinterpret_cast<const uint8_t*>(sc);
+  if (e.rowscale) e.rowscale = sc;
+  if (e.gate) { e.gate = sc; e.gate_groups = 0; }
+  if (e.res) { e.res = sc; e.ldres = 0; }
+  if (e.out_f32) { e.out_f32 = sc; e.ld_f32 = 0; }
+  if (e.out_op) { e.out_op = sc; e.ld_op = 0; }
+  e.out_opT = nullptr;
+}
+
 // Epilogue of one 128 x BN accumulator tile (TMEM columns [tmem_cols, tmem_cols + BN) of this CTA), executed by the 8
 // epilogue warps (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
 // Phase A: tcgen05.ld (one accumulator row per thread) -> padded FP32 staging tile in the (now idle) pipeline smem;
@@ -282,9 +300,12 @@ __device__ __forceinline__ void epilogue_rows_fast(const EpiParams& e, const flo
 // row-contiguous 128-bit accesses.
 // U = rows in flight per lane in the row loop: 4 where the register budget allows (the persistent kernel owns its SM), 2 in
 // the kernels that keep two CTAs resident per SM (96 registers per thread)
+// dry = true: instruction-cache warm-up while the epilogue warps wait for the accumulator (see pp_epilogue_pass).  The staging tile
+// of this kernel is the pipeline's shared memory, which the k-loop is still using: the dry pass neither reads tensor memory nor
+// writes the staging tile (it only reads it), and all its global accesses go to the scratch block.
 template <int BN, int U = 2>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& g, uint32_t tmem_cols, int m0, int n0,
-                                              int warp, int lane, float* stg_base, long long m_limit) {
+                                              int warp, int lane, float* stg_base, long long m_limit, bool dry = false) {
   constexpr int PITCH = BN + 4;              // floats; 16-byte groups of consecutive rows fall in distinct banks
   constexpr int HALF = BN / 2;               // columns per warp
   constexpr int LPR = HALF / 4;              // lanes per row in phase B (16 | 8)
@@ -293,7 +314,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& 
   const uint32_t tmem_base = tmem_cols;
   float* stg = stg_base + q * 32 * PITCH + half * HALF;
 #pragma unroll 1
-  for (int c = 0; c < HALF / 32; ++c) {
+  for (int c = 0; c < (dry ? 0 : HALF / 32); ++c) {
     uint32_t r[32];
     tc_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * HALF + c * 32, r);
     tc_wait_ld();
@@ -304,9 +325,13 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TcGroup& 
                                                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
   }
   __syncwarp();
-  const EpiParams& e = g.epi;
+  EpiParams e = g.epi;
   const int cl = lane % LPR, rsub = lane / LPR;
-  const int n = n0 + half * HALF + cl * 4;
+  int n = n0 + half * HALF + cl * 4;
+  if (dry) {
+    epi_make_dry(e);
+    n = cl * 4; n0 = 0; m0 = 0; m_limit = 1 << 20;
+  }
   const int nvalid = min(4, p.N - n);        // <= 0: this lane's columns are past N
   const long long op_split = e.ld_op / 2;
   const bool has_res = e.res != nullptr, has_gate = e.gate != nullptr;
@@ -556,19 +581,25 @@ gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
     }
     __syncwarp();     // same for the MMA issuer's warp
   } else {
-    // ===== epilogue: warps 2..9 =====
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    if (ph_out && threadIdx.x == 64) ph_out[5] = clock_stamp();       // accumulator ready
+    // ===== epilogue: warps 2..9 =====  (iteration 0 = dry pass: the epilogue's code is fetched while the k-loop runs)
     float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)));
-    if constexpr (BN == 256) {       // experiment (UNAV_TC_BN=256): two 128-column halves through the 128-wide staging tile
-      for (int hf = 0; hf < 2; ++hf) {
-        if (n0 + hf * 128 >= p.N) break;
-        epilogue_tile<128>(p, g, tmem_base + hf * 128, m0, n0 + hf * 128, warp, lane, stg, m_limit);
-        __syncwarp();
+#pragma unroll 1
+    for (int it = p.no_dry ? 1 : 0; it < 2; ++it) {
+      const bool dry = it == 0;
+      if (!dry) {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        if (ph_out && threadIdx.x == 64) ph_out[5] = clock_stamp();       // accumulator ready
       }
-    } else {
-      epilogue_tile<BN>(p, g, tmem_base, m0, n0, warp, lane, stg, m_limit);
+      if constexpr (BN == 256) {       // experiment (UNAV_TC_BN=256): two 128-column halves through the 128-wide staging tile
+        for (int hf = 0; hf < (dry ? 1 : 2); ++hf) {
+          if (n0 + hf * 128 >= p.N) break;
+          epilogue_tile<128>(p, g, tmem_base + hf * 128, m0, n0 + hf * 128, warp, lane, stg, m_limit, dry);
+          __syncwarp();
+        }
+      } else {
+        epilogue_tile<BN>(p, g, tmem_base, m0, n0, warp, lane, stg, m_limit, dry);
+      }
     }
   }
   if (ph_out && threadIdx.x == 64) ph_out[6] = clock_stamp();         // this warp's epilogue done
@@ -739,9 +770,15 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ TcParams p) {
 // gate_width % 4 == 0), so there is no generic fallback and the per-pass set-up is a few dozen instructions (ncu source page of
 // the first version: 359 of the 1 053 instructions a warp executed per pass were set-up).  The bias / column-scale loads are
 // issued before the tensor-memory read so their latency overlaps it.
+// dry = true: instruction-cache warm-up.  The epilogue warps of a persistent CTA idle through the first tile's k-loop (13 - 18 k
+// clocks) and then execute the row loop for the first time: the fine trace showed ~10 k clocks for that first 128 x 64 pass
+// against 3.2 k for every later one — the loop's ~3 - 5 KB of code arriving line by line from L2.  A dry pass runs the SAME call
+// site (hence the same inlined instructions) while the warps would otherwise wait: every pointer of the epilogue is redirected to
+// a 1 KB scratch block with zero strides, the tensor-memory read and the transposed store are skipped.
 template <int U, int EW>
 __device__ __forceinline__ void pp_epilogue_pass(const TcParams& p, const TcGroup& g, uint32_t tmem_cols, int m0, int n0, int warp,
-                                                 int lane, float* stg_base, long long m_limit, long long* fine = nullptr) {
+                                                 int lane, float* stg_base, long long m_limit, long long* fine = nullptr,
+                                                 bool dry = false) {
   if (fine) fine[0] = clock_stamp();            // diagnostics (UNAV_PP_FINE=1 + unav_set_phase_trace): inside one pass
   // EW epilogue warps share a 64-column pass: TMEM lane quarter = warp % 4 (a warp can only read its own quarter), column
   // block = (warp - 2) / 4 of CW = 32 (EW = 8) or 16 (EW = 16) columns.  Sixteen warps: the pass is latency bound (tensor-memory
@@ -749,10 +786,16 @@ __device__ __forceinline__ void pp_epilogue_pass(const TcParams& p, const TcGrou
   constexpr int BN = 64, PITCH = BN + 4, CW = BN / (EW / 4), LPR = CW / 4, RPP = 32 / LPR;
   static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
   const int q = warp & 3, cb = (warp - 2) >> 2;
-  const EpiParams& e = g.epi;
+  EpiParams e = g.epi;
   float* stg = stg_base + q * 32 * PITCH + cb * CW;
   const int cl = lane % LPR, rsub = lane / LPR;
-  const int n = n0 + cb * CW + cl * 4;
+  int n = n0 + cb * CW + cl * 4;
+  if (dry) {            // same code, harmless addresses
+    epi_make_dry(e);
+    n = cl * 4;
+    m0 = 0;
+    m_limit = 1 << 20;
+  }
   float bias[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f};
   if (e.bias) {
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
@@ -765,9 +808,14 @@ __device__ __forceinline__ void pp_epilogue_pass(const TcParams& p, const TcGrou
   {
     uint32_t r[CW];
     const uint32_t taddr = tmem_cols + (static_cast<uint32_t>(q * 32) << 16) + cb * CW;
-    if constexpr (CW == 32) tc_ld_32x32b_x32(taddr, r);
-    else tc_ld_32x32b_x16(taddr, r);
-    tc_wait_ld();
+    if (!dry) {
+      if constexpr (CW == 32) tc_ld_32x32b_x32(taddr, r);
+      else tc_ld_32x32b_x16(taddr, r);
+      tc_wait_ld();
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) r[j] = 0u;
+    }
     if (fine) fine[1] = clock_stamp();
     float* dst = stg + lane * PITCH;
 #pragma unroll
@@ -921,7 +969,7 @@ gemm_tcgen05_ppair_kernel(const __grid_constant__ TcParams p) {
           const int s = it % NS;
           const uint32_t ph = (it / NS) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
-          if (ph_out && kb == 0 && ti < 3) ph_out[8 * (ti + 1) + 0] = clock_stamp();
+          if (ph_out && kb == 0 && ti < (p.fine ? 2u : 3u)) ph_out[8 * (ti + 1) + 0] = clock_stamp();
           if (rank == 0) mbar_expect_tx(full_bar(s), 2u * stage_bytes);
           else mbar_arrive_remote(full_bar(s), 0);
           const uint32_t sa = base + s * stage_bytes;
@@ -940,14 +988,14 @@ gemm_tcgen05_ppair_kernel(const __grid_constant__ TcParams p) {
         const uint32_t a = i & 1, aph = (i >> 1) & 1;
         mbar_wait(tempty_bar(a), aph ^ 1);        // both CTAs' epilogues have drained this accumulator (first use: free)
         tc_fence_after();
-        if (ph_out && i < 3) ph_out[8 * (i + 1) + 1] = clock_stamp();
+        if (ph_out && i < (p.fine ? 2u : 3u)) ph_out[8 * (i + 1) + 1] = clock_stamp();
         const uint32_t acc = tmem_base + a * PN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % NS;
           const uint32_t ph = (it / NS) & 1;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          if (ph_out && kb == 0 && i < 3) ph_out[8 * (i + 1) + 2] = clock_stamp();
+          if (ph_out && kb == 0 && i < (p.fine ? 2u : 3u)) ph_out[8 * (i + 1) + 2] = clock_stamp();
           const uint32_t sa = base + s * stage_bytes;
           // canonical order: per 32-wide k-step hi.hi, lo.hi, hi.lo
 #pragma unroll
@@ -962,7 +1010,7 @@ gemm_tcgen05_ppair_kernel(const __grid_constant__ TcParams p) {
           tc_commit_pair(empty_bar(s));
         }
         tc_commit_pair(tfull_bar(a));
-        if (ph_out && i < 3) ph_out[8 * (i + 1) + 3] = clock_stamp();
+        if (ph_out && i < (p.fine ? 2u : 3u)) ph_out[8 * (i + 1) + 3] = clock_stamp();
       }
     }
     __syncwarp();
@@ -970,29 +1018,38 @@ gemm_tcgen05_ppair_kernel(const __grid_constant__ TcParams p) {
     // ===== epilogue (both CTAs): four 64-column passes over this CTA's 128 x PN accumulator =====
     float* stg = reinterpret_cast<float*>(smem_raw + (stg_addr - smem_u32(smem_raw)));
     uint32_t i = 0;
-    for (int tile = pair_id; tile < ntiles; tile += npairs, ++i) {
+    bool dry = !p.no_dry && pair_id < ntiles;       // one dry pass first (instruction-cache warm-up, see pp_epilogue_pass)
+    for (int tile = pair_id; tile < ntiles;) {
       const int g = tile / tiles_per_group, r = tile - g * tiles_per_group;
       const int n_t = r / tiles_m, m_t = r - n_t * tiles_m;
       const int m0 = m_t * 256 + static_cast<int>(rank) * 128;
       const int n0 = n_t * PN;
       const uint32_t a = i & 1, aph = (i >> 1) & 1;
-      mbar_wait(tfull_bar(a), aph);
-      tc_fence_after();
-      const bool stamp = ph_out && threadIdx.x == 64 && i < (p.fine ? 2 : 3);
+      if (!dry) {
+        mbar_wait(tfull_bar(a), aph);
+        tc_fence_after();
+      }
+      const bool stamp = !dry && ph_out && threadIdx.x == 64 && i < (p.fine ? 2 : 3);
       if (stamp) ph_out[8 * (i + 1) + 4] = clock_stamp();
 #pragma unroll 1
-      for (int c = 0; c < PN / PP_STG_BN; ++c) {
+      for (int c = 0; c < (dry ? 1 : PN / PP_STG_BN); ++c) {
         // fine trace: the second pass of the CTA's second tile, in the (otherwise unused) epilogue slots of the third tile's row
-        long long* fine = (p.fine && ph_out && threadIdx.x == 64 && i == 1 && c == 1) ? ph_out + 24 + 4 : nullptr;
-        pp_epilogue_pass<4, EW>(p, p.g[g], tmem_base + a * PN + c * PP_STG_BN, m0, n0 + c * PP_STG_BN, warp, lane, stg, p.M, fine);
+        long long* fine = nullptr;
+        if (!dry && p.fine && ph_out && threadIdx.x == 64) {
+          if (i == 0 && c == 0) fine = ph_out + 24;             // the very first pass of the CTA
+          else if (i == 1 && c == 1) fine = ph_out + 28;
+        }
+        pp_epilogue_pass<4, EW>(p, p.g[g], tmem_base + a * PN + c * PP_STG_BN, m0, n0 + c * PP_STG_BN, warp, lane, stg, p.M, fine, dry);
         __syncwarp();
         if (stamp && c == 0) ph_out[8 * (i + 1) + 5] = clock_stamp();
       }
+      if (dry) { dry = false; continue; }             // now the same tile for real
       if (stamp) ph_out[8 * (i + 1) + 6] = clock_stamp();
       tc_fence_before();
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");      // all epilogue warps have read accumulator a
       if (threadIdx.x == 64) mbar_arrive_remote(tempty_bar(a), 0);
       if (stamp) ph_out[8 * (i + 1) + 7] = clock_stamp();
+      tile += npairs; ++i;
     }
   }
   tc_fence_before();
@@ -1266,6 +1323,7 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
   p.nseg = op_passes(op_arg);       // 1 pass on split operands reads the hi halves only
   p.phase = g_phase_buf; p.phase_cap = g_phase_cap;
   p.fine = (g_phase_buf && getenv("UNAV_PP_FINE")) ? 1 : 0;
+  p.no_dry = getenv("UNAV_PP_NO_DRY") ? 1 : 0;           // A/B knob: skip the epilogue's instruction-cache warm-up pass
   const int conv_T = groups[0].conv_T;
   for (int i = 0; i < ngroups; ++i) UNAV_REQUIRE(groups[i].conv_T == conv_T, "gemm_tcgen05: groups must share conv_T");
   if (conv_T > 0)
@@ -1284,6 +1342,12 @@ int gemm_tcgen05(const UnavGemmGroup* groups, int ngroups, int M, int N, int K, 
     }
   }
   const int pair = ppair ? 256 : (conv_T == 0 ? use_pair(M, N, K, ngroups) : 0);
+  // The dry epilogue pass pays the cold instruction fetch (~10 k clocks) while the epilogue warps wait for the first accumulator;
+  // it only helps where that wait is at least as long: the persistent kernel with K >= 512 (13 k-clock k-loop: first pass
+  // 9.9 k -> 3.0 k clocks, 1.24 -> 1.21 ms per step over its 21 launches).  In the one-tile kernels it DELAYS the real epilogue
+  // (their k-loops last 3 - 8 k clocks: 1x[7168,512,512] 16.3 -> 24.8 us forced on for every K, and still 284 -> 331 us per
+  // step for the <128,64> class with K >= 1024 only), so it stays off there (UNAV_TC_DRY=1 enables it for experiments).
+  if (ppair ? K < 512 : !getenv("UNAV_TC_DRY")) p.no_dry = 1;
   const TcChoice ch = choose_tile(M, N, K, ngroups, p.nseg);
   const int bn = pair ? pair / 2 : ch.bn, bk = pair ? P2_BK : (ch.sched == 2 ? 32 : 64);
   p.once = ch.sched ? 1 : 0;
