@@ -206,6 +206,33 @@ def test_rowcopy_upsample_im2col_stride2(cuda):
     assert (got[:, :14] - col(x, 14)).abs().max() < 2e-4 and (got[:, 14:] - col(y, 7)).abs().max() < 2e-4
 
 
+@pytest.mark.parametrize("op", [K.BF16X2, K.BF16])
+def test_rowcopy_im2col_scatter_equals_gather(cuda, monkeypatch, op):
+    """The scatter-form k = 3 im2col (one thread per source element, three stores) writes the same bytes as the gather form
+    (UNAV_ROWCOPY_GATHER=1): segments of length 1, 7 and 224, column windows of wider source / destination buffers, a
+    destination with another segment stride and row offset, edge taps zero-filled."""
+    g = torch.Generator().manual_seed(21)
+    nseg, C = 5, 256
+    jobs_def = [(1, 0), (7, 1), (224, 8)]                 # (segment length, row offset inside the destination segment)
+    stride_rows = 1 + 7 + 224 + 3
+    srcs = [torch.randn(nseg * T, C + 64, generator=g).to(cuda) for T, _ in jobs_def]
+    outs = []
+    for gather in ("1", None):
+        if gather:
+            monkeypatch.setenv("UNAV_ROWCOPY_GATHER", gather)
+        else:
+            monkeypatch.delenv("UNAV_ROWCOPY_GATHER", raising=False)
+        dst = K.new_operand(nseg * stride_rows, 2 * 3 * C, op, cuda)
+        dst.fill_(3.0)
+        jobs = [{"src": K.View(src, 32, C), "dst": K.View(dst, 3 * C, 3 * C), "nseg": nseg, "seg_len_in": T, "seg_len_out": T,
+                 "dst_seg_stride": stride_rows, "dst_row_off": off, "ntaps": 3, "tap_stride": C, "C": C}
+                for src, (T, off) in zip(srcs, jobs_def)]
+        K.rowcopy(jobs, op)
+        torch.cuda.synchronize()
+        outs.append(dst.clone())
+    assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
+
+
 def test_transpose_align_embed_masks(cuda):
     g = torch.Generator().manual_seed(4)
     nb, R, Cc = 3, 128, 224
