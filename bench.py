@@ -465,7 +465,23 @@ def main():
     reps = len(passes)
     tot_ms = sum(a[0] for a in agg.values())
     shares = {k: round(a[0] / tot_ms, 4) for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])}
-    top = max(agg, key=lambda k: agg[k][0])
+    # Which class DOMINATES the streamed step: not the largest serial share.  With three batches in flight a launch costs the
+    # step its duration x the fraction of the SMs it occupies ("what bounds the streamed step": the ~100
+    # launches of the short pyramid levels run a few CTAs each and are hidden completely), so the traced class times are
+    # weighted with the SM-active fraction of the class from the committed ncu launch list (profiles/traffic.json); without
+    # that file (other batch sizes / modes) the serial share decides, as in round 1.
+    sm_frac, sm_src = {}, None
+    try:
+        tj0 = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
+        if B == 16 and args.mode == "bf16x3":
+            sm_frac = {k: v["sm_active_frac"] for k, v in tj0.get("per_kernel", {}).items() if "sm_active_frac" in v}
+            sm_src = tj0.get("source")
+    except Exception:                                   # noqa: BLE001
+        pass
+    sm_time = {k: a[0] * sm_frac.get(k, 1.0) for k, a in agg.items()}
+    tot_sm = sum(sm_time.values())
+    sm_shares = {k: round(v / tot_sm, 4) for k, v in sorted(sm_time.items(), key=lambda kv: -kv[1])}
+    top = max(agg, key=lambda k: sm_time[k])
     a = agg[top]
     if a[1] > 0:   # FLOP-carrying kernel class: tensor roofline (algorithmic FLOPs / summed launch time)
         ach = a[1] / (a[0] / 1e3) / 1e12
@@ -504,6 +520,10 @@ def main():
     roof.update({"events": trace_kind, "class_us_per_step": a[0] / reps * 1e3, "traced_step_us": tot_ms / reps * 1e3,
                  "peak_source": peaks["source"], "launches_timed": a[3] // reps, "avg_launch_us": a[0] / a[3] * 1e3,
                  "share_of_step": shares[top], "kernel_time_shares": shares,
+                 "sm_time_share": sm_shares[top], "sm_time_shares": sm_shares,
+                 "dominance": ("largest SM-time share: traced class time x SM-active fraction of the class (" + str(sm_src) + ")") if sm_frac
+                              else "largest share of the traced (serial) step",
+                 "sm_time_step_us": tot_sm / reps * 1e3,
                  "whole_path_tflops": GFLOP_PER_VIDEO * 1e9 * value / world / 1e12,
                  "whole_path_frac_of_bf16_sustained": GFLOP_PER_VIDEO * 1e9 * value / world / 1e12 / peaks["tf_sustained"]})
 

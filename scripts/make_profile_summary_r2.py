@@ -106,7 +106,10 @@ out += ["", f"Sum of the {per_step} launches under ncu: {tot:.0f} us, SM-time {t
         "20-step bench of this build: see the bench line in DESIGN.md section 8)."]
 open(f"profiles/{tag}_launch_summary.md", "w").write("\n".join(out) + "\n")
 json.dump({"source": f"profiles/{tag}_launches_b16_bf16x3.csv (ncu, batch 16, bf16x3)",
-           "per_kernel": {c: {"launches": n, "dram_bytes_per_launch": by / n} for c, (n, us, by) in cagg.items()}},
+           "sm_active": "sm_active_frac = SM-time / duration of the class: sum over its launches of duration x (sm__cycles_active.avg / "
+                        "sm__cycles_elapsed.avg), over the summed duration (bench.py weights the traced class times with it)",
+           "per_kernel": {c: {"launches": n, "dram_bytes_per_launch": by / n, "sm_active_frac": round(csmw[c] / max(us, 1e-9), 4)}
+                          for c, (n, us, by) in cagg.items()}},
           open("profiles/traffic.json", "w"), indent=1)
 print("\n".join(out))
 
