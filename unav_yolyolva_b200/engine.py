@@ -99,6 +99,7 @@ class HotPathEngine:
         # key-chunked + merge above that (config 4, T = 2304); the CUDA-core kernel serves the fp32 / *_simt modes
         self.tc_attn = self.backend == GEMM_TCGEN05 and not (self.T + 1 > 256 and os.environ.get("UNAV_ATTN_LONG_SIMT") == "1")   # A/B knob
         self.attn_simt_max_t = int(os.environ.get("UNAV_ATTN_SIMT_MAX_T", "0"))      # A/B knob, see _tc_attn_for
+        self.implicit_c3 = os.environ.get("UNAV_IMPLICIT_C3", "0") == "1"            # A/B knob, see _csp
         self.stage_passes = STAGE_PASSES.get(mode, {})
         self._stage = "alignment"
         self.w: Dict[str, torch.Tensor] = {}
@@ -752,10 +753,17 @@ class HotPathEngine:
                              NB, Tl, C, heads, hc, op, passes=self.stage_passes.get(self._stage, 0))
         else:
             K.maxsig_gate(c3, View(G, g_off, Ch), w[name + ".hb"], gate, NB, Tl, C, heads, hc)
-        K.rowcopy([{"src": c3, "dst": P["c3i"][:M], "nseg": NB, "seg_len_in": Tl, "seg_len_out": Tl, "ntaps": 3,
-                    "tap_stride": Ch, "C": Ch}], op)
-        self._gemm([{"A": P["c3i"][:M], "W": w[name + ".proj"], "bias": w[name + ".proj.b"], "rowmask": mask, "gate": gate,
-                     "gate_groups": heads, "gate_width": hc, "out_op": View(CAT, C + 3 * Ch, Ch)}], M, Ch, 3 * Ch)
+        if self.implicit_c3 and self.tc_attn:
+            # implicit k = 3 convolution: the GEMM reads c_3's PLAIN operand (the CAT window block 2's projection wrote) through a
+            # 4-D tensor map, tap t of a tile from rows t0 + t - 1 with TMA zero fill outside the item — no im2col operand, no copy
+            # launch; same accumulation order as the im2col GEMM (test_implicit_conv3_equals_im2col_gemm)
+            self._gemm([{"A": View(CAT, C + 2 * Ch, Ch), "conv_T": Tl, "W": w[name + ".proj"], "bias": w[name + ".proj.b"], "rowmask": mask,
+                         "gate": gate, "gate_groups": heads, "gate_width": hc, "out_op": View(CAT, C + 3 * Ch, Ch)}], M, Ch, 3 * Ch)
+        else:
+            K.rowcopy([{"src": c3, "dst": P["c3i"][:M], "nseg": NB, "seg_len_in": Tl, "seg_len_out": Tl, "ntaps": 3,
+                        "tap_stride": Ch, "C": Ch}], op)
+            self._gemm([{"A": P["c3i"][:M], "W": w[name + ".proj"], "bias": w[name + ".proj.b"], "rowmask": mask, "gate": gate,
+                         "gate_groups": heads, "gate_width": hc, "out_op": View(CAT, C + 3 * Ch, Ch)}], M, Ch, 3 * Ch)
         d = {"A": CAT, "W": w[name + ".final"], "bias": w[name + ".final.b"], "rowmask": mask, "out_f32": out_f32}
         if out_op is not None:
             d["out_op"] = out_op
