@@ -5,10 +5,10 @@ run() {  # tag, env...
   python - "$tag" <<PY
 import json,sys
 b=json.loads(open(f'gpurun_out/bench_{sys.argv[1]}.json').read().strip().splitlines()[-1])
-print(sys.argv[1], 'value', round(b['value'],1), 'long', round(b['long_window']['ms_per_step'],3), 'e2e', round(b['e2e']['value']), 'b1 sync ms', round(b['config1_batch1']['gpu_ms_per_video_sync'],3), 'traced', round(b['roofline']['traced_step_us']))
+print(sys.argv[1], 'value', round(b['value'],1), 'long', round(b['long_window']['ms_per_step'],3), 'dwconv', round(b['roofline']['per_kernel']['dwconv_ln']['us_per_step']), 'traced', round(b['roofline']['traced_step_us']))
 PY
 }
-run hack1 UNAV_ATTN_HACK_HEADS=1
-run base1 X=1
-run hack2 UNAV_ATTN_HACK_HEADS=1
-run base2 X=1
+run base X=1
+run b296 UNAV_DWCONV_BLOCKS=296
+run b148 UNAV_DWCONV_BLOCKS=148
+run b296s2 UNAV_DWCONV_BLOCKS=296 UNAV_DWCONV_STRIP=2

@@ -949,7 +949,9 @@ extern "C" int unav_dwconv_ln(const UnavDwLnGroup* groups, int ngroups, int nseg
       const int nw = 8;
       const long long strips = static_cast<long long>(nseg) * ((p.seg_len_out + strip - 1) / strip);
       long long blocks = (strips + nw - 1) / nw;
-      if (blocks > 148 * 4) blocks = 148 * 4;
+      long long cap_blocks = 148 * 4;
+      if (const char* env = getenv("UNAV_DWCONV_BLOCKS")) { const int v = atoi(env); if (v >= 1) cap_blocks = v; }
+      if (blocks > cap_blocks) blocks = cap_blocks;
       cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
       dim3 grid(static_cast<unsigned>(blocks), ngroups);
 #define UNAV_DWS_CASE(NVV, STR)                                                                         \
