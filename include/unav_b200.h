@@ -101,6 +101,13 @@ int unav_gemm_variant_counts(long long* out, int n);
  * allocated), S ready, P written, O ready, epilogue done, all warps done}.  NULL switches it off (the default). */
 int unav_set_phase_trace(long long* device_buf, int capacity_ctas);
 
+/* Programmatic dependent launch for the launches that follow (every kernel of the library waits with griddepcontrol.wait
+ * before it touches global memory): 1 = on, 0 = off, -1 = follow the UNAV_PDL environment variable (default off).  The launch
+ * attribute is captured into CUDA graphs, so the engine turns it on around the capture of its batch <= 2 latency plans only:
+ * it shortens the dependent chain of a single small batch (2.83 -> 2.64 ms at batch 1) but costs throughput with several
+ * batches in flight (early-launched CTAs hold SM resources while they wait). */
+int unav_set_pdl(int mode);
+
 /* ---- GEMM: C[M,N] = epilogue(A[M,K] . W[N,K]^T) ---------------------------------------- */
 /* Epilogue, per element (m, n), in this order:
  *   v = acc + bias[n]; v *= rowmask[m]; v *= rowscale[m]; v *= gate[m*gate_groups + n/gate_width];

@@ -78,6 +78,7 @@ _PROTOS = {
     "unav_gemm_last_variant": (c_i, []),
     "unav_gemm_variant_counts": (c_i, [C.POINTER(c_ll), c_i]),
     "unav_set_phase_trace": (c_i, [c_vp, c_i]),
+    "unav_set_pdl": (c_i, [c_i]),
     "unav_gemm": (c_i, [C.POINTER(GemmGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "unav_layernorm_rows": (c_i, [C.POINTER(LnGroup), c_i, c_i, c_i, c_f, c_i, c_i, c_vp]),
     "unav_dwconv_ln": (c_i, [C.POINTER(DwLnGroup), c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp]),

@@ -19,7 +19,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<int> g_pdl_override{-1};      // unav_set_pdl: -1 = follow UNAV_PDL, 0 / 1 = forced (e.g. around a graph capture)
+
 bool pdl_enabled() {
+  const int o = g_pdl_override.load(std::memory_order_relaxed);
+  if (o >= 0) return o == 1;
   static int v = -1;
   if (v < 0) {
     // measured on B200 (scripts/gemm_probe.py): -0.8 us per back-to-back tiny GEMM, no change on the whole forward,
@@ -55,6 +59,10 @@ extern "C" const char* unav_version(void) {
 }
 extern "C" const char* unav_last_error(void) { return unav::g_err; }
 extern "C" long long unav_launch_count(void) { return unav::g_launches.load(); }
+extern "C" int unav_set_pdl(int mode) {
+  unav::g_pdl_override.store(mode < 0 ? -1 : (mode ? 1 : 0), std::memory_order_relaxed);
+  return 0;
+}
 extern "C" int unav_set_phase_trace(long long* device_buf, int capacity_ctas) {
   unav::g_phase_buf = device_buf;
   unav::g_phase_cap = device_buf ? capacity_ctas : 0;

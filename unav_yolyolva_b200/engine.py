@@ -33,6 +33,7 @@ from typing import Dict, List, Optional
 
 import torch
 
+from . import _cabi
 from . import kernels as K
 from .kernels import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, BF16, BF16X2, F16, F16X2, F32, GEMM_SIMT, GEMM_TCGEN05, View
 
@@ -811,8 +812,19 @@ class HotPathEngine:
                         cur.synchronize()
                         n0 = K.launch_count()
                         g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g):
-                            self._launch_all(P)
+                        # latency plans (batch <= 2, synchronous path): programmatic dependent launch captured into the graph
+                        # — the next kernel's prologue overlaps the previous kernel's tail (2.83 -> 2.64 ms at batch 1); not
+                        # for the streamed plans, where early-launched CTAs take SM resources from the other batches
+                        lib = _cabi.load(self.op)
+                        pdl = B <= 2 and os.environ.get("UNAV_PDL") is None
+                        if pdl:
+                            lib.unav_set_pdl(1)
+                        try:
+                            with torch.cuda.graph(g):
+                                self._launch_all(P)
+                        finally:
+                            if pdl:
+                                lib.unav_set_pdl(-1)
                         P["launches_per_step"] = K.launch_count() - n0
                         P["graph"] = g
                     P["graph"].replay()
