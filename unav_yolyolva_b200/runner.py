@@ -278,9 +278,18 @@ def split_benchmark(model, n_videos: int, batch_size: int, device, rank: int, wo
     import time
     import zlib
 
+    import os
+
     from . import synth
     dev = torch.device(device)
     net = model.module if hasattr(model, "module") else model
+    # Host threads of this rank: the pass is host bound once the ranks share the box's cores, and a torch
+    # intra-op pool per rank (OpenMP workers that spin after every parallel region) only adds to it — the packing copies and
+    # the launch path are one thread each.  UNAV_SPLIT_THREADS overrides; single-process runs keep their setting.
+    nt = int(os.environ.get("UNAV_SPLIT_THREADS", "1" if world > 1 else "0"))
+    prev_threads = torch.get_num_threads()
+    if nt > 0:
+        torch.set_num_threads(nt)
     mine = shard_indices(n_videos, rank, world)
     items = [synth.make_items(1, i)[0] for i in mine]          # this rank's shard of the synthetic dataset, in host memory
     cache = dict(zip(mine, items))
@@ -314,4 +323,7 @@ def split_benchmark(model, n_videos: int, batch_size: int, device, rank: int, wo
                      "staging allocation / NCCL warm-up excluded"}
     if ms_per_step is not None:
         out["ideal_pass_s_at_device_rate"] = (len(mine) / batch_size) * ms_per_step / 1e3
+    out["host_threads"] = torch.get_num_threads()
+    if nt > 0:
+        torch.set_num_threads(prev_threads)
     return out
