@@ -121,7 +121,7 @@ def evaluate(args):
             ok &= okm
         lines += ["", f"Per-tIoU gate (every row within 0.1): {'PASSED' if okm else 'FAILED'}; north_star gate (mAP@[0.5:0.9] within "
                   f"0.1): {'PASSED' if ok5 else 'FAILED'}.", ""]
-    out = os.path.join(ROOT, "profiles", "r01_map_parity.md")
+    out = os.path.join(ROOT, "profiles", os.environ.get("UNAV_MAP_PARITY_OUT", "r01_map_parity.md"))
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
     return 0 if ok else 1
