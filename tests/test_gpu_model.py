@@ -58,6 +58,40 @@ def test_logits_offsets_vs_oracle(model, oracle, mode):
     assert torch.equal(plan["m_heads"].cpu().view(B, 441).bool(), oracle["masks"])
 
 
+def test_valid_lengths_at_tile_boundaries_vs_oracle(model):
+    """Valid lengths that put the first padded position exactly on a 128-query tile boundary (127 frames = 128 Alignment
+    tokens with the CLS token, 128 frames, 96 = a stride-2 level boundary): the reference masks convolution OUTPUTS only
+    (blocks.py:36-61), so a k = 3 convolution at the last valid position reads what was computed at the first padded one.
+    Skipping 'masked' work is only exact where a mask is applied before the next consumer; the Alignment attention is not
+    such a place (a version that zero-filled its all-padded query tiles passed every other test and lost 0.08 mAP points)."""
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    sd = synth.trained_like_state_dict()
+    lens = [127, 128, 96, 129]
+    b = synth.make_batch(len(lens), 224, first_index=900)
+    for i, L in enumerate(lens):
+        g = torch.Generator().manual_seed(77 + i)
+        b["visual"][i].zero_(); b["audio"][i].zero_(); b["mask"][i].zero_()
+        b["visual"][i, :, :L] = 0.3 * torch.randn(2048, L, generator=g).abs()
+        b["audio"][i, :, :L] = 0.5 * torch.randn(128, L, generator=g).abs()
+        b["mask"][i, 0, :L] = True
+        b["duration"][i] = (L * 8 + 24) / 25.0
+    with torch.no_grad():
+        logits, offsets, masks = R.forward_logits(sd, b["visual"], b["audio"], b["mask"])
+    ref_l, ref_o = torch.cat(logits, 1), torch.cat(offsets, 1)
+    for mode in ("bf16x3", "fp32"):
+        model.precision = mode
+        model.use_cuda_graph = False
+        plan = model.run_hot_path(b)
+        torch.cuda.synchronize()
+        lg = plan["logits"].cpu().view(len(lens), 441, 100)
+        of = plan["offsets"].cpu().view(len(lens), 441, 100, 2)
+        for i in range(len(lens)):                      # per video, so that one boundary case cannot hide behind the others
+            e1, e2 = _rel(lg[i], ref_l[i]), _rel(of[i], ref_o[i])
+            print(f"[{mode}] L = {lens[i]}: logits rel err {e1:.3e}, offsets rel err {e2:.3e}")
+            assert e1 <= TOL[mode][0] and e2 <= TOL[mode][1], (mode, lens[i], e1, e2)
+    model.precision = "bf16x3"
+
+
 def test_detections_bit_exact_given_same_logits(model, oracle):
     """Stage-level gate: decode + soft-NMS + seconds on the device vs the oracle fed the SAME (device-produced)
     logits/offsets: identical labels, identical score and segment bits."""

@@ -522,7 +522,9 @@ class HotPathEngine:
                 if self.tc_attn:
                     oop = P["QKVop"][g * hm:(g + 1) * hm]
                     groups.append({"q": View(oop, 0, C), "k": View(oop, C, C), "vt": P["VTa"][g * B * C:(g + 1) * B * C],
-                                   "kmask": P["m_cls"], "qmask": P["m_cls"],
+                                   "kmask": P["m_cls"],      # no qmask here: nothing masks these rows before the embedding
+                                   # convolution reads its first padded neighbour (blocks.py:36-61 masks the OUTPUT only), so the
+                                   # padded query rows must hold what the reference computes, not zeros
                                    "q32": View(own, 0, C), "xk": View(oth, C, C), "xv": View(oth, 2 * C, C), "x_first": 1,
                                    "out": P["AOa"][g * hm:(g + 1) * hm]})
                 else:
