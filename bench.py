@@ -284,7 +284,11 @@ def main():
     with torch.cuda.stream(pl["nms_stream"]):
         _w = runner.pack_detections(pl["out_segs"], pl["out_scores"], pl["out_labels"]).clone()
     barrier()
-    runner.gather_detections(_w, torch.arange(B, device=dev) + rank * B, world * B)
+    # NCCL warm-up with the SHAPE of the timed all-gather (Kst steps of detections): a first collective of a new size can set up
+    # buffers / pick another protocol (seen on 2 GPUs: 8 - 10 ms for the timed gather after a one-step warm-up, 0.8 ms otherwise)
+    _wf = _w.repeat(Kst, 1, 1)
+    for _ in range(2):
+        runner.gather_detections(_wf, torch.arange(Kst * B, device=dev) + rank * Kst * B, Kst * world * B)
     launches_per_step = pl.get("launches_per_step", launches_per_step)
     barrier()
     sampler = ClockSampler(local_rank)
