@@ -66,7 +66,7 @@ def test_valid_lengths_at_tile_boundaries_vs_oracle(model):
     such a place (a version that zero-filled its all-padded query tiles passed every other test and lost 0.08 mAP points)."""
     torch.set_num_threads(min(16, os.cpu_count() or 1))
     sd = synth.trained_like_state_dict()
-    lens = [127, 128, 96, 129]
+    lens = [127, 128, 96, 129, 224, 3, 8, 64, 112, 193]          # + full length, very short, and level / chunk boundaries
     b = synth.make_batch(len(lens), 224, first_index=900)
     for i, L in enumerate(lens):
         g = torch.Generator().manual_seed(77 + i)
